@@ -1,0 +1,154 @@
+/*
+ * treedist_cuda.h -- C ABI of libtreedist_cuda.so, the B200-native engine for treeCl's all-pairs inter-tree
+ * distance matrix (Robinson-Foulds, weighted RF, branch-length Euclidean, BHV geodesic).
+ *
+ * What this boundary replaces in the reference (/root/reference, treeCl 0.1.41).  The reference has no C ABI
+ * for this path; its native seam is the Cython module `tree_distance` (PyPI, un-vendored), reached per PAIR:
+ *     PhyloTree(bytes newick, bool rooted)                       treeCl/tree.py:830-845
+ *     getRobinsonFouldsDistance / getWeightedRobinsonFouldsDistance /
+ *     getEuclideanDistance / getGeodesicDistance (t1, t2, normalise) -> float
+ *                                                                treeCl/treedist.py:7-8,70,111-118
+ * driven by the per-pair task + JobHandler loop                  treeCl/tasks.py:41-75,648-678,
+ *                                                                treeCl/parutils.py:113-254,
+ *                                                                treeCl/collection.py:421-456.
+ * This library is bound at the level of the WHOLE matrix instead: trees are encoded once (td_encode_newick
+ * replaces N*(N-1) PhyloTree constructions), and one call fills the scipy-condensed vector that
+ * collection.py:456 hands to squareform()/DistanceMatrix.from_array.
+ *
+ * Conventions: every function returns a td_status (0 = ok); td_last_error() gives a thread-local message.
+ * All pointers are plain host or device pointers; no torch / C++ types cross this boundary.  There is NO CPU
+ * fallback: compute entry points return TD_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef TREEDIST_CUDA_H
+#define TREEDIST_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct td_treeset td_treeset;
+
+typedef enum {
+    TD_RF = 0,   /* getRobinsonFouldsDistance         (treeCl/treedist.py:113) */
+    TD_WRF = 1,  /* getWeightedRobinsonFouldsDistance (treeCl/treedist.py:114) */
+    TD_EUC = 2,  /* getEuclideanDistance              (treeCl/treedist.py:111) */
+    TD_GEO = 3   /* getGeodesicDistance               (treeCl/treedist.py:112) */
+} td_metric;
+
+#define TD_MASK(metric) (1u << (metric))
+
+typedef enum {
+    TD_OK = 0,
+    TD_ERR_PARSE = 1,          /* malformed Newick           -> Python ValueError, as tree_distance raises */
+    TD_ERR_MIXED_ROOTING = 2,  /* rooted vs unrooted pair    -> undefined in the reference; refused here  */
+    TD_ERR_ARG = 3,
+    TD_ERR_NOMEM = 4,
+    TD_ERR_CUDA = 5,
+    TD_ERR_NO_DEVICE = 6,      /* no usable GPU: there is deliberately no CPU fallback                      */
+    TD_ERR_UNSUPPORTED = 7,    /* e.g. geodesic on trees with more internal edges than the kernel supports  */
+    TD_ERR_NOT_UPLOADED = 8
+} td_status;
+
+typedef struct {
+    int64_t n_trees;
+    int32_t n_taxa;          /* size of the shared (sorted) taxon index = union of all leaf labels           */
+    int32_t words;           /* W = ceil(n_taxa / 64) 64-bit words per split mask                            */
+    int32_t max_splits;      /* max internal edges of any tree                                               */
+    int32_t max_shared;      /* max per-tree count of splits that also occur in some other tree              */
+    int32_t uniform;         /* 1: all trees share one leaf set and one rootedness -> fast kernels           */
+    int32_t rooted;          /* valid when uniform                                                           */
+    int64_t dict_size;       /* D: distinct splits over the whole set (uniform sets only, else 0)            */
+    int64_t dict_shared;     /* distinct splits held by >= 2 trees                                           */
+    int64_t total_splits;
+    int32_t device;          /* device the set is resident on, -1 if not uploaded                            */
+    int32_t reserved;
+} td_info;
+
+/* ---- host side: split encoder ------------------------------------------------------------------------ */
+
+/* Parse n_trees Newick strings and encode every tree's bipartitions as canonical taxon bitmasks + fp64 branch
+ * lengths over a shared taxon index (replaces PhyloTree(newick, rooted), treeCl/tree.py:830-845; rooted <=> the
+ * root has exactly two children, treeCl/tree.py:858-862).  n_threads <= 0: use all host cores. */
+int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, td_treeset **out);
+
+void td_treeset_free(td_treeset *ts);
+int td_treeset_info(const td_treeset *ts, td_info *info);
+
+/* Introspection (tests, INTEGRATION.md examples).  `what`: see TD_GET_*.  Copies at most cap_bytes, returns the
+ * full size through *need_bytes. */
+enum {
+    TD_GET_LABELS = 0,       /* '\n'-joined sorted taxon labels (char)                                       */
+    TD_GET_NSPLITS = 1,      /* int32[n_trees]                                                              */
+    TD_GET_MASKS = 2,        /* uint64[n_trees][max_splits][W], rows sorted by split id, zero padded         */
+    TD_GET_LENGTHS = 3,      /* double[n_trees][max_splits]                                                 */
+    TD_GET_LEAFLEN = 4,      /* double[n_trees][n_taxa]                                                     */
+    TD_GET_IDS = 5,          /* uint32[n_trees][max_splits] dictionary ids (uniform sets), 0xFFFFFFFF padded */
+    TD_GET_LEAFMASK = 6,     /* uint64[n_trees][W]                                                          */
+    TD_GET_ROOTED = 7        /* int32[n_trees]                                                              */
+};
+int td_treeset_get(const td_treeset *ts, int what, void *dst, int64_t cap_bytes, int64_t *need_bytes);
+
+/* Host-side helpers that mirror treeCl.Tree for this path (no GPU needed):
+ *   td_newick_labels : '\n'-joined sorted leaf labels + rootedness   (Tree.labels / Tree.rooted, tree.py:792-796,858-862)
+ *   td_newick_prune  : Tree.prune_to_subset(subset).newick            (tree.py:989-1001; merged edge lengths are summed) */
+int td_newick_labels(const char *newick, char *dst, int64_t cap_bytes, int64_t *need_bytes, int *rooted);
+int td_newick_prune(const char *newick, const char *const *keep, int64_t n_keep, char *dst, int64_t cap_bytes,
+                    int64_t *need_bytes);
+
+/* ---- device side --------------------------------------------------------------------------------------- */
+
+int td_device_count(int *count);
+
+/* Make the encoded set resident in the HBM of `device` (SoA: taxon-major leaf lengths, per-tree sorted split
+ * ids + lengths, split masks, per-tree aggregates).  `stream` is a cudaStream_t (NULL = legacy default). */
+int td_upload(td_treeset *ts, int device, void *stream);
+
+/* Number of condensed entries belonging to rows [row_begin, row_end) of the upper triangle. */
+int64_t td_condensed_offset(int64_t n_trees, int64_t row);
+
+/* Kernels only.  For every metric bit set in metric_mask (TD_MASK(TD_RF) | ...), fill
+ *     d_out[metric][p - td_condensed_offset(N,row_begin)]   for all pairs p=(i,j), row_begin <= i < row_end, i < j,
+ * in scipy-condensed order (itertools.combinations order, treeCl/tasks.py:651-653).  d_out[m] are DEVICE pointers
+ * (double; entries for metrics not requested are ignored).  Asynchronous on `stream`.  Multi-GPU: every rank
+ * uploads the same set and calls this with its own row range; no collective is involved.
+ * Pairs whose leaf sets differ follow treeCl/treedist.py:63-68: fewer than min_overlap common leaves ->
+ * overlap_fail_value, else both trees are restricted to the intersection first. */
+int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap,
+                       double overlap_fail_value, int64_t row_begin, int64_t row_end, void *const d_out[4],
+                       void *stream);
+
+/* Same, end to end with HOST output buffers: uploads the set if needed, runs the kernels, and streams the
+ * condensed result(s) into out[metric] (host pointers, pinned or pageable).  Synchronous. */
+int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                int64_t row_begin, int64_t row_end, double *const out[4], int device);
+
+/* Rectangular variant (treeCl/bootstrap.py:174-218): all |A| x |B| distances, row-major
+ * out[a * nB + b].  Both sets must have been encoded TOGETHER (one td_encode_newick call) - `split` is the index
+ * of the first tree of B inside `ts`. */
+int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4],
+                            void *stream);
+
+/* Exact RF through the int8 tcgen05 split-incidence contraction C = X * X^T (uniform sets whose shared-split
+ * dictionary is small enough); RF = S_i + S_j - 2 C_ij.  d_out: uint16 or double condensed, device pointer. */
+int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out,
+                           int out_is_u16, void *stream);
+
+/* Counters of the last geodesic launch on this set (mean GTP iterations etc.), for DESIGN.md / bench.py. */
+typedef struct {
+    uint64_t pairs, maxflow_solves, ratios, augmentations, launches;
+} td_geo_stats;
+int td_geo_get_stats(td_treeset *ts, td_geo_stats *out);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t td_launch_count(void);
+
+const char *td_last_error(void);
+const char *td_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREEDIST_CUDA_H */

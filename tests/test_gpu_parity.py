@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (through the C ABI / the treeCl-shaped Python API) against the CPU oracle and the
+reference's golden vectors.  Tolerances: RF bit-exact; wRF / Euclidean / geodesic <= 1e-9 relative (fp64; the order
+of summation differs from the oracle's), as BASELINE.json's north_star states."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy.spatial.distance import squareform
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def assert_close(got, want, rtol=RTOL, atol=1e-12):
+    got, want = np.asarray(got), np.asarray(want)
+    err = np.abs(got - want)
+    bad = err > rtol * np.abs(want) + atol
+    assert not bad.any(), 'max rel err {:.3e} at {}'.format((err / np.maximum(np.abs(want), 1e-300)).max(), np.argmax(err))
+
+
+@pytest.fixture(scope='module')
+def td():
+    import treecl_b200
+    from treecl_b200 import _lib
+    assert _lib.device_count() > 0, 'these tests need a GPU; the product has no CPU fallback'
+    return treecl_b200
+
+
+# ---- the reference's own tests, ported (reference tests/test.py:234-294) -------------------------------------------
+class TestTreeDistanceGoldens:
+    @pytest.fixture(autouse=True)
+    def setup(self, td, fixture_trees):
+        self.td = td
+        self.c = td.Collection(trees_dir=os.path.join(GOLDEN, 'trees'), show_progress=False)
+        self.tree1 = td.Tree(self.c[0].tree)
+        self.tree2 = td.Tree(self.c[1].tree)
+
+    @pytest.mark.parametrize('metric', ['geo', 'euc', 'wrf', 'rf'])
+    @pytest.mark.parametrize('norm', [False, True])
+    def test_scalar(self, golden_scalars, metric, norm):
+        fn = getattr(self.td.treedist, metric + 'dist')
+        want = golden_scalars[metric + ('_norm' if norm else '')]
+        got = fn(self.tree1, self.tree2, norm)
+        if metric == 'rf':
+            assert got == want
+        else:
+            assert got == pytest.approx(want, rel=RTOL)
+
+    def test_intertree(self):
+        dm = self.c.get_inter_tree_distances('rf', show_progress=False)
+        assert dm.values[0, 1] == self.td.treedist.rfdist(self.tree1, self.tree2, False)
+        assert dm.get_names() == self.c.names and dm.values.shape == (15, 15)
+        assert (dm.values == dm.values.T).all() and (np.diag(dm.values) == 0).all()
+
+
+class TestGeodesicMatrixGolden:
+    """reference tests/test.py:320-326 and ParallelTests :437-467 (every jobhandler gives the same checksum)."""
+
+    def test_matrix(self, td, cache_trees, golden_scalars):
+        names, trees = cache_trees
+        c = td.Collection(records=[td.Record(n, ml_tree=t) for n, t in zip(names, trees)])
+        handlers = [None, td.parutils.SequentialJobHandler(), td.parutils.ProcesspoolJobHandler(2),
+                    td.parutils.ThreadpoolJobHandler(2)]
+        first = None
+        for h in handlers:
+            for bs in (1, 5):
+                kw = dict(show_progress=False, batchsize=bs)
+                if h is not None:
+                    kw['jobhandler'] = h
+                dm = c.get_inter_tree_distances('geo', **kw)
+                assert dm.df.values.sum() == pytest.approx(golden_scalars['geo_matrix_checksum'], abs=5e-8)
+                if first is None:
+                    first = dm.values.copy()
+                assert np.array_equal(first, dm.values)
+        want = pd.read_csv(os.path.join(GOLDEN, 'geo_dm.csv'), index_col=0).values
+        iu = np.triu_indices(15, 1)
+        assert_close(first[iu], want[iu])
+
+    def test_matrix_functions_return_ndarray(self, td, cache_trees, oracle_mod):
+        names, trees = cache_trees
+        objs = [td.Tree(t) for t in trees]
+        for metric in ('rf', 'wrf', 'euc', 'geo'):
+            sq = getattr(td.treedist, metric + 'dist_matrix')(objs, False, show_progress=False)
+            assert isinstance(sq, np.ndarray) and sq.shape == (15, 15)
+            want = squareform(oracle_mod.matrix(trees, metric))
+            if metric == 'rf':
+                assert np.array_equal(sq, want)
+            else:
+                assert_close(sq, want)
+
+
+# ---- randomised parity against the oracle ---------------------------------------------------------------------------
+CASES = [
+    # (n_trees, n_taxa, kind)
+    (2, 4, 'uniform'), (3, 5, 'uniform'), (65, 8, 'uniform'), (200, 20, 'uniform'), (130, 50, 'uniform'),
+    (97, 64, 'uniform'), (70, 65, 'uniform'), (66, 100, 'uniform'), (40, 200, 'uniform'),
+    (150, 30, 'structured'), (100, 100, 'structured'),
+]
+
+
+def make(kind, n_trees, n_taxa, seed):
+    from treecl_b200 import synth
+    if kind == 'uniform':
+        return synth.uniform_trees(n_trees, n_taxa, seed=seed)
+    return synth.structured_trees(n_trees, n_taxa, n_classes=3, class_nni=4, lam=1.5, seed=seed)
+
+
+@pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
+@pytest.mark.parametrize('norm', [False, True])
+def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
+    from treecl_b200 import _lib
+    trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)
+    ts = _lib.TreeSet(trees)
+    got = ts.pairwise(('rf', 'wrf', 'euc'), normalise=norm)
+    for metric in ('rf', 'wrf', 'euc'):
+        want = oracle_mod.matrix(trees, metric, normalise=norm, nthreads=4)
+        if metric == 'rf':
+            assert np.array_equal(got[metric], want), metric          # bit exact (also when normalised)
+        else:
+            assert_close(got[metric], want)
+    # single-metric launches use other template instantiations: same answers, bit for bit
+    for metric in ('rf', 'wrf', 'euc'):
+        assert np.array_equal(ts.pairwise((metric,), normalise=norm)[metric], got[metric])
+
+
+@pytest.mark.parametrize('n_trees,n_taxa,kind', [(2, 4, 'uniform'), (3, 5, 'uniform'), (120, 10, 'uniform'),
+                                                 (150, 20, 'uniform'), (200, 30, 'uniform'), (60, 35, 'uniform'),
+                                                 (50, 50, 'uniform'), (30, 67, 'uniform'),
+                                                 (150, 30, 'structured'), (60, 60, 'structured')])
+@pytest.mark.parametrize('norm', [False, True])
+def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
+    from treecl_b200 import _lib
+    trees = make(kind, n_trees, n_taxa, seed=300 + n_taxa)
+    ts = _lib.TreeSet(trees)
+    got = ts.pairwise(('geo',), normalise=norm)['geo']
+    want = oracle_mod.matrix(trees, 'geo', normalise=norm, nthreads=8)
+    assert_close(got, want)
+    st = ts.geo_stats()
+    assert st['pairs'] == n_trees * (n_trees - 1) // 2 and st['ratios'] >= 0
+
+
+def test_polytomies_and_rooted_trees(td, oracle_mod):
+    """UNPINNED by the reference (no golden): extended common-edge rule and clade (rooted) mode, oracle vs CUDA."""
+    from treecl_b200 import _lib
+    poly = ['(A:1,B:1,(C:1,D:1,E:1):2,F:1,G:0.5);', '((A:1,B:1):1,(C:1,D:1):1,E:1,F:1,G:0.25);',
+            '((A:1,C:1):1,(B:2,D:1):0.7,(E:1,F:1):0.3,G:1);', '(A:1,B:1,C:1,D:1,E:1,F:1,G:1);',
+            '(((A:1,B:1):1,C:2):1,D:1,(E:1,(F:0.1,G:1):0.0):1);']
+    rooted = ['((A:1,B:2):0.5,((C:1,D:1):0.25,E:3):0.75);', '(((A:1,C:2):0.5,B:1):0.3,(D:1,E:1):0.4);',
+              '((A:1,(B:1,(C:1,D:1):0.5):0.5):1,E:2);', '((A:1,B:1):0.1,(C:1,(D:1,E:1):2):0.2);']
+    for trees in (poly, rooted):
+        ts = _lib.TreeSet(trees)
+        got = ts.pairwise(('rf', 'wrf', 'euc', 'geo'))
+        for metric in ('rf', 'wrf', 'euc', 'geo'):
+            want = oracle_mod.matrix(trees, metric)
+            if metric == 'rf':
+                assert np.array_equal(got[metric], want)
+            else:
+                assert_close(got[metric], want)
+
+
+def test_identical_trees_give_exact_zero(td):
+    from treecl_b200 import _lib, synth
+    trees = synth.uniform_trees(5, 40, seed=9)
+    ts = _lib.TreeSet([trees[0], trees[1], trees[0], trees[1], trees[0]])
+    got = ts.pairwise(('rf', 'wrf', 'euc', 'geo'))
+    sq = {m: squareform(v) for m, v in got.items()}
+    for m in sq:
+        assert sq[m][0, 2] == 0.0 and sq[m][1, 3] == 0.0 and sq[m][2, 4] == 0.0 and sq[m][0, 1] > 0
+
+
+def test_row_sharding_is_byte_identical(td):
+    """Multi-GPU path: any partition of the rows reproduces the one-shot matrix bit for bit."""
+    from treecl_b200 import _lib, engine, synth
+    trees = synth.uniform_trees(333, 24, seed=21)
+    ts = _lib.TreeSet(trees)
+    full = ts.pairwise(('rf', 'wrf', 'euc', 'geo'), normalise=True)
+    n = len(trees)
+    for parts in (2, 3, 8):
+        for m in full:
+            pieces = [ts.pairwise((m,), normalise=True, row_begin=a, row_end=b)[m]
+                      for a, b in engine.balanced_row_ranges(n, parts)]
+            assert np.array_equal(np.concatenate(pieces), full[m])
+    # odd, non tile-aligned ranges
+    a = ts.pairwise(('euc',), normalise=True, row_begin=5, row_end=131)['euc']
+    p0, p1 = _lib.condensed_offset(n, 5), _lib.condensed_offset(n, 131)
+    assert np.array_equal(a, full['euc'][p0:p1])
+    out = engine.pairwise_condensed(ts, ('rf', 'geo'), normalise=True, devices=[0] * 3)
+    assert np.array_equal(out['rf'], full['rf']) and np.array_equal(out['geo'], full['geo'])
+
+
+def test_rectangular_variant(td):
+    """query x reference distances (treeCl/bootstrap.py:174-218) = a block of the square matrix."""
+    import torch
+    from treecl_b200 import _lib, synth
+    trees = synth.uniform_trees(150, 30, seed=33)
+    split = 70
+    ts = _lib.TreeSet(trees).upload(0)
+    sq = {m: squareform(v) for m, v in ts.pairwise(('rf', 'wrf', 'euc', 'geo')).items()}
+    outs = {m: torch.zeros(split * (150 - split), dtype=torch.float64, device='cuda:0') for m in sq}
+    ts.pairwise_rect_device(split, tuple(sq), {m: outs[m].data_ptr() for m in sq},
+                            stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for m in sq:
+        assert np.array_equal(outs[m].cpu().numpy().reshape(split, 150 - split), sq[m][:split, split:]), m
+
+
+def test_properties_at_bench_size(td):
+    """BASELINE config 2 (5,000 x 50): too big for the oracle, so check size-independent properties."""
+    from treecl_b200 import _lib, synth
+    n, taxa = 5000, 50
+    trees = synth.uniform_trees(n, taxa, seed=0xCA55E77E + 1)
+    ts = _lib.TreeSet(trees)
+    got = ts.pairwise(('rf', 'euc', 'wrf'))
+    rf, euc, wrf = got['rf'], got['euc'], got['wrf']
+    assert rf.size == n * (n - 1) // 2
+    assert (rf == np.round(rf)).all() and (rf % 2 == 0).all() and rf.min() >= 0 and rf.max() <= 2 * (taxa - 3)
+    assert (euc > 0).all() and (wrf >= euc).all()                   # L1 >= L2
+    # order reversal: d(i,j) computed with the trees listed backwards is the same matrix transposed
+    ts_rev = _lib.TreeSet(trees[::-1])
+    rev = ts_rev.pairwise(('rf', 'euc'))
+    idx = np.random.default_rng(0).integers(0, n, size=(2000, 2))
+    idx = idx[idx[:, 0] < idx[:, 1]]
+    p = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
+    fwd = p(idx[:, 0], idx[:, 1]); bwd = p(n - 1 - idx[:, 1], n - 1 - idx[:, 0])
+    assert np.array_equal(rf[fwd], rev['rf'][bwd])
+    assert_close(euc[fwd], rev['euc'][bwd], rtol=1e-12)
+    # a 300-tree sub-block agrees with the matrix of the sub-collection (dictionary ids differ between the two runs)
+    sub = _lib.TreeSet(trees[:300]).pairwise(('rf', 'euc'))
+    blk = np.concatenate([np.arange(p(i, i + 1), p(i, 299) + 1) for i in range(299)])
+    assert np.array_equal(sub['rf'], rf[blk])
+    assert_close(sub['euc'], euc[blk], rtol=1e-12)

@@ -1,0 +1,175 @@
+"""CPU tests of the product's host side: C-ABI surface, split encoder, Tree / Collection mirrors, sharding plan.
+No compute entry point is called here (there is no CPU fallback to call)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_every_declared_symbol_is_exported(lib_built):
+    header = open(os.path.join(ROOT, 'include', 'treedist_cuda.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(td_[a-z0-9_]+)\s*\(', header))
+    assert {'td_encode_newick', 'td_upload', 'td_pairwise', 'td_pairwise_device', 'td_last_error'} <= declared
+    lib = ctypes.CDLL(lib_built)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_compute_fails_loudly_without_gpu(lib_built, cache_trees):
+    from treecl_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip('a GPU is present')
+    ts = _lib.TreeSet(cache_trees[1])
+    with pytest.raises(_lib.NoDeviceError):
+        ts.upload(0)
+    with pytest.raises(_lib.TreedistError):
+        ts.pairwise(('rf',))
+
+
+def test_encoder_matches_oracle_encoding(lib_built, oracle_mod, cache_trees):
+    from treecl_b200 import _lib
+    names, trees = cache_trees
+    ts = _lib.TreeSet(trees)
+    inf = ts.info
+    assert (inf.n_trees, inf.n_taxa, inf.words, inf.uniform, inf.rooted) == (15, 10, 1, 1, 0)
+    assert ts.get(_lib.TD_GET_LABELS, None) == sorted('Sp%d' % i for i in range(1, 11))
+    ns = ts.get(_lib.TD_GET_NSPLITS, np.int32)
+    lens = ts.get(_lib.TD_GET_LENGTHS, np.float64).reshape(15, -1)
+    leaf = ts.get(_lib.TD_GET_LEAFLEN, np.float64).reshape(15, -1)
+    for i, t in enumerate(trees):
+        s = oracle_mod.encode_summary(t)
+        assert (s['n_leaves'], s['n_splits'], s['rooted']) == (10, ns[i], False)
+        assert lens[i, :ns[i]].sum() == pytest.approx(s['sum_internal'], rel=1e-14)
+        assert leaf[i].sum() == pytest.approx(s['sum_leaf'], rel=1e-14)
+
+
+def _host_distances(ts, i, j):
+    """rf / wrf / euc recomputed in numpy from the product's encoding (ids, lengths, leaf lengths)."""
+    from treecl_b200 import _lib
+    n = ts.n_trees
+    ns = ts.get(_lib.TD_GET_NSPLITS, np.int32)
+    ids = ts.get(_lib.TD_GET_IDS, np.uint32).reshape(n, -1)
+    lens = ts.get(_lib.TD_GET_LENGTHS, np.float64).reshape(n, -1)
+    leaf = ts.get(_lib.TD_GET_LEAFLEN, np.float64).reshape(n, -1)
+    di = dict(zip(ids[i][:ns[i]].tolist(), lens[i])); dj = dict(zip(ids[j][:ns[j]].tolist(), lens[j]))
+    keys = set(di) | set(dj)
+    rf = sum(1 for k in keys if (k in di) != (k in dj))
+    wrf = sum(abs(di.get(k, 0) - dj.get(k, 0)) for k in keys) + np.abs(leaf[i] - leaf[j]).sum()
+    euc = np.sqrt(sum((di.get(k, 0) - dj.get(k, 0)) ** 2 for k in keys) + ((leaf[i] - leaf[j]) ** 2).sum())
+    return rf, wrf, euc
+
+
+@pytest.mark.parametrize('n_taxa', [5, 20, 64, 65, 130])
+def test_dictionary_ids_reproduce_oracle_distances(lib_built, oracle_mod, n_taxa):
+    from treecl_b200 import _lib, synth
+    trees = synth.uniform_trees(10, n_taxa, seed=11) + synth.structured_trees(10, n_taxa, n_classes=2, seed=5)
+    ts = _lib.TreeSet(trees, n_threads=3)
+    assert ts.info.words == (n_taxa + 63) // 64 and ts.info.uniform == 1
+    ids = ts.get(_lib.TD_GET_IDS, np.uint32).reshape(20, -1)
+    ns = ts.get(_lib.TD_GET_NSPLITS, np.int32)
+    for i in range(20):
+        assert (np.diff(ids[i][:ns[i]].astype(np.int64)) > 0).all()          # sorted, unique
+    for (i, j) in [(0, 1), (3, 17), (10, 11), (12, 19), (5, 5)]:
+        rf, wrf, euc = _host_distances(ts, i, j)
+        assert rf == oracle_mod.pair(trees[i], trees[j], 'rf')
+        assert wrf == pytest.approx(oracle_mod.pair(trees[i], trees[j], 'wrf'), rel=1e-12, abs=1e-15)
+        assert euc == pytest.approx(oracle_mod.pair(trees[i], trees[j], 'euc'), rel=1e-12, abs=1e-15)
+
+
+def test_rooted_and_multifurcating_encoding(lib_built, oracle_mod):
+    from treecl_b200 import _lib
+    rooted = ['((A:1,B:2):0.5,((C:1,D:1):0.25,E:3):0.75);', '(((A:1,C:2):0.5,B:1):0.3,(D:1,E:1):0.4);']
+    ts = _lib.TreeSet(rooted)
+    assert ts.info.rooted == 1 and list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [3, 3]      # n-2 clades
+    assert _host_distances(ts, 0, 1)[0] == oracle_mod.pair(rooted[0], rooted[1], 'rf')
+    poly = ['(A:1,B:1,(C:1,D:1,E:1):2,F:1);', '((A:1,B:1):1,(C:1,D:1):1,E:1,F:1);']
+    ts = _lib.TreeSet(poly)
+    assert list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [1, 2]
+    for k, m in enumerate(('rf', 'wrf', 'euc')):
+        assert _host_distances(ts, 0, 1)[k] == pytest.approx(oracle_mod.pair(poly[0], poly[1], m), rel=1e-13)
+    # quoted labels, comments, support values, scientific notation
+    fancy = "(('t 1':1e-1,t_2:2E0)0.99:1[&c],[x]'it''s':1,(t4:1,t5:1)55:+3.5);"
+    ts = _lib.TreeSet([fancy, "((t_2:1,t4:1):1,'t 1':1,('it''s':1,t5:1):1);"])
+    assert ts.get(_lib.TD_GET_LABELS, None) == sorted(["t 1", "t_2", "it's", "t4", "t5"])
+    assert ts.get(_lib.TD_GET_LENGTHS, np.float64).reshape(2, -1)[0].sum() == pytest.approx(4.5)
+
+
+def test_non_uniform_sets_are_flagged(lib_built):
+    from treecl_b200 import _lib
+    ts = _lib.TreeSet(['((A:1,B:1):1,C:1,(D:1,E:1):1);', '((A:1,B:1):1,C:1,(D:1,F:1):1);'])
+    assert ts.info.uniform == 0 and ts.info.n_taxa == 6
+    lm = ts.get(_lib.TD_GET_LEAFMASK, np.uint64)
+    assert [bin(int(x)).count('1') for x in lm] == [5, 5]
+
+
+@pytest.mark.parametrize('bad', ['', 'A;', '((A,B),C', '(A,B))', '(A,,B);', "('A,B);", '(A:x,B:1);', '(A,A,B);'])
+def test_parse_errors_are_value_errors(lib_built, bad):
+    from treecl_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.TreeSet(['(A,B,C);', bad])
+
+
+def test_tree_mirror(lib_built, oracle_mod, fixture_trees):
+    import treecl_b200
+    t1 = treecl_b200.Tree(fixture_trees['class1_1'])
+    t2 = treecl_b200.Tree(fixture_trees['class1_2'])
+    assert len(t1) == 10 and t1.rooted is False and not (t1 ^ t2) and (t1 & t2) == t1.labels
+    keep = {'Sp1', 'Sp2', 'Sp3', 'Sp4', 'Sp5', 'Sp6', 'Sp7'}
+    p1 = t1.prune_to_subset(keep)
+    assert p1.labels == keep and t1.labels != keep
+    # the product's pruning (C++) and the oracle's (C, tree level) describe the same tree
+    a = oracle_mod.encode_summary(p1.newick); b = oracle_mod.encode_summary(oracle_mod.prune_newick(t1.newick, keep))
+    assert a['n_splits'] == b['n_splits'] == 4
+    assert a['sum_internal'] == pytest.approx(b['sum_internal'], rel=1e-15)
+    assert a['sum_leaf'] == pytest.approx(b['sum_leaf'], rel=1e-15)
+    assert oracle_mod.pair(p1.newick, oracle_mod.prune_newick(t1.newick, keep), 'euc') == pytest.approx(0.0, abs=1e-15)
+    assert treecl_b200.Tree('((A:1,B:1):1,(C:1,D:1):1);').rooted is True
+    with pytest.raises(ValueError):
+        treecl_b200.Tree('((A,B)').labels
+
+
+def test_collection_loading_and_option_check(lib_built, cache_trees):
+    import json
+    import tempfile
+    import treecl_b200
+    names, trees = cache_trees
+    c = treecl_b200.Collection(trees_dir=os.path.join(GOLDEN, 'trees'), show_progress=False)
+    assert c.names == names and len(c) == 15
+    assert c[0].tree.strip() == open(os.path.join(GOLDEN, 'trees', 'class1_1.nwk')).read().strip()
+    with tempfile.TemporaryDirectory() as d:
+        for n, t in zip(names, trees):
+            open(os.path.join(d, n + '.phy'), 'w').write(' 0 0\n')
+            json.dump({'ml_tree': t, 'nj_tree': None}, open(os.path.join(d, n + '.json'), 'w'))
+        c2 = treecl_b200.Collection(input_dir=d, param_dir=d, file_format='phylip', show_progress=False)
+        assert c2.names == names and c2.trees == trees
+    with pytest.raises(treecl_b200.OptionError):
+        c.get_inter_tree_distances('nope', show_progress=False)
+    with pytest.raises(AttributeError):
+        treecl_b200.Collection(records=[treecl_b200.Record('x')]).trees
+
+
+def test_balanced_row_ranges_cover_the_triangle():
+    from treecl_b200 import _lib, engine
+    for n in (2, 3, 17, 200, 5000):
+        for parts in (1, 2, 3, 8):
+            r = engine.balanced_row_ranges(n, parts)
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            counts = [_lib.condensed_offset(n, b) - _lib.condensed_offset(n, a) for a, b in r]
+            assert sum(counts) == n * (n - 1) // 2
+            if n >= 200:
+                assert max(counts) - min(counts) <= 2 * n
+
+
+def test_synthetic_sets_are_deterministic(lib_built):
+    from treecl_b200 import _lib, synth
+    a = synth.uniform_trees(6, 20, seed=3); b = synth.uniform_trees(6, 20, seed=3)
+    assert a == b and a != synth.uniform_trees(6, 20, seed=4)
+    ts = _lib.TreeSet(a)
+    assert list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [17] * 6      # binary, trifurcating root: n-3
+    s = _lib.TreeSet(synth.structured_trees(64, 30, n_classes=4, lam=0.5, seed=1))
+    assert s.info.dict_size < 64 * 27 // 4            # shared structure -> small dictionary

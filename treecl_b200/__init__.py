@@ -1,0 +1,15 @@
+"""treecl_b200: B200-native engine for treeCl's all-pairs inter-tree distance matrix.
+
+Drop-in surface (same names and arguments as kgori/treeCl for this path):
+    treecl_b200.Collection(...).get_inter_tree_distances('rf'|'wrf'|'euc'|'geo', ...) -> DistanceMatrix
+    treecl_b200.treedist.{rf,wrf,euc,geo}dist / *_matrix
+    treecl_b200.Tree, treecl_b200.DistanceMatrix, treecl_b200.parutils.*JobHandler
+Everything is computed by libtreedist_cuda.so (hand-written sm_100a kernels); there is no CPU fallback.
+"""
+from . import parutils, tasks, treedist  # noqa: F401
+from .collection import Collection, Record  # noqa: F401
+from .distance_matrix import DistanceMatrix  # noqa: F401
+from .errors import OptionError  # noqa: F401
+from .tree import Tree  # noqa: F401
+
+__version__ = '0.1.0'

@@ -1,0 +1,224 @@
+"""ctypes binding of libtreedist_cuda.so (include/treedist_cuda.h).
+
+There is deliberately no fallback: if the shared library is missing or no B200 is visible, the compute entry
+points raise.  The CPU oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtreedist_cuda.so')
+
+TD_RF, TD_WRF, TD_EUC, TD_GEO = 0, 1, 2, 3
+METRIC_INDEX = {'rf': TD_RF, 'wrf': TD_WRF, 'euc': TD_EUC, 'geo': TD_GEO}
+
+TD_OK, TD_ERR_PARSE, TD_ERR_MIXED_ROOTING, TD_ERR_ARG, TD_ERR_NOMEM, TD_ERR_CUDA, TD_ERR_NO_DEVICE, \
+    TD_ERR_UNSUPPORTED, TD_ERR_NOT_UPLOADED = range(9)
+
+(TD_GET_LABELS, TD_GET_NSPLITS, TD_GET_MASKS, TD_GET_LENGTHS, TD_GET_LEAFLEN, TD_GET_IDS, TD_GET_LEAFMASK,
+ TD_GET_ROOTED) = range(8)
+
+
+class TreedistError(RuntimeError):
+    """CUDA / library failure (no CPU fallback exists)."""
+
+
+class NoDeviceError(TreedistError):
+    pass
+
+
+class td_info(ctypes.Structure):
+    _fields_ = [('n_trees', ctypes.c_int64), ('n_taxa', ctypes.c_int32), ('words', ctypes.c_int32),
+                ('max_splits', ctypes.c_int32), ('max_shared', ctypes.c_int32), ('uniform', ctypes.c_int32),
+                ('rooted', ctypes.c_int32), ('dict_size', ctypes.c_int64), ('dict_shared', ctypes.c_int64),
+                ('total_splits', ctypes.c_int64), ('device', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class td_geo_stats(ctypes.Structure):
+    _fields_ = [('pairs', ctypes.c_uint64), ('maxflow_solves', ctypes.c_uint64), ('ratios', ctypes.c_uint64),
+                ('augmentations', ctypes.c_uint64), ('launches', ctypes.c_uint64)]
+
+
+_lib = None
+_c_void_p4 = ctypes.c_void_p * 4
+
+
+def load():
+    """Load the shared library; raises if it was not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TreedistError('libtreedist_cuda.so is missing at {} - build it (make -C treecl_b200/csrc); '
+                            'there is no CPU fallback'.format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, u32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+    lib.td_last_error.restype = ctypes.c_char_p
+    lib.td_version.restype = ctypes.c_char_p
+    lib.td_launch_count.restype = ctypes.c_uint64
+    lib.td_encode_newick.argtypes = [ctypes.POINTER(ctypes.c_char_p), i64, i32, ctypes.POINTER(vp)]
+    lib.td_treeset_free.argtypes = [vp]
+    lib.td_treeset_free.restype = None
+    lib.td_treeset_info.argtypes = [vp, ctypes.POINTER(td_info)]
+    lib.td_treeset_get.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
+    lib.td_newick_labels.argtypes = [ctypes.c_char_p, ctypes.c_char_p, i64, ctypes.POINTER(i64), ctypes.POINTER(i32)]
+    lib.td_newick_prune.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), i64, ctypes.c_char_p, i64,
+                                    ctypes.POINTER(i64)]
+    lib.td_device_count.argtypes = [ctypes.POINTER(i32)]
+    lib.td_upload.argtypes = [vp, i32, vp]
+    lib.td_condensed_offset.argtypes = [i64, i64]
+    lib.td_condensed_offset.restype = i64
+    lib.td_pairwise_device.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, vp]
+    lib.td_pairwise.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, i32]
+    lib.td_pairwise_rect_device.argtypes = [vp, i64, u32, i32, _c_void_p4, vp]
+    lib.td_rf_incidence_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
+    lib.td_geo_get_stats.argtypes = [vp, ctypes.POINTER(td_geo_stats)]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc == TD_OK:
+        return
+    msg = load().td_last_error().decode(errors='replace')
+    if rc in (TD_ERR_PARSE, TD_ERR_MIXED_ROOTING, TD_ERR_ARG):
+        raise ValueError(msg)                 # tree_distance surfaces C++ exceptions as ValueError (treeCl/tree.py:842)
+    if rc == TD_ERR_NOMEM:
+        raise MemoryError(msg)
+    if rc == TD_ERR_NO_DEVICE:
+        raise NoDeviceError(msg)
+    if rc == TD_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise TreedistError(msg)
+
+
+def _b(s):
+    return s.encode() if isinstance(s, str) else s
+
+
+def condensed_offset(n, row):
+    return int(row) * int(n) - int(row) * (int(row) + 1) // 2
+
+
+class TreeSet(object):
+    """N trees encoded once: canonical split bitmasks + branch lengths over a shared taxon index.
+
+    Replaces the N*(N-1) PhyloTree(newick, rooted) constructions of the reference (treeCl/tree.py:830-845 reached
+    from treeCl/tasks.py:41-75 for every pair).
+    """
+
+    def __init__(self, newicks, n_threads=0):
+        lib = load()
+        newicks = [_b(s) for s in newicks]
+        arr = (ctypes.c_char_p * len(newicks))(*newicks)
+        handle = ctypes.c_void_p()
+        check(lib.td_encode_newick(arr, len(newicks), int(n_threads), ctypes.byref(handle)))
+        self._h = handle
+        self._lib = lib
+        self.n_trees = len(newicks)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.td_treeset_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def info(self):
+        inf = td_info()
+        check(self._lib.td_treeset_info(self._h, ctypes.byref(inf)))
+        return inf
+
+    def get(self, what, dtype):
+        need = ctypes.c_int64()
+        check(self._lib.td_treeset_get(self._h, what, None, 0, ctypes.byref(need)))
+        if what == TD_GET_LABELS:
+            buf = ctypes.create_string_buffer(max(need.value, 1))
+            check(self._lib.td_treeset_get(self._h, what, buf, need.value, None))
+            raw = buf.raw[:need.value].decode()
+            return raw.split('\n') if raw else []
+        out = np.empty(need.value // np.dtype(dtype).itemsize, dtype=dtype)
+        check(self._lib.td_treeset_get(self._h, what, out.ctypes.data, need.value, None))
+        return out
+
+    def upload(self, device=0, stream=0):
+        check(self._lib.td_upload(self._h, int(device), ctypes.c_void_p(stream)))
+        return self
+
+    def pairwise_device(self, metrics, d_out_ptrs, normalise=False, min_overlap=4, overlap_fail_value=0.0,
+                        row_begin=0, row_end=None, stream=0):
+        """Kernels only; d_out_ptrs maps metric name -> device pointer (int). Asynchronous on `stream`."""
+        mask, table = 0, [None] * 4
+        for m in metrics:
+            mask |= 1 << METRIC_INDEX[m]
+            table[METRIC_INDEX[m]] = d_out_ptrs[m]
+        if row_end is None:
+            row_end = self.n_trees
+        check(self._lib.td_pairwise_device(self._h, mask, int(bool(normalise)), int(min_overlap),
+                                           float(overlap_fail_value), int(row_begin), int(row_end),
+                                           _c_void_p4(*table), ctypes.c_void_p(stream)))
+
+    def pairwise_rect_device(self, split, metrics, d_out_ptrs, normalise=False, stream=0):
+        mask, table = 0, [None] * 4
+        for m in metrics:
+            mask |= 1 << METRIC_INDEX[m]
+            table[METRIC_INDEX[m]] = d_out_ptrs[m]
+        check(self._lib.td_pairwise_rect_device(self._h, int(split), mask, int(bool(normalise)), _c_void_p4(*table),
+                                                ctypes.c_void_p(stream)))
+
+    def pairwise(self, metrics, normalise=False, min_overlap=4, overlap_fail_value=0.0, row_begin=0, row_end=None,
+                 device=0, out=None):
+        """End to end with host buffers: returns {metric: condensed float64 ndarray} for rows [row_begin,row_end)."""
+        if row_end is None:
+            row_end = self.n_trees
+        n = self.n_trees
+        pairs = condensed_offset(n, row_end) - condensed_offset(n, row_begin)
+        mask, table, res = 0, [None] * 4, {}
+        for m in metrics:
+            mask |= 1 << METRIC_INDEX[m]
+            arr = out[m] if out is not None else np.empty(pairs, dtype=np.float64)
+            assert arr.dtype == np.float64 and arr.size >= pairs and arr.flags.c_contiguous
+            res[m] = arr
+            table[METRIC_INDEX[m]] = arr.ctypes.data
+        check(self._lib.td_pairwise(self._h, mask, int(bool(normalise)), int(min_overlap), float(overlap_fail_value),
+                                    int(row_begin), int(row_end), _c_void_p4(*table), int(device)))
+        return res
+
+    def geo_stats(self):
+        st = td_geo_stats()
+        check(self._lib.td_geo_get_stats(self._h, ctypes.byref(st)))
+        return dict(pairs=st.pairs, maxflow_solves=st.maxflow_solves, ratios=st.ratios, augmentations=st.augmentations)
+
+
+def newick_labels(newick):
+    lib = load()
+    need, rooted = ctypes.c_int64(), ctypes.c_int()
+    check(lib.td_newick_labels(_b(newick), None, 0, ctypes.byref(need), ctypes.byref(rooted)))
+    buf = ctypes.create_string_buffer(need.value + 1)
+    check(lib.td_newick_labels(_b(newick), buf, need.value + 1, None, None))
+    s = buf.value.decode()
+    return (s.split('\n') if s else []), bool(rooted.value)
+
+
+def newick_prune(newick, keep):
+    lib = load()
+    keep = [_b(k) for k in keep]
+    arr = (ctypes.c_char_p * len(keep))(*keep)
+    need = ctypes.c_int64()
+    check(lib.td_newick_prune(_b(newick), arr, len(keep), None, 0, ctypes.byref(need)))
+    buf = ctypes.create_string_buffer(need.value + 1)
+    check(lib.td_newick_prune(_b(newick), arr, len(keep), buf, need.value + 1, None))
+    return buf.value.decode()
+
+
+def device_count():
+    c = ctypes.c_int()
+    load().td_device_count(ctypes.byref(c))
+    return c.value
+
+
+def launch_count():
+    return int(load().td_launch_count())

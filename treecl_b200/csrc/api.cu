@@ -1,0 +1,413 @@
+// api.cu -- extern "C" entry points of libtreedist_cuda.so (see include/treedist_cuda.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "td_internal.h"
+
+namespace td {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_counter_add(uint64_t n) { return g_launches.fetch_add(n) + n; }
+
+constexpr int kCounters = 64;
+
+struct DeviceSet {
+    int device = -1, sm_count = 148;
+    int64_t N = 0, Npad = 0;
+    int n_taxa = 0, n_k = 0, W = 1, stride = 1, sh_stride = 2;
+    double *leafT = nullptr, *leaflen = nullptr;
+    SplitRec *shared = nullptr;
+    int32_t *nsplits = nullptr;
+    double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr;
+    uint32_t *ids = nullptr;
+    double *lens = nullptr;
+    uint64_t *masks = nullptr;
+    unsigned long long *work_counter = nullptr, *stats = nullptr;   // work_counter: ring of kCounters, one per launch in flight
+    std::atomic<uint32_t> next_counter{0};
+    int *error_flag = nullptr;
+    size_t max_smem_optin = 0;
+    td_geo_stats geo_stats{};
+    std::vector<void *> allocs;
+};
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? TD_ERR_NO_DEVICE : TD_ERR_CUDA; \
+        }                                                                                                \
+    } while (0)
+
+template <class T>
+static int dev_alloc(DeviceSet *d, T **ptr, size_t count)
+{
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    d->allocs.push_back(p); *ptr = reinterpret_cast<T *>(p);
+    return TD_OK;
+}
+
+static void free_device(DeviceSet *d)
+{
+    if (!d) return;
+    int cur = -1; cudaGetDevice(&cur);
+    if (d->device >= 0) cudaSetDevice(d->device);
+    for (void *p : d->allocs) cudaFree(p);
+    if (cur >= 0) cudaSetDevice(cur);
+    delete d;
+}
+
+static int64_t condensed_offset(int64_t N, int64_t row) { return row * N - row * (row + 1) / 2; }
+
+static int upload(td_treeset *ts, int device, cudaStream_t st)
+{
+    HostSet &h = ts->host;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) { set_error("no CUDA device available (%s); libtreedist_cuda has no CPU fallback", cudaGetErrorString(ce)); return TD_ERR_NO_DEVICE; }
+    if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return TD_ERR_ARG; }
+    std::lock_guard<std::mutex> guard(ts->mu);
+    if ((int)ts->devs.size() <= device) ts->devs.resize(device + 1, nullptr);
+    if (ts->devs[device]) return TD_OK;                 // already resident on this GPU
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceSet *d = new DeviceSet();
+    struct Guard { DeviceSet *d; bool keep = false; ~Guard() { if (!keep) free_device(d); } } own{d};
+    d->device = device;
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    d->sm_count = prop.multiProcessorCount; d->max_smem_optin = prop.sharedMemPerBlockOptin;
+    d->N = h.N; d->Npad = (h.N + kTile - 1) / kTile * kTile;
+    d->n_taxa = h.n_taxa; d->W = h.W; d->stride = std::max(h.max_splits, 1); d->sh_stride = h.sh_stride;
+    const int kc = pairwise_kc();
+    d->n_k = (h.n_taxa + kc - 1) / kc * kc;
+    const size_t N = h.N, Npad = d->Npad;
+    int rc;
+    if ((rc = dev_alloc(d, &d->leafT, (size_t)d->n_k * Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->leaflen, N * std::max(h.n_taxa, 1)))) return rc;
+    if ((rc = dev_alloc(d, &d->shared, Npad * d->sh_stride))) return rc;
+    if ((rc = dev_alloc(d, &d->nsplits, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->sum_len, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->norm, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->single_l1, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->single_l2, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->ids, N * d->stride))) return rc;
+    if ((rc = dev_alloc(d, &d->lens, N * d->stride))) return rc;
+    if ((rc = dev_alloc(d, &d->masks, N * d->stride * d->W))) return rc;
+    if ((rc = dev_alloc(d, &d->work_counter, kCounters))) return rc;
+    if ((rc = dev_alloc(d, &d->stats, 4))) return rc;
+    if ((rc = dev_alloc(d, &d->error_flag, 1))) return rc;
+
+    CUDA_TRY(cudaMemsetAsync(d->leafT, 0, (size_t)d->n_k * Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->nsplits, 0, Npad * sizeof(int32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d->sum_len, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->norm, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->single_l1, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->single_l2, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->stats, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(d->error_flag, 0, sizeof(int), st));
+    // sentinel rows for the padded trees: id = 0xFFFFFFFF (the length of a sentinel is never read)
+    CUDA_TRY(cudaMemsetAsync(d->shared, 0xFF, Npad * d->sh_stride * sizeof(SplitRec), st));
+
+    CUDA_TRY(cudaMemcpyAsync(d->leaflen, h.leaflen.data(), N * h.n_taxa * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->shared, h.shared.data(), N * d->sh_stride * sizeof(SplitRec), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->nsplits, h.n_splits.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->sum_len, h.sum_len.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->norm, h.norm.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->single_l1, h.single_l1.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->single_l2, h.single_l2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (h.n_taxa > 0) {
+        CUDA_TRY(launch_transpose_leaf(d->leaflen, d->leafT, h.N, h.n_taxa, d->Npad, st));
+        launch_counter_add(1);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    own.keep = true;
+    ts->devs[device] = d;
+    return TD_OK;
+}
+
+static DeviceSet *resident(td_treeset *ts, int device)
+{
+    std::lock_guard<std::mutex> guard(ts->mu);
+    return (device >= 0 && device < (int)ts->devs.size()) ? ts->devs[device] : nullptr;
+}
+
+// the GPU a set of output pointers lives on (they must all be device memory of one GPU)
+static int device_of(void *const d_out[4], uint32_t mask, int *device)
+{
+    *device = -1;
+    for (int m = 0; m < 4; m++) {
+        if (!(mask >> m & 1u)) continue;
+        if (!d_out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+        cudaPointerAttributes attr;
+        CUDA_TRY(cudaPointerGetAttributes(&attr, d_out[m]));
+        if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { set_error("output pointer for metric %d is not device memory", m); return TD_ERR_ARG; }
+        if (*device >= 0 && attr.device != *device) { set_error("output pointers live on different GPUs"); return TD_ERR_ARG; }
+        *device = attr.device;
+    }
+    return TD_OK;
+}
+
+static int check_ready(td_treeset *ts, int device, DeviceSet **d)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    *d = resident(ts, device);
+    if (!*d) { set_error("treeset is not resident on device %d: call td_upload first", device); return TD_ERR_NOT_UPLOADED; }
+    return TD_OK;
+}
+
+static int pick_tile(const DeviceSet *d, bool weighted)
+{
+    const size_t budget = std::min<size_t>(d->max_smem_optin, 200 * 1024);
+    if (pairwise_smem_bytes(64, d->sh_stride, weighted) <= budget / 2) return 64;     // two CTAs per SM
+    if (pairwise_smem_bytes(64, d->sh_stride, weighted) <= budget) return 64;
+    if (pairwise_smem_bytes(32, d->sh_stride, weighted) <= budget) return 32;
+    return 0;
+}
+
+static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, bool rect, int64_t split, int64_t row_begin,
+                        int64_t row_end, void *const d_out[4], cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    if (!h.uniform) { set_error("trees with differing leaf sets / rootedness need the restrict-then-join path, which this build does not have yet"); return TD_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(d->device));
+    const uint32_t m3 = mask & 7u;
+    if (m3) {
+        const bool weighted = (m3 & 6u) != 0;
+        const int tile = pick_tile(d, weighted);
+        if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
+        PairParams p{};
+        p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits;
+        p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
+        p.N = d->N; p.n_k = d->n_k; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
+        p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
+        for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+        int64_t tile_cols;
+        if (rect) { p.col_offset = split; p.n_cols = d->N - split; p.col_end = d->N; p.p_base = 0; tile_cols = (p.n_cols + tile - 1) / tile; }
+        else { p.col_offset = 0; p.n_cols = d->N; p.col_end = d->N; p.p_base = condensed_offset(d->N, row_begin); tile_cols = (d->N + tile - 1) / tile; }
+        p.tile_row0 = (int)(row_begin / tile);
+        const int64_t tile_rows = (row_end + tile - 1) / tile - p.tile_row0;
+        if (tile_rows > 0 && tile_cols > 0) {
+            CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
+            launch_counter_add(1);
+        }
+    }
+    if (mask & TD_MASK(TD_GEO)) {
+        if (!d_out[TD_GEO]) { set_error("output pointer for the geodesic metric is null"); return TD_ERR_ARG; }
+        if (h.max_splits > 64 || h.W > 2) { set_error("geodesic kernel holds at most 64 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
+        GeoParams g{};
+        g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
+        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise;
+        g.out = (double *)d_out[TD_GEO]; g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
+        if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
+        else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
+        if (g.p_end > g.p_begin) {
+            CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+            CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : 64, d->sm_count, st));
+            launch_counter_add(1);
+        }
+    }
+    return TD_OK;
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" {
+
+const char *td_last_error(void) { return last_error(); }
+const char *td_version(void) { return "treedist_cuda 0.1 (sm_100a)"; }
+uint64_t td_launch_count(void) { return g_launches.load(); }
+
+int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, td_treeset **out)
+{
+    if (!out) { set_error("null output pointer"); return TD_ERR_ARG; }
+    *out = nullptr;
+    td_treeset *ts = new (std::nothrow) td_treeset();
+    if (!ts) { set_error("out of memory"); return TD_ERR_NOMEM; }
+    int rc;
+    try { rc = encode_newick(newick, n_trees, n_threads, ts->host); }
+    catch (const std::bad_alloc &) { set_error("out of memory while encoding"); rc = TD_ERR_NOMEM; }
+    if (rc) { delete ts; return rc; }
+    *out = ts;
+    return TD_OK;
+}
+
+void td_treeset_free(td_treeset *ts)
+{
+    if (!ts) return;
+    for (DeviceSet *d : ts->devs) free_device(d);
+    delete ts;
+}
+
+int td_treeset_info(const td_treeset *ts, td_info *info)
+{
+    if (!ts || !info) { set_error("null argument"); return TD_ERR_ARG; }
+    const HostSet &h = ts->host;
+    memset(info, 0, sizeof *info);
+    info->n_trees = h.N; info->n_taxa = h.n_taxa; info->words = h.W; info->max_splits = h.max_splits; info->max_shared = h.max_shared;
+    info->uniform = h.uniform; info->rooted = h.rooted; info->dict_size = h.dict_size; info->dict_shared = h.dict_shared;
+    info->total_splits = h.total_splits; info->device = -1;
+    for (DeviceSet *d : ts->devs) if (d) { info->device = d->device; break; }
+    return TD_OK;
+}
+
+int td_treeset_get(const td_treeset *ts, int what, void *dst, int64_t cap_bytes, int64_t *need_bytes)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    const HostSet &h = ts->host;
+    const void *src = nullptr; int64_t n = 0; std::string joined;
+    switch (what) {
+        case TD_GET_LABELS: for (size_t i = 0; i < h.labels.size(); i++) { if (i) joined.push_back('\n'); joined += h.labels[i]; }
+                            src = joined.data(); n = (int64_t)joined.size(); break;
+        case TD_GET_NSPLITS: src = h.n_splits.data(); n = h.n_splits.size() * sizeof(int32_t); break;
+        case TD_GET_MASKS: src = h.masks.data(); n = h.masks.size() * sizeof(uint64_t); break;
+        case TD_GET_LENGTHS: src = h.lens.data(); n = h.lens.size() * sizeof(double); break;
+        case TD_GET_LEAFLEN: src = h.leaflen.data(); n = (int64_t)h.N * h.n_taxa * sizeof(double); break;
+        case TD_GET_IDS: src = h.ids.data(); n = h.ids.size() * sizeof(uint32_t); break;
+        case TD_GET_LEAFMASK: src = h.leafmask.data(); n = h.leafmask.size() * sizeof(uint64_t); break;
+        case TD_GET_ROOTED: src = h.tree_rooted.data(); n = h.tree_rooted.size() * sizeof(int32_t); break;
+        default: set_error("unknown TD_GET_* selector %d", what); return TD_ERR_ARG;
+    }
+    if (need_bytes) *need_bytes = n;
+    if (dst && cap_bytes > 0) memcpy(dst, src, (size_t)std::min<int64_t>(n, cap_bytes));
+    return TD_OK;
+}
+
+int td_newick_labels(const char *newick, char *dst, int64_t cap_bytes, int64_t *need_bytes, int *rooted)
+{
+    if (!newick) { set_error("null newick"); return TD_ERR_ARG; }
+    std::vector<std::string> labels; int r = 0;
+    int rc = newick_labels(newick, labels, r); if (rc) return rc;
+    std::string joined;
+    for (size_t i = 0; i < labels.size(); i++) { if (i) joined.push_back('\n'); joined += labels[i]; }
+    if (need_bytes) *need_bytes = (int64_t)joined.size() + 1;
+    if (rooted) *rooted = r;
+    if (dst && cap_bytes > 0) { size_t n = std::min<size_t>(joined.size(), (size_t)cap_bytes - 1); memcpy(dst, joined.data(), n); dst[n] = 0; }
+    return TD_OK;
+}
+
+int td_newick_prune(const char *newick, const char *const *keep, int64_t n_keep, char *dst, int64_t cap_bytes, int64_t *need_bytes)
+{
+    if (!newick || (!keep && n_keep > 0)) { set_error("null argument"); return TD_ERR_ARG; }
+    std::vector<std::string> k; for (int64_t i = 0; i < n_keep; i++) k.emplace_back(keep[i]);
+    std::string out; int rc = newick_prune(newick, k, out); if (rc) return rc;
+    if (need_bytes) *need_bytes = (int64_t)out.size() + 1;
+    if (dst && cap_bytes > 0) { size_t n = std::min<size_t>(out.size(), (size_t)cap_bytes - 1); memcpy(dst, out.data(), n); dst[n] = 0; }
+    return TD_OK;
+}
+
+int td_device_count(int *count)
+{
+    int c = 0; cudaError_t e = cudaGetDeviceCount(&c);
+    if (count) *count = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess) { set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return TD_ERR_NO_DEVICE; }
+    return TD_OK;
+}
+
+int td_upload(td_treeset *ts, int device, void *stream)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    return upload(ts, device, (cudaStream_t)stream);
+}
+
+int64_t td_condensed_offset(int64_t n_trees, int64_t row) { return condensed_offset(n_trees, row); }
+
+int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                       int64_t row_begin, int64_t row_end, void *const d_out[4], void *stream)
+{
+    (void)min_overlap; (void)overlap_fail_value;     // only reachable for non-uniform sets
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    const int64_t N = ts->host.N;
+    if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
+    if (row_begin < 0 || row_end > N || row_begin > row_end) { set_error("row range [%lld,%lld) outside [0,%lld]", (long long)row_begin, (long long)row_end, (long long)N); return TD_ERR_ARG; }
+    if (!d_out) { set_error("null output table"); return TD_ERR_ARG; }
+    int device, rc; DeviceSet *d;
+    if ((rc = device_of(d_out, metric_mask, &device))) return rc;
+    if ((rc = check_ready(ts, device, &d))) return rc;
+    return run_pairwise(ts, d, metric_mask, normalise, false, 0, row_begin, row_end, d_out, (cudaStream_t)stream);
+}
+
+int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4], void *stream)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    const int64_t N = ts->host.N;
+    if (split <= 0 || split >= N) { set_error("split %lld must be inside (0,%lld)", (long long)split, (long long)N); return TD_ERR_ARG; }
+    if (!(metric_mask & 15u) || (metric_mask & ~15u) || !d_out) { set_error("bad metric_mask / output table"); return TD_ERR_ARG; }
+    int device, rc; DeviceSet *d;
+    if ((rc = device_of(d_out, metric_mask, &device))) return rc;
+    if ((rc = check_ready(ts, device, &d))) return rc;
+    return run_pairwise(ts, d, metric_mask, normalise, true, split, 0, split, d_out, (cudaStream_t)stream);
+}
+
+int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                int64_t row_begin, int64_t row_end, double *const out[4], int device)
+{
+    if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    int rc;
+    if ((rc = upload(ts, device, 0))) return rc;        // no-op when already resident
+    DeviceSet *dset = resident(ts, device);
+    const int64_t N = ts->host.N;
+    if (row_begin < 0 || row_end > N || row_begin > row_end) { set_error("row range outside [0,N]"); return TD_ERR_ARG; }
+    const int64_t pairs = condensed_offset(N, row_end) - condensed_offset(N, row_begin);
+    if (pairs <= 0) return TD_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    void *dbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto cleanup = [&] { for (int m = 0; m < 4; m++) if (dbuf[m]) cudaFree(dbuf[m]); };
+    for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u) {
+        if (!out[m]) { cleanup(); set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+        cudaError_t e = cudaMalloc(&dbuf[m], (size_t)pairs * sizeof(double));
+        if (e != cudaSuccess) { cleanup(); set_error("cudaMalloc of %lld bytes failed: %s", (long long)pairs * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    }
+    cudaStream_t st = 0;
+    rc = td_pairwise_device(ts, metric_mask, normalise, min_overlap, overlap_fail_value, row_begin, row_end, dbuf, st);
+    if (rc) { cleanup(); return rc; }
+    for (int m = 0; m < 4; m++) if (dbuf[m]) {
+        cudaError_t e = cudaMemcpyAsync(out[m], dbuf[m], (size_t)pairs * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { cleanup(); set_error("D2H copy failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    if (metric_mask & TD_MASK(TD_GEO)) {
+        int flag = 0; cudaMemcpy(&flag, dset->error_flag, sizeof flag, cudaMemcpyDeviceToHost);
+        if (flag) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
+    }
+    return TD_OK;
+}
+
+int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16, void *stream)
+{
+    (void)normalise; (void)row_begin; (void)row_end; (void)d_out; (void)out_is_u16; (void)stream;
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    set_error("int8 tcgen05 split-incidence path is not built yet");
+    return TD_ERR_UNSUPPORTED;
+}
+
+int td_geo_get_stats(td_treeset *ts, td_geo_stats *out)
+{
+    if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    memset(out, 0, sizeof *out);
+    std::vector<DeviceSet *> devs;
+    { std::lock_guard<std::mutex> guard(ts->mu); devs = ts->devs; }
+    for (DeviceSet *d : devs) {
+        if (!d) continue;
+        unsigned long long s[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaSetDevice(d->device));
+        CUDA_TRY(cudaMemcpy(s, d->stats, sizeof s, cudaMemcpyDeviceToHost));
+        out->pairs += s[0]; out->maxflow_solves += s[1]; out->ratios += s[2]; out->augmentations += s[3];
+        CUDA_TRY(cudaMemset(d->stats, 0, sizeof s));
+    }
+    return TD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+// host_encoder.cpp -- Newick -> canonical split bitmasks + branch lengths over a shared taxon index.
+//
+// Replaces, once per TREE instead of once per PAIR, what the reference does inside every task:
+//   Tree(newick)  -> dendropy parse                       treeCl/tree.py:745-762
+//   Tree.rooted   -> root has exactly two children        treeCl/tree.py:858-862
+//   Tree.phylotree-> tree_distance.PhyloTree(newick, rooted): one bitset per internal edge + length,
+//                    one length per leaf edge             treeCl/tree.py:830-845 (arithmetic in PyPI tree_distance)
+// and builds the global split dictionary the merge / incidence kernels work on.
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+
+#include "td_internal.h"
+
+namespace td {
+
+static thread_local char g_error[512];
+void set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_error, sizeof g_error, fmt, ap); va_end(ap);
+}
+const char *last_error() { return g_error; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Newick
+// ------------------------------------------------------------------------------------------------------------
+struct FlatTree {
+    std::vector<int32_t> parent, nchild;
+    std::vector<double> len;
+    std::vector<std::string_view> label;     // leaves only; views into the input text or into `owned`
+    std::deque<std::string> owned;           // unescaped quoted labels
+    void clear() { parent.clear(); nchild.clear(); len.clear(); label.clear(); owned.clear(); }
+    int add(int p)
+    {
+        parent.push_back(p); nchild.push_back(0); len.push_back(0.0); label.emplace_back();
+        if (p >= 0) nchild[p]++;
+        return (int)parent.size() - 1;
+    }
+    int size() const { return (int)parent.size(); }
+};
+
+static inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+static inline bool is_delim(char c) { return c == '(' || c == ')' || c == ':' || c == ',' || c == ';' || c == '['; }
+
+static const char *skip_blank(const char *s, const char *e)
+{
+    for (;;) {
+        while (s < e && is_ws(*s)) s++;
+        if (s < e && *s == '[') { while (s < e && *s != ']') s++; if (s < e) s++; continue; }
+        return s;
+    }
+}
+
+// reads a (possibly quoted) label starting at s; returns the end or nullptr on an unterminated quote
+static const char *scan_label(const char *s, const char *e, FlatTree *t, std::string_view &out)
+{
+    if (s < e && *s == '\'') {
+        const char *b = ++s; bool esc = false;
+        while (true) {
+            if (s >= e) return nullptr;
+            if (*s == '\'') { if (s + 1 < e && s[1] == '\'') { esc = true; s += 2; continue; } break; }
+            s++;
+        }
+        if (!esc) out = std::string_view(b, s - b);
+        else if (t) {
+            std::string u; for (const char *p = b; p < s; p++) { u.push_back(*p); if (*p == '\'') p++; }
+            t->owned.push_back(std::move(u)); out = t->owned.back();
+        }
+        return s + 1;
+    }
+    const char *b = s;
+    while (s < e && !is_delim(*s) && !is_ws(*s)) s++;
+    out = std::string_view(b, s - b);
+    return s;
+}
+
+// Node 0 is the root; "(": the current node gets its first child; ",": next sibling; ")": back to the parent.
+static int parse_newick(const char *text, FlatTree &t)
+{
+    t.clear();
+    const char *s = text, *e = text + strlen(text);
+    int cur = t.add(-1), depth = 0; bool want_subtree = true;
+    s = skip_blank(s, e);
+    if (s >= e || *s != '(') { set_error("newick: expected '(' at start"); return TD_ERR_PARSE; }
+    while (s < e) {
+        s = skip_blank(s, e);
+        if (s >= e) break;
+        char c = *s;
+        if (want_subtree) {
+            if (c == '(') { depth++; cur = t.add(cur); s++; continue; }
+            std::string_view lab; const char *n = scan_label(s, e, &t, lab);
+            if (!n) { set_error("newick: unterminated quoted label"); return TD_ERR_PARSE; }
+            if (lab.empty()) { set_error("newick: empty leaf label near '%.16s'", s); return TD_ERR_PARSE; }
+            t.label[cur] = lab; s = n; want_subtree = false; continue;
+        }
+        if (c == ':') {
+            s = skip_blank(s + 1, e);
+            const char *b = s; if (b < e && *b == '+') b++;
+            double v = 0; auto r = std::from_chars(b, e, v);
+            if (r.ec != std::errc() || r.ptr == b) { set_error("newick: bad branch length near '%.16s'", s); return TD_ERR_PARSE; }
+            t.len[cur] = v; s = r.ptr; continue;
+        }
+        if (c == ',') {
+            if (depth == 0) { set_error("newick: ',' outside parentheses"); return TD_ERR_PARSE; }
+            cur = t.add(t.parent[cur]); s++; want_subtree = true; continue;
+        }
+        if (c == ')') {
+            if (depth == 0) { set_error("newick: unbalanced ')'"); return TD_ERR_PARSE; }
+            depth--; cur = t.parent[cur]; s++; continue;
+        }
+        if (c == ';') break;
+        // internal node label / support value: dropped (treeCl/tree.py:823-825)
+        std::string_view lab; const char *n = scan_label(s, e, nullptr, lab);
+        if (!n || n == s) { set_error("newick: unexpected '%c'", c); return TD_ERR_PARSE; }
+        s = n;
+    }
+    if (depth != 0 || cur != 0) { set_error("newick: unbalanced '('"); return TD_ERR_PARSE; }
+    int leaves = 0;
+    for (int i = 0; i < t.size(); i++) if (t.nchild[i] == 0) { if (t.label[i].empty()) { set_error("newick: unlabeled leaf"); return TD_ERR_PARSE; } leaves++; }
+    if (leaves < 2) { set_error("newick: fewer than two leaves"); return TD_ERR_PARSE; }
+    return TD_OK;
+}
+
+// effective root: skip unifurcations at the top (their stem edges carry no split)
+static int effective_root(const FlatTree &t, const std::vector<int> *first_child = nullptr)
+{
+    int r = 0;
+    while (t.nchild[r] == 1) {
+        int c = -1;
+        for (int i = r + 1; i < t.size(); i++) if (t.parent[i] == r) { c = i; break; }
+        if (c < 0 || t.nchild[c] == 0) break;
+        r = c;
+    }
+    (void)first_child;
+    return r;
+}
+
+int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted)
+{
+    FlatTree t; int rc = parse_newick(newick, t); if (rc) return rc;
+    labels.clear();
+    for (int i = 0; i < t.size(); i++) if (t.nchild[i] == 0) labels.emplace_back(t.label[i]);
+    std::sort(labels.begin(), labels.end());
+    rooted = t.nchild[effective_root(t)] == 2;
+    return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tree.prune_to_subset(subset).newick  (treeCl/tree.py:989-1001): drop the other leaves, suppress unifurcations
+// summing the merged edge lengths, keep an unrooted tree's base trifurcating.
+// ------------------------------------------------------------------------------------------------------------
+struct PNode { std::string label; double len = 0; std::vector<PNode> kids; };
+
+static bool prune_rec(const FlatTree &t, const std::vector<std::vector<int>> &ch, int v,
+                      const std::unordered_map<std::string_view, int> &keep, PNode &out)
+{
+    if (t.nchild[v] == 0) {
+        if (!keep.count(t.label[v])) return false;
+        out.label = std::string(t.label[v]); out.len = t.len[v]; return true;
+    }
+    std::vector<PNode> kids;
+    for (int c : ch[v]) { PNode k; if (prune_rec(t, ch, c, keep, k)) kids.push_back(std::move(k)); }
+    if (kids.empty()) return false;
+    if (kids.size() == 1) { out = std::move(kids[0]); out.len += t.len[v]; return true; }
+    out.kids = std::move(kids); out.len = t.len[v]; return true;
+}
+
+static void put_double(std::string &s, double v)
+{
+    char buf[40]; auto r = std::to_chars(buf, buf + sizeof buf, v); s.append(buf, r.ptr);
+}
+
+static bool needs_quote(const std::string &l)
+{
+    for (char c : l) if (is_delim(c) || is_ws(c) || c == '\'' || c == ']') return true;
+    return false;
+}
+
+static void write_rec(const PNode &n, bool is_root, std::string &s)
+{
+    if (n.kids.empty()) {
+        if (needs_quote(n.label)) { s.push_back('\''); for (char c : n.label) { s.push_back(c); if (c == '\'') s.push_back('\''); } s.push_back('\''); }
+        else s += n.label;
+    } else {
+        s.push_back('(');
+        for (size_t i = 0; i < n.kids.size(); i++) { if (i) s.push_back(','); write_rec(n.kids[i], false, s); }
+        s.push_back(')');
+    }
+    if (!is_root) { s.push_back(':'); put_double(s, n.len); }
+}
+
+int newick_prune(const char *newick, const std::vector<std::string> &keep_list, std::string &out)
+{
+    FlatTree t; int rc = parse_newick(newick, t); if (rc) return rc;
+    std::unordered_map<std::string_view, int> keep;
+    for (auto &k : keep_list) keep.emplace(std::string_view(k), 1);
+    std::vector<std::vector<int>> ch(t.size());
+    for (int i = 1; i < t.size(); i++) ch[t.parent[i]].push_back(i);
+    bool was_rooted = t.nchild[effective_root(t)] == 2;
+    PNode root;
+    if (!prune_rec(t, ch, 0, keep, root)) { set_error("prune: no leaf of the tree is in the subset"); return TD_ERR_ARG; }
+    root.len = 0;
+    // unrooted trees keep a trifurcating base: merge the two root edges (lengths summed)
+    if (!was_rooted && root.kids.size() == 2) {
+        int del = -1;
+        if (root.kids[1].kids.size() >= 2) del = 1; else if (root.kids[0].kids.size() >= 2) del = 0;
+        if (del >= 0) {
+            PNode d = std::move(root.kids[del]); root.kids.erase(root.kids.begin() + del);
+            root.kids[0].len += d.len;
+            for (auto &k : d.kids) root.kids.push_back(std::move(k));
+        }
+    }
+    out.clear(); write_rec(root, true, out); out.push_back(';');
+    return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Split encoding of one tree over the shared taxon table.
+// ------------------------------------------------------------------------------------------------------------
+struct TreeEnc {
+    int rooted = 0, n_leaves = 0;
+    std::vector<uint64_t> leafmask;          // W
+    std::vector<uint64_t> masks;             // S*W, sorted by mask, unique
+    std::vector<double> lens;                // S
+    std::vector<double> leaflen;             // n_taxa
+    double sum_len = 0, sum_sq = 0;
+};
+
+struct TaxonTable {
+    std::vector<std::string> labels;                         // sorted
+    std::unordered_map<std::string_view, int> index;         // views into `labels`
+    void build(std::vector<std::string> &&l)
+    {
+        labels = std::move(l); std::sort(labels.begin(), labels.end());
+        labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+        index.clear(); index.reserve(labels.size() * 2);
+        for (size_t i = 0; i < labels.size(); i++) index.emplace(std::string_view(labels[i]), (int)i);
+    }
+};
+
+static inline int mask_cmp(const uint64_t *a, const uint64_t *b, int W)
+{
+    for (int w = W - 1; w >= 0; w--) { if (a[w] != b[w]) return a[w] < b[w] ? -1 : 1; }
+    return 0;
+}
+static inline int mask_popc(const uint64_t *m, int W) { int c = 0; for (int w = 0; w < W; w++) c += __builtin_popcountll(m[w]); return c; }
+static inline int mask_low(const uint64_t *m, int W) { for (int w = 0; w < W; w++) if (m[w]) return 64 * w + __builtin_ctzll(m[w]); return -1; }
+
+// returns TD_OK, TD_ERR_PARSE, or -1 when a label is missing from the table (caller rebuilds the table)
+static int encode_tree(const FlatTree &t, const TaxonTable &tab, TreeEnc &e, std::vector<uint64_t> &clade,
+                       std::vector<int> &order)
+{
+    const int n_taxa = (int)tab.labels.size(), W = std::max(1, (n_taxa + 63) / 64), nn = t.size();
+    e.leafmask.assign(W, 0); e.leaflen.assign(n_taxa, 0.0); e.masks.clear(); e.lens.clear();
+    clade.assign((size_t)nn * W, 0);
+    for (int i = nn - 1; i >= 0; i--) {       // children have larger indices than their parent
+        uint64_t *m = &clade[(size_t)i * W];
+        if (t.nchild[i] == 0) {
+            auto it = tab.index.find(t.label[i]);
+            if (it == tab.index.end()) return -1;
+            int k = it->second;
+            if (e.leafmask[k >> 6] >> (k & 63) & 1) { set_error("newick: duplicate leaf label '%.*s'", (int)t.label[i].size(), t.label[i].data()); return TD_ERR_PARSE; }
+            m[k >> 6] |= 1ull << (k & 63); e.leafmask[k >> 6] |= 1ull << (k & 63);
+        }
+        if (t.parent[i] >= 0) { uint64_t *p = &clade[(size_t)t.parent[i] * W]; for (int w = 0; w < W; w++) p[w] |= m[w]; }
+    }
+    const int root = effective_root(t);
+    e.rooted = t.nchild[root] == 2;
+    e.n_leaves = mask_popc(e.leafmask.data(), W);
+    const int ref = mask_low(e.leafmask.data(), W);
+    order.clear();
+    for (int i = 1; i < nn; i++) {
+        if (i == root) continue;
+        uint64_t *m = &clade[(size_t)i * W];
+        const int c = mask_popc(m, W), cc = e.n_leaves - c;
+        if (c == 0 || cc == 0) continue;                                   // stem above the effective root
+        if (c == 1) { e.leaflen[mask_low(m, W)] += t.len[i]; continue; }   // leaf edge (or a unifurcation above one)
+        if (!e.rooted) {
+            if (cc == 1) { for (int w = 0; w < W; w++) m[w] = e.leafmask[w] & ~m[w]; e.leaflen[mask_low(m, W)] += t.len[i]; continue; }
+            if (m[ref >> 6] >> (ref & 63) & 1) for (int w = 0; w < W; w++) m[w] = e.leafmask[w] & ~m[w];
+        }
+        order.push_back(i);
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return mask_cmp(&clade[(size_t)a * W], &clade[(size_t)b * W], W) < 0; });
+    for (int i : order) {
+        const uint64_t *m = &clade[(size_t)i * W];
+        size_t S = e.lens.size();
+        if (S && mask_cmp(&e.masks[(S - 1) * W], m, W) == 0) { e.lens[S - 1] += t.len[i]; continue; }   // merged edges: lengths add
+        e.masks.insert(e.masks.end(), m, m + W); e.lens.push_back(t.len[i]);
+    }
+    e.sum_len = 0; e.sum_sq = 0;
+    for (double l : e.lens) { e.sum_len += l; e.sum_sq += l * l; }
+    for (double l : e.leaflen) { e.sum_len += l; e.sum_sq += l * l; }
+    return TD_OK;
+}
+
+static inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+static inline uint64_t mask_hash(const uint64_t *m, int W)
+{
+    uint64_t h = 0x9e3779b97f4a7c15ULL;
+    for (int w = 0; w < W; w++) h = mix64(h ^ m[w]) + 0x9e3779b97f4a7c15ULL * (w + 1);
+    return h;
+}
+
+template <class F>
+static void parallel_for(int64_t n, int n_threads, F &&fn)
+{
+    if (n_threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) fn(i, 0); return; }
+    std::atomic<int64_t> next{0};
+    const int64_t chunk = std::max<int64_t>(1, n / (n_threads * 16));
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&, t] {
+            for (;;) { int64_t b = next.fetch_add(chunk); if (b >= n) break; int64_t e = std::min(n, b + chunk); for (int64_t i = b; i < e; i++) fn(i, t); }
+        });
+    for (auto &x : th) x.join();
+}
+
+int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &hs)
+{
+    if (N < 1 || !newick) { set_error("td_encode_newick: need at least one tree"); return TD_ERR_ARG; }
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, N / 8));
+
+    std::vector<TreeEnc> enc(N);
+    TaxonTable tab;
+    std::atomic<int> status{TD_OK};
+    std::mutex err_mu; std::string err_msg;
+    auto fail = [&](int rc, int64_t i) {
+        int exp = TD_OK;
+        if (status.compare_exchange_strong(exp, rc)) { std::lock_guard<std::mutex> g(err_mu); err_msg = "tree " + std::to_string(i) + ": " + last_error(); }
+    };
+    // seed the taxon table from tree 0; trees with labels outside it force one rebuild over the union
+    {
+        std::vector<std::string> l0; int r0;
+        int rc = newick_labels(newick[0], l0, r0);
+        if (rc) { std::string m = std::string("tree 0: ") + last_error(); set_error("%s", m.c_str()); return rc; }
+        tab.build(std::move(l0));
+    }
+    std::atomic<bool> missing{false};
+    struct Scratch { FlatTree t; std::vector<uint64_t> clade; std::vector<int> order; };
+    std::vector<Scratch> scratch(n_threads);
+    auto run_pass = [&] {
+        parallel_for(N, n_threads, [&](int64_t i, int tid) {
+            if (status.load(std::memory_order_relaxed) != TD_OK) return;
+            Scratch &sc = scratch[tid];
+            int rc = parse_newick(newick[i], sc.t);
+            if (rc) { fail(rc, i); return; }
+            rc = encode_tree(sc.t, tab, enc[i], sc.clade, sc.order);
+            if (rc == -1) missing = true; else if (rc) fail(rc, i);
+        });
+    };
+    run_pass();
+    if (status == TD_OK && missing) {
+        std::vector<std::vector<std::string>> per(n_threads);
+        parallel_for(N, n_threads, [&](int64_t i, int tid) {
+            Scratch &sc = scratch[tid];
+            if (parse_newick(newick[i], sc.t)) return;
+            for (int v = 0; v < sc.t.size(); v++) if (sc.t.nchild[v] == 0 && !tab.index.count(sc.t.label[v])) per[tid].emplace_back(sc.t.label[v]);
+        });
+        std::vector<std::string> all = tab.labels;
+        for (auto &p : per) all.insert(all.end(), p.begin(), p.end());
+        tab.build(std::move(all));
+        missing = false;
+        run_pass();
+    }
+    if (status != TD_OK) { set_error("%s", err_msg.c_str()); return status; }
+
+    // ---- pack ------------------------------------------------------------------------------------------
+    const int n_taxa = (int)tab.labels.size(), W = std::max(1, (n_taxa + 63) / 64);
+    hs = HostSet();
+    hs.N = N; hs.n_taxa = n_taxa; hs.W = W; hs.labels = tab.labels;
+    hs.n_splits.resize(N); hs.n_leaves.resize(N); hs.tree_rooted.resize(N); hs.n_shared.assign(N, 0);
+    hs.leafmask.resize((size_t)N * W); hs.sum_len.resize(N); hs.norm.resize(N);
+    hs.single_l1.assign(N, 0.0); hs.single_l2.assign(N, 0.0);
+    int smax = 0; bool uniform = true; int64_t total = 0;
+    for (int64_t i = 0; i < N; i++) {
+        const TreeEnc &e = enc[i];
+        hs.n_splits[i] = (int)e.lens.size(); hs.n_leaves[i] = e.n_leaves; hs.tree_rooted[i] = e.rooted;
+        memcpy(&hs.leafmask[(size_t)i * W], e.leafmask.data(), W * 8);
+        hs.sum_len[i] = e.sum_len; hs.norm[i] = std::sqrt(e.sum_sq);
+        smax = std::max(smax, hs.n_splits[i]); total += hs.n_splits[i];
+        if (e.rooted != enc[0].rooted || memcmp(e.leafmask.data(), enc[0].leafmask.data(), W * 8)) uniform = false;
+    }
+    hs.max_splits = smax; hs.uniform = uniform; hs.rooted = enc[0].rooted; hs.total_splits = total;
+    const size_t stride = (size_t)std::max(smax, 1);
+    hs.masks.assign((size_t)N * stride * W, 0); hs.lens.assign((size_t)N * stride, 0.0);
+    hs.ids.assign((size_t)N * stride, kSentinelId);
+    hs.leaflen.resize((size_t)N * std::max(n_taxa, 1));
+    parallel_for(N, n_threads, [&](int64_t i, int) {
+        memcpy(&hs.leaflen[(size_t)i * n_taxa], enc[i].leaflen.data(), (size_t)n_taxa * 8);
+    });
+
+    // ---- global split dictionary (exact: ties on the 64-bit hash are resolved by comparing the masks) --------
+    struct Ent { uint64_t h; uint32_t tree, slot; };
+    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0);
+    if (total > 0) {
+        std::vector<int64_t> off(N + 1, 0);
+        for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
+        std::vector<Ent> ents(total);
+        parallel_for(N, n_threads, [&](int64_t i, int) {
+            for (int s = 0; s < hs.n_splits[i]; s++) ents[off[i] + s] = Ent{mask_hash(&enc[i].masks[(size_t)s * W], W), (uint32_t)i, (uint32_t)s};
+        });
+        constexpr int NB = 256;
+        std::vector<int64_t> bstart(NB + 1, 0);
+        for (auto &en : ents) bstart[(en.h >> 56) + 1]++;
+        for (int b = 0; b < NB; b++) bstart[b + 1] += bstart[b];
+        std::vector<Ent> sorted(total);
+        { std::vector<int64_t> pos(bstart.begin(), bstart.end() - 1); for (auto &en : ents) sorted[pos[en.h >> 56]++] = en; }
+        ents.clear(); ents.shrink_to_fit();
+        auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
+        std::vector<int64_t> uniq(NB + 1, 0), shared(NB, 0);
+        parallel_for(NB, n_threads, [&](int64_t b, int) {
+            auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
+            std::sort(lo, hi, [&](const Ent &x, const Ent &y) {
+                if (x.h != y.h) return x.h < y.h;
+                int c = mask_cmp(mask_of(x), mask_of(y), W);
+                if (c) return c < 0;
+                return x.tree < y.tree;
+            });
+            int64_t u = 0, sh = 0;
+            for (auto it = lo; it != hi;) {
+                auto run = it + 1;
+                while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
+                u++; if (run - it >= 2) sh++;
+                it = run;
+            }
+            uniq[b + 1] = u; shared[b] = sh;
+        });
+        for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; hs.dict_shared += shared[b]; }
+        hs.dict_size = uniq[NB];
+        parallel_for(NB, n_threads, [&](int64_t b, int) {
+            auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
+            int64_t id = uniq[b];
+            for (auto it = lo; it != hi;) {
+                auto run = it + 1;
+                while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
+                for (auto k = it; k != run; k++) { id_of[(size_t)k->tree * stride + k->slot] = (uint32_t)id; mult_of[(size_t)k->tree * stride + k->slot] = (uint32_t)(run - it); }
+                id++; it = run;
+            }
+        });
+    }
+    // ---- per-tree lists sorted by dictionary id; shared-split lists ------------------------------------------
+    std::vector<int32_t> nsh(N, 0);
+    parallel_for(N, n_threads, [&](int64_t i, int) {
+        const int S = hs.n_splits[i];
+        std::vector<int> perm(S);
+        for (int s = 0; s < S; s++) perm[s] = s;
+        std::sort(perm.begin(), perm.end(), [&](int a, int b) { return id_of[(size_t)i * stride + a] < id_of[(size_t)i * stride + b]; });
+        int sh = 0; double s1 = 0, s2 = 0;
+        for (int k = 0; k < S; k++) {
+            const int s = perm[k];
+            memcpy(&hs.masks[((size_t)i * stride + k) * W], &enc[i].masks[(size_t)s * W], W * 8);
+            hs.lens[(size_t)i * stride + k] = enc[i].lens[s];
+            hs.ids[(size_t)i * stride + k] = id_of[(size_t)i * stride + s];
+            if (mult_of[(size_t)i * stride + s] >= 2) sh++;
+            else { s1 += std::fabs(enc[i].lens[s]); s2 += enc[i].lens[s] * enc[i].lens[s]; }
+        }
+        nsh[i] = sh; hs.single_l1[i] = s1; hs.single_l2[i] = s2;
+    });
+    int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
+    hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
+    hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
+    hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
+    parallel_for(N, n_threads, [&](int64_t i, int) {
+        const int S = hs.n_splits[i]; int k = 0;
+        // mult_of is indexed by the pre-sort slot: recover through the id (ids are unique inside one tree)
+        std::vector<std::pair<uint32_t, uint32_t>> m(S);
+        for (int s = 0; s < S; s++) m[s] = {id_of[(size_t)i * stride + s], mult_of[(size_t)i * stride + s]};
+        std::sort(m.begin(), m.end());
+        for (int s = 0; s < S; s++)
+            if (m[s].second >= 2) hs.shared[(size_t)i * hs.sh_stride + k++] = SplitRec{hs.ids[(size_t)i * stride + s], 0, hs.lens[(size_t)i * stride + s]};
+    });
+    return TD_OK;
+}
+
+}  // namespace td

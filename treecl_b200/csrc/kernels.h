@@ -1,0 +1,58 @@
+// kernels.h -- launch interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "td_internal.h"
+
+namespace td {
+
+struct PairParams {
+    const double *leafT;      // [n_k][ldT] taxon-major leaf-edge lengths (zero padded)
+    int64_t ldT;
+    const SplitRec *shared;   // [Npad][sh_stride] sorted shared-split lists, sentinel padded
+    int sh_stride;
+    const int32_t *nsplits;   // [Npad]
+    const double *sum_len, *norm, *single_l1, *single_l2;   // [Npad]
+    int64_t N;                // trees
+    int n_k;                  // taxa padded to the k-chunk
+    int64_t row_begin, row_end, p_base;
+    int64_t col_offset, n_cols, col_end;   // rectangular variant: columns are trees [col_offset, col_offset + n_cols)
+    int tile_row0;
+    int normalise;
+    double *out[3];           // rf, wrf, euc (device)
+};
+
+size_t pairwise_smem_bytes(int tile, int sh_stride, bool weighted);
+int pairwise_kc();
+cudaError_t launch_pairwise(uint32_t mask, bool rect, PairParams p, int64_t tile_rows, int64_t tile_cols, int tile,
+                            cudaStream_t st);
+cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
+
+struct GeoParams {
+    const uint32_t *ids;      // [N][stride] sorted split ids, sentinel padded
+    const double *lens;       // [N][stride]
+    const uint64_t *masks;    // [N][stride][W]
+    const int32_t *nsplits;   // [N]
+    const double *leaflen;    // [N][n_taxa] tree-major
+    const double *norm;       // [N]
+    int64_t N;
+    int stride, n_taxa, W;
+    int64_t p_begin, p_end, p_base;      // condensed pair range (triangular) ...
+    int64_t rect_split, rect_cols;       // ... or rectangular: rows [0,split) x cols [split, split+cols); p = a*cols + b
+    int rect;
+    int normalise;
+    double *out;
+    unsigned long long *work_counter;    // dynamic pair scheduler
+    unsigned long long *stats;           // [4]: pairs, maxflow solves, final ratios, augmentations
+    int *error_flag;                     // set when an iteration cap was hit
+};
+
+// cap: 32 or 64 (max internal edges per tree the warp-per-pair GTP kernel holds in registers/shared memory)
+cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
+size_t geodesic_smem_bytes(int cap, int W, int warps);
+
+uint64_t launch_counter_add(uint64_t n);
+
+}  // namespace td

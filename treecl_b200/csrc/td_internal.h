@@ -1,0 +1,65 @@
+// td_internal.h -- internal structures shared by the host encoder, the C-ABI layer and the kernels.
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/treedist_cuda.h"
+
+namespace td {
+
+constexpr uint32_t kSentinelId = 0xFFFFFFFFu;
+constexpr int kTile = 64;          // trees per tile edge; N is padded to a multiple of this on the device
+
+// one entry of a per-tree sorted split list as the merge kernels see it (16 B -> one LDS.128 / LDG.128)
+struct SplitRec {
+    uint32_t id;
+    uint32_t pad;
+    double len;
+};
+static_assert(sizeof(SplitRec) == 16, "SplitRec must be 16 bytes");
+
+struct HostSet {
+    int64_t N = 0;
+    int32_t n_taxa = 0, W = 1;
+    int32_t max_splits = 0, max_shared = 0;
+    bool uniform = false;
+    int32_t rooted = 0;
+    int64_t dict_size = 0, dict_shared = 0, total_splits = 0;
+    std::vector<std::string> labels;           // sorted taxon table
+
+    // per tree (N entries)
+    std::vector<int32_t> n_splits, n_leaves, tree_rooted, n_shared;
+    std::vector<uint64_t> leafmask;            // [N][W]
+    std::vector<double> sum_len, norm;         // all edges incl. leaves: sum l, sqrt(sum l^2)
+    std::vector<double> single_l1, single_l2;  // sums over splits held by this tree only: sum |l|, sum l^2
+
+    // full lists, rows sorted by split id (uniform sets) or by mask (otherwise); stride max_splits
+    std::vector<uint64_t> masks;               // [N][max_splits][W]
+    std::vector<double> lens;                  // [N][max_splits]
+    std::vector<uint32_t> ids;                 // [N][max_splits], kSentinelId padded (uniform sets only)
+    std::vector<double> leaflen;               // [N][n_taxa]
+
+    // shared-split lists (splits that occur in >= 2 trees), sentinel padded, stride sh_stride
+    int32_t sh_stride = 0;
+    std::vector<SplitRec> shared;              // [N][sh_stride]
+};
+
+struct DeviceSet;   // defined in api.cu
+
+void set_error(const char *fmt, ...);
+const char *last_error();
+
+// host_encoder.cpp
+int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, HostSet &hs);
+int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted);
+int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
+
+}  // namespace td
+
+struct td_treeset {
+    td::HostSet host;
+    std::mutex mu;                             // guards `devs`
+    std::vector<td::DeviceSet *> devs;         // indexed by CUDA device ordinal; the set is replicated per GPU
+};
