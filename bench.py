@@ -208,10 +208,12 @@ def run_ours(args):
         t.close()
         return h2d
 
-    e2e_step()
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
+    h2d_bytes = 0
+    if e2e_steps:
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
         h2d_bytes = e2e_step()
     barrier()
@@ -248,7 +250,7 @@ def run_ours(args):
                    'best_cpu_value': best,
                    'best_cpu_sample': 'same oracle, trees encoded once, {} threads, first {} pairs'.format(threads, take_b)}
         line = {
-            'metric': 'tree-pairs/sec (rf+euc matrices)', 'value': value, 'unit': 'pairs/s', 'n_gpus': n_gpus,
+            'metric': 'tree-pairs/sec ({} matrices)'.format('+'.join(METRICS)), 'value': value, 'unit': 'pairs/s', 'n_gpus': n_gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': '{} uniform random {}-taxon trees, rf+euc condensed matrices, one fused launch per step'.format(nt, nx),
@@ -257,7 +259,7 @@ def run_ours(args):
                        'dict_size': int(info.dict_size), 'dict_shared': int(info.dict_shared), 'max_shared': int(info.max_shared)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
-                         'algorithmic_bytes_per_launch': alg, 'kernel': 'pairwise_kernel<rf|euc>'},
+                         'algorithmic_bytes_per_launch': alg, 'kernel': 'pairwise_kernel<{}>'.format('|'.join(METRICS))},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(my_pairs * 8 * len(METRICS)),
@@ -286,7 +288,12 @@ def main():
     ap.add_argument('--trees', type=int, default=None, help='override the tree count (testing)')
     ap.add_argument('--taxa', type=int, default=None, help='override the taxon count (testing)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--metrics', default=None, help='comma list overriding rf,euc (experiments)')
+    ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
+    global METRICS
+    if args.metrics:
+        METRICS = tuple(args.metrics.split(','))
     if args.impl == 'reference':
         return run_reference(args)
     return run_ours(args)

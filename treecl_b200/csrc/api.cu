@@ -191,8 +191,14 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
         for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
         int64_t tile_cols;
-        if (rect) { p.col_offset = split; p.n_cols = d->N - split; p.col_end = d->N; p.p_base = 0; tile_cols = (p.n_cols + tile - 1) / tile; }
-        else { p.col_offset = 0; p.n_cols = d->N; p.col_end = d->N; p.p_base = condensed_offset(d->N, row_begin); tile_cols = (d->N + tile - 1) / tile; }
+        if (rect) {
+            // column tiles start at the tile boundary at or below `split` so that every B tile is tile aligned
+            // (16-byte cp.async sources, no read past the padded set); columns below `split` are masked on store
+            p.col_offset = split; p.n_cols = d->N - split; p.col_end = d->N; p.p_base = 0;
+            p.col_tile0 = (int)(split / tile);
+            tile_cols = (d->N + tile - 1) / tile - p.col_tile0;
+        }
+        else { p.col_offset = 0; p.n_cols = d->N; p.col_end = d->N; p.col_tile0 = 0; p.p_base = condensed_offset(d->N, row_begin); tile_cols = (d->N + tile - 1) / tile; }
         p.tile_row0 = (int)(row_begin / tile);
         const int64_t tile_rows = (row_end + tile - 1) / tile - p.tile_row0;
         if (tile_rows > 0 && tile_cols > 0) {

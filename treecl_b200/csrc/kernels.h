@@ -19,7 +19,7 @@ struct PairParams {
     int n_k;                  // taxa padded to the k-chunk
     int64_t row_begin, row_end, p_base;
     int64_t col_offset, n_cols, col_end;   // rectangular variant: columns are trees [col_offset, col_offset + n_cols)
-    int tile_row0;
+    int tile_row0, col_tile0;
     int normalise;
     double *out[3];           // rf, wrf, euc (device)
 };

@@ -44,7 +44,7 @@ pairwise_kernel(const PairParams p)
     const int tile_c = blockIdx.x, tile_r = blockIdx.y + p.tile_row0;
     if (!RECT && tile_c < tile_r) return;
     const int64_t i0 = (int64_t)tile_r * TILE;
-    const int64_t j0 = (RECT ? p.col_offset : 0) + (int64_t)tile_c * TILE;
+    const int64_t j0 = (int64_t)(tile_c + p.col_tile0) * TILE;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SplitRec *recA = reinterpret_cast<SplitRec *>(smem_raw);
@@ -171,7 +171,7 @@ pairwise_kernel(const PairParams p)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const int64_t j = j0 + 4 * tx + c;
-            if (j >= p.col_end || (!RECT && j <= i)) continue;
+            if (j >= p.col_end || (RECT ? j < p.col_offset : j <= i)) continue;
             const int64_t idx = row_off + j;
             if constexpr (kRF) {
                 const int den = si + sj[c];
