@@ -108,9 +108,20 @@ def make(kind, n_trees, n_taxa, seed):
     return synth.structured_trees(n_trees, n_taxa, n_classes=3, class_nni=4, lam=1.5, seed=seed)
 
 
+@pytest.fixture
+def pair_kernel(request, monkeypatch):
+    """Force one of the two rf/wrf/euc kernels (hash join for sparse sharing, merge-join for dense) or let the library choose."""
+    if request.param != 'auto':
+        monkeypatch.setenv('TREEDIST_PAIR_KERNEL', request.param)
+    else:
+        monkeypatch.delenv('TREEDIST_PAIR_KERNEL', raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
 @pytest.mark.parametrize('norm', [False, True])
-def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join'], indirect=True)
+def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_kernel):
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)
     ts = _lib.TreeSet(trees)
@@ -161,7 +172,8 @@ def test_polytomies_and_rooted_trees(td, oracle_mod):
                 assert_close(got[metric], want)
 
 
-def test_identical_trees_give_exact_zero(td):
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+def test_identical_trees_give_exact_zero(td, pair_kernel):
     from treecl_b200 import _lib, synth
     trees = synth.uniform_trees(5, 40, seed=9)
     ts = _lib.TreeSet([trees[0], trees[1], trees[0], trees[1], trees[0]])
@@ -171,7 +183,8 @@ def test_identical_trees_give_exact_zero(td):
         assert sq[m][0, 2] == 0.0 and sq[m][1, 3] == 0.0 and sq[m][2, 4] == 0.0 and sq[m][0, 1] > 0
 
 
-def test_row_sharding_is_byte_identical(td):
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+def test_row_sharding_is_byte_identical(td, pair_kernel):
     """Multi-GPU path: any partition of the rows reproduces the one-shot matrix bit for bit."""
     from treecl_b200 import _lib, engine, synth
     trees = synth.uniform_trees(333, 24, seed=21)
@@ -191,7 +204,8 @@ def test_row_sharding_is_byte_identical(td):
     assert np.array_equal(out['rf'], full['rf']) and np.array_equal(out['geo'], full['geo'])
 
 
-def test_rectangular_variant(td):
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+def test_rectangular_variant(td, pair_kernel):
     """query x reference distances (treeCl/bootstrap.py:174-218) = a block of the square matrix."""
     import torch
     from treecl_b200 import _lib, synth

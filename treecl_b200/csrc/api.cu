@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,8 +24,8 @@ struct DeviceSet {
     int n_taxa = 0, n_k = 0, W = 1, stride = 1, sh_stride = 2;
     double *leafT = nullptr, *leaflen = nullptr;
     SplitRec *shared = nullptr;
-    int32_t *nsplits = nullptr;
-    double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr;
+    int32_t *nsplits = nullptr, *nshared = nullptr;
+    double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr, *q1 = nullptr, *q2 = nullptr;
     uint32_t *ids = nullptr;
     double *lens = nullptr;
     uint64_t *masks = nullptr;
@@ -92,10 +93,13 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     if ((rc = dev_alloc(d, &d->leaflen, N * std::max(h.n_taxa, 1)))) return rc;
     if ((rc = dev_alloc(d, &d->shared, Npad * d->sh_stride))) return rc;
     if ((rc = dev_alloc(d, &d->nsplits, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->nshared, Npad))) return rc;
     if ((rc = dev_alloc(d, &d->sum_len, Npad))) return rc;
     if ((rc = dev_alloc(d, &d->norm, Npad))) return rc;
     if ((rc = dev_alloc(d, &d->single_l1, Npad))) return rc;
     if ((rc = dev_alloc(d, &d->single_l2, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->q1, Npad))) return rc;
+    if ((rc = dev_alloc(d, &d->q2, Npad))) return rc;
     if ((rc = dev_alloc(d, &d->ids, N * d->stride))) return rc;
     if ((rc = dev_alloc(d, &d->lens, N * d->stride))) return rc;
     if ((rc = dev_alloc(d, &d->masks, N * d->stride * d->W))) return rc;
@@ -105,10 +109,13 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
 
     CUDA_TRY(cudaMemsetAsync(d->leafT, 0, (size_t)d->n_k * Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->nsplits, 0, Npad * sizeof(int32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d->nshared, 0, Npad * sizeof(int32_t), st));
     CUDA_TRY(cudaMemsetAsync(d->sum_len, 0, Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->norm, 0, Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->single_l1, 0, Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->single_l2, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->q1, 0, Npad * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(d->q2, 0, Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->stats, 0, 4 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(d->error_flag, 0, sizeof(int), st));
     // sentinel rows for the padded trees: id = 0xFFFFFFFF (the length of a sentinel is never read)
@@ -117,10 +124,13 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     CUDA_TRY(cudaMemcpyAsync(d->leaflen, h.leaflen.data(), N * h.n_taxa * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->shared, h.shared.data(), N * d->sh_stride * sizeof(SplitRec), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->nsplits, h.n_splits.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->nshared, h.n_shared.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->sum_len, h.sum_len.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->norm, h.norm.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->single_l1, h.single_l1.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->single_l2, h.single_l2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->q1, h.q1.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->q2, h.q2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -182,11 +192,19 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
     const uint32_t m3 = mask & 7u;
     if (m3) {
         const bool weighted = (m3 & 6u) != 0;
-        const int tile = pick_tile(d, weighted);
+        // kernel choice: sparse sharing -> tile hash join (work ~ entries + matches); dense sharing -> merge-join
+        const int slots = pairjoin_table_slots(h.max_shared);
+        const char *force = getenv("TREEDIST_PAIR_KERNEL");
+        const bool join_fits = h.max_shared <= 255 && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
+        bool use_join = join_fits && h.mean_common <= 6.0;
+        if (force && !strcmp(force, "merge")) use_join = false;
+        if (force && !strcmp(force, "join") && join_fits) use_join = true;
+        const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
-        p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits;
+        p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits; p.nshared = d->nshared;
         p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
+        p.q1 = d->q1; p.q2 = d->q2; p.table_slots = slots;
         p.N = d->N; p.n_k = d->n_k; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
         p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
         for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
@@ -202,7 +220,8 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         p.tile_row0 = (int)(row_begin / tile);
         const int64_t tile_rows = (row_end + tile - 1) / tile - p.tile_row0;
         if (tile_rows > 0 && tile_cols > 0) {
-            CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
+            if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, st));
+            else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
             launch_counter_add(1);
         }
     }

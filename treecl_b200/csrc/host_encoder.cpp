@@ -386,6 +386,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     hs.n_splits.resize(N); hs.n_leaves.resize(N); hs.tree_rooted.resize(N); hs.n_shared.assign(N, 0);
     hs.leafmask.resize((size_t)N * W); hs.sum_len.resize(N); hs.norm.resize(N);
     hs.single_l1.assign(N, 0.0); hs.single_l2.assign(N, 0.0);
+    hs.q1.assign(N, 0.0); hs.q2.assign(N, 0.0);
     int smax = 0; bool uniform = true; int64_t total = 0;
     for (int64_t i = 0; i < N; i++) {
         const TreeEnc &e = enc[i];
@@ -423,6 +424,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         ents.clear(); ents.shrink_to_fit();
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
         std::vector<int64_t> uniq(NB + 1, 0), shared(NB, 0);
+        std::vector<double> copairs(NB, 0.0);
         parallel_for(NB, n_threads, [&](int64_t b, int) {
             auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
             std::sort(lo, hi, [&](const Ent &x, const Ent &y) {
@@ -431,16 +433,19 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
                 if (c) return c < 0;
                 return x.tree < y.tree;
             });
-            int64_t u = 0, sh = 0;
+            int64_t u = 0, sh = 0; double cp = 0;
             for (auto it = lo; it != hi;) {
                 auto run = it + 1;
                 while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
                 u++; if (run - it >= 2) sh++;
+                cp += 0.5 * (double)(run - it) * (double)(run - it - 1);
                 it = run;
             }
-            uniq[b + 1] = u; shared[b] = sh;
+            uniq[b + 1] = u; shared[b] = sh; copairs[b] = cp;
         });
-        for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; hs.dict_shared += shared[b]; }
+        double cp_total = 0;
+        for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; hs.dict_shared += shared[b]; cp_total += copairs[b]; }
+        hs.mean_common = N > 1 ? cp_total / (0.5 * (double)N * (double)(N - 1)) : 0.0;
         hs.dict_size = uniq[NB];
         parallel_for(NB, n_threads, [&](int64_t b, int) {
             auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
@@ -460,16 +465,17 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         std::vector<int> perm(S);
         for (int s = 0; s < S; s++) perm[s] = s;
         std::sort(perm.begin(), perm.end(), [&](int a, int b) { return id_of[(size_t)i * stride + a] < id_of[(size_t)i * stride + b]; });
-        int sh = 0; double s1 = 0, s2 = 0;
+        int sh = 0; double s1 = 0, s2 = 0, t1 = 0, t2 = 0;
         for (int k = 0; k < S; k++) {
             const int s = perm[k];
             memcpy(&hs.masks[((size_t)i * stride + k) * W], &enc[i].masks[(size_t)s * W], W * 8);
             hs.lens[(size_t)i * stride + k] = enc[i].lens[s];
             hs.ids[(size_t)i * stride + k] = id_of[(size_t)i * stride + s];
+            t1 += std::fabs(enc[i].lens[s]); t2 += enc[i].lens[s] * enc[i].lens[s];
             if (mult_of[(size_t)i * stride + s] >= 2) sh++;
             else { s1 += std::fabs(enc[i].lens[s]); s2 += enc[i].lens[s] * enc[i].lens[s]; }
         }
-        nsh[i] = sh; hs.single_l1[i] = s1; hs.single_l2[i] = s2;
+        nsh[i] = sh; hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2;
     });
     int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
     hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;

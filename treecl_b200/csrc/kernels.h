@@ -13,8 +13,11 @@ struct PairParams {
     int64_t ldT;
     const SplitRec *shared;   // [Npad][sh_stride] sorted shared-split lists, sentinel padded
     int sh_stride;
-    const int32_t *nsplits;   // [Npad]
+    const int32_t *nsplits;   // [Npad] internal edges per tree
+    const int32_t *nshared;   // [Npad] entries of the tree's shared-split list
     const double *sum_len, *norm, *single_l1, *single_l2;   // [Npad]
+    const double *q1, *q2;    // [Npad] totals over ALL internal edges: sum |l|, sum l^2 (hash-join kernel)
+    int table_slots, tiles_x; // hash-join kernel: power-of-two table size; tile columns of the grid
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
     int64_t row_begin, row_end, p_base;
@@ -28,6 +31,9 @@ size_t pairwise_smem_bytes(int tile, int sh_stride, bool weighted);
 int pairwise_kc();
 cudaError_t launch_pairwise(uint32_t mask, bool rect, PairParams p, int64_t tile_rows, int64_t tile_cols, int tile,
                             cudaStream_t st);
+int pairjoin_table_slots(int max_shared);
+size_t pairjoin_smem_bytes(uint32_t mask, int table_slots);
+cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, cudaStream_t st);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
 
 struct GeoParams {

@@ -1,0 +1,364 @@
+// kernels_pairjoin.cu -- RF / weighted RF / Euclidean for SPARSELY sharing tree sets: tile-level hash join (sm_100a).
+//
+// Same contract as kernels_pairwise.cu (getRobinsonFoulds / getWeightedRobinsonFoulds / getEuclideanDistance of
+// treeCl/treedist.py:111-114 for a whole tile of pairs), different way of finding the common splits.
+//
+// The merge kernel walks both trees' shared-split lists for every pair: pairs x (s_i + s_j) dependent shared-memory
+// loads, although in a set of independent random trees a pair has ~0.2 splits in common.  Here the work is
+// proportional to the tile's ENTRIES plus its MATCHES.  A tile is 64 row trees x 32 column trees, 256 threads:
+//   build : the column trees' entries (id -> column, length) go into an open-addressing hash table in shared memory
+//   probe : ONE thread per row tree walks that tree's entries in list order and looks each id up; every hit is a
+//           (row, column) match that it adds to per-cell slots in shared memory which only it writes:
+//           cnt += 1,  E2 += -2*la*lb,  E1 += |la-lb| - |la| - |lb|.  No atomics, fixed summation order: results are
+//           bit-reproducible and do not depend on how rows are sharded over GPUs.
+//   leaf  : dense fp64 "distance GEMM" over the taxon-major leaf lengths (4x2 register tile per thread, k-chunks
+//           double buffered with cp.async), accumulators initialised with E
+//   out   : rf  = S_i + S_j - 2 cnt
+//           euc = sqrt((Q2_i + Q2_j) + E2 + leaf2),  wrf = (Q1_i + Q1_j) + E1 + leaf1     (Q = per-tree totals)
+// (Q + E) subtracts, so a pair whose |E| exceeds kRisk * (Q_i + Q_j) - nearly identical trees - is recomputed exactly
+// by a merge over the two lists (all terms non-negative): identical trees still give exactly 0.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.h"
+
+namespace td {
+
+namespace {
+
+constexpr int KC = 8;
+constexpr int TR = 64, TC = 32;       // tile: rows x columns
+constexpr int NT = 256;
+constexpr double kRisk = 0.9;
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t mask) { return (id * 2654435761u >> 7) & mask; }
+
+// exact, purely additive recomputation for one pair: internal edges by a merge of the two shared-split lists, leaf
+// edges by a strided walk over the taxon-major leaf matrix (global memory / L2; only nearly identical trees come here)
+__device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2)
+{
+    s1 = 0.0; s2 = 0.0;
+    const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
+    SplitRec a = *A, b = *B;
+    while ((a.id & b.id) != kSentinelId) {
+        const bool adv_a = a.id <= b.id, adv_b = b.id <= a.id;
+        const double la = adv_a ? a.len : 0.0, lb = adv_b ? b.len : 0.0;
+        const double d = la - lb;
+        s1 += fabs(d); s2 = fma(d, d, s2);
+        if (adv_a) a = *++A;
+        if (adv_b) b = *++B;
+    }
+    s1 += p.single_l1[i] + p.single_l1[j];
+    s2 += p.single_l2[i] + p.single_l2[j];
+    for (int k = 0; k < p.n_k; k++) {
+        const double d = p.leafT[(size_t)k * p.ldT + i] - p.leafT[(size_t)k * p.ldT + j];
+        s1 += fabs(d); s2 = fma(d, d, s2);
+    }
+}
+
+template <uint32_t MASK, bool RECT>
+__global__ void __launch_bounds__(NT, 3) pairjoin_kernel(const PairParams p)
+{
+    constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
+    constexpr bool kWeighted = kWRF || kEUC;
+
+    // ---- which tile ---------------------------------------------------------------------------------------------
+    int tile_r, tile_c;           // in units of 64 rows / 32 columns
+    if (RECT) {
+        tile_r = (int)(blockIdx.x / p.tiles_x) + p.tile_row0;
+        tile_c = (int)(blockIdx.x % p.tiles_x) + p.col_tile0;
+    } else {
+        // tile row u (from p.tile_row0) needs column tiles 2*tile_r .. tiles_x-1: L0 - 2u of them, L0 = tiles_x - 2*tile_row0
+        const long long t = blockIdx.x, L0 = p.tiles_x - 2 * p.tile_row0;
+        const double b = (double)L0 + 1.0;
+        long long u = (long long)floor((b - sqrt(b * b - 4.0 * (double)t)) * 0.5);
+        if (u < 0) u = 0;
+        while (u * L0 - u * (u - 1) > t) u--;
+        while ((u + 1) * L0 - (u + 1) * u <= t) u++;
+        tile_r = (int)u + p.tile_row0;
+        tile_c = 2 * tile_r + (int)(t - (u * L0 - u * (u - 1)));
+    }
+    const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
+
+    // ---- shared memory ------------------------------------------------------------------------------------------
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t slots = p.table_slots, smask = slots - 1;
+    unsigned char *cur = smem_raw;
+    double *tab_len = nullptr, *E1 = nullptr, *E2 = nullptr, *leaf = nullptr;
+    if constexpr (kWeighted) { tab_len = reinterpret_cast<double *>(cur); cur += (size_t)slots * sizeof(double); }
+    if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
+    if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
+    if constexpr (kWeighted) { leaf = reinterpret_cast<double *>(cur); cur += 2 * KC * (TR + TC) * sizeof(double); }
+    uint32_t *tab_id = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);
+    unsigned char *tab_col = cur; cur += slots;
+    unsigned char *cnt = cur;                                       // [TR*TC] common-split counts (<= 255)
+
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+
+    // ---- leaf-length k-chunks start flowing while the join runs --------------------------------------------------------------
+    const int n_chunks = kWeighted ? p.n_k / KC : 0;
+    auto load_chunk = [&](int chunk, int stage) {
+        // per stage: A [KC][TR] then B [KC][TC]
+        double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
+        constexpr int PA = KC * TR / 2, PB = KC * TC / 2;
+        for (int e = tid; e < PA + PB; e += NT) {
+            if (e < PA) {
+                const int kk = e / (TR / 2), c2 = e % (TR / 2);
+                cp_async16(sA + kk * TR + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + i0 + 2 * c2);
+            } else {
+                const int f = e - PA, kk = f / (TC / 2), c2 = f % (TC / 2);
+                cp_async16(sB + kk * TC + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + j0 + 2 * c2);
+            }
+        }
+    };
+    if constexpr (kWeighted) {
+        if (n_chunks > 0) load_chunk(0, 0);
+        cp_async_commit();
+        if (n_chunks > 1) load_chunk(1, 1);
+        cp_async_commit();
+    }
+
+    // ---- init table and per-cell slots ---------------------------------------------------------------------------------------------
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);
+        for (uint32_t e = tid; e < slots / 4; e += NT) t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        if constexpr (kWRF) { double2 *z = reinterpret_cast<double2 *>(E1); for (int e = tid; e < TR * TC / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
+        if constexpr (kEUC) { double2 *z = reinterpret_cast<double2 *>(E2); for (int e = tid; e < TR * TC / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
+        uint32_t *z = reinterpret_cast<uint32_t *>(cnt);
+        for (int e = tid; e < TR * TC / 4; e += NT) z[e] = 0u;
+    }
+    __syncthreads();
+
+    // ---- build: column trees -> hash table (multi-map: equal ids from different trees sit in successive slots) -------------------
+    {
+        const SplitRec *gB = p.shared + j0 * p.sh_stride;
+        const int n_rec = TC * p.sh_stride;
+        for (int e = tid; e < n_rec; e += NT) {
+            const SplitRec b = gB[e];
+            if (b.id == kSentinelId) continue;
+            uint32_t h = hash_id(b.id, smask);
+            while (atomicCAS(&tab_id[h], kEmpty, b.id) != kEmpty) h = (h + 1) & smask;
+            tab_col[h] = (unsigned char)(e / p.sh_stride);
+            if constexpr (kWeighted) tab_len[h] = b.len;
+        }
+    }
+    __syncthreads();
+
+    // ---- probe: thread `row` walks its tree's entries in list order; it alone writes the slots of its row ---------------------------
+    if (tid < TR) {
+        const int row = tid;
+        const int64_t i = i0 + row;
+        const int n = p.nshared[i];
+        const SplitRec *A = p.shared + i * p.sh_stride;
+        const int first_col = RECT ? 0 : (int)(i - j0) + 1;        // columns below this are on or under the diagonal
+        for (int base = 0; base < n; base += 4) {
+            SplitRec a[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) a[k] = (base + k < n) ? A[base + k] : SplitRec{kSentinelId, 0, 0.0};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (a[k].id == kSentinelId) continue;
+                uint32_t h = hash_id(a[k].id, smask);
+                for (;;) {
+                    const uint32_t sid = tab_id[h];
+                    if (sid == kEmpty) break;
+                    if (sid == a[k].id) {
+                        const int col = tab_col[h];
+                        if (col >= first_col) {
+                            const int cell = row * TC + col;
+                            cnt[cell] = (unsigned char)(cnt[cell] + 1);
+                            if constexpr (kWeighted) {
+                                const double lb = tab_len[h];
+                                if constexpr (kEUC) E2[cell] += -2.0 * a[k].len * lb;
+                                if constexpr (kWRF) E1[cell] += fabs(a[k].len - lb) - fabs(a[k].len) - fabs(lb);
+                            }
+                        }
+                    }
+                    h = (h + 1) & smask;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- my pairs: rows 4ty..4ty+3, columns tx and tx+16.  acc starts as the (negative) correction E --------------------------------
+    double acc1[4][2], acc2[4][2];
+    int common[4][2];
+    uint32_t risky = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int64_t i = i0 + 4 * ty + r;
+        double q1i = 0, q2i = 0;
+        if constexpr (kWRF) q1i = p.q1[i];
+        if constexpr (kEUC) q2i = p.q2[i];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int cell = (4 * ty + r) * TC + tx + 16 * c;
+            const int64_t j = j0 + tx + 16 * c;
+            common[r][c] = cnt[cell];
+            acc1[r][c] = 0.0; acc2[r][c] = 0.0;
+            bool rk = false;
+            if constexpr (kWRF) { acc1[r][c] = E1[cell]; rk |= (-acc1[r][c] > kRisk * (q1i + p.q1[j])); }
+            if constexpr (kEUC) { acc2[r][c] = E2[cell]; rk |= (-acc2[r][c] > kRisk * (q2i + p.q2[j])); }
+            risky |= (rk ? 1u : 0u) << (2 * r + c);
+        }
+    }
+
+    // ---- leaf edges -----------------------------------------------------------------------------------------------------------------
+    if constexpr (kWeighted) {
+        for (int chunk = 0; chunk < n_chunks; chunk++) {
+            const int stage = chunk & 1;
+            cp_async_wait<1>();
+            __syncthreads();
+            const double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const double2 a01 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty);
+                const double2 a23 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty + 2);
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                const double bv[2] = {sB[kk * TC + tx], sB[kk * TC + tx + 16]};
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const double d = av[r] - bv[c];
+                        if constexpr (kWRF) acc1[r][c] += fabs(d);
+                        if constexpr (kEUC) acc2[r][c] = fma(d, d, acc2[r][c]);
+                    }
+            }
+            __syncthreads();
+            if (chunk + 2 < n_chunks) load_chunk(chunk + 2, stage);
+            cp_async_commit();
+        }
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------------------------------------------------
+    int sj[2]; double q1j[2], q2j[2], sumj[2], normj[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const int64_t j = j0 + tx + 16 * c;
+        sj[c] = p.nsplits[j];
+        if constexpr (kWRF) { q1j[c] = p.q1[j]; sumj[c] = p.sum_len[j]; }
+        if constexpr (kEUC) { q2j[c] = p.q2[j]; normj[c] = p.norm[j]; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int64_t i = i0 + 4 * ty + r;
+        if (i < p.row_begin || i >= p.row_end) continue;
+        const int si = p.nsplits[i];
+        double q1i = 0, q2i = 0, sumi = 0, normi = 0;
+        if constexpr (kWRF) { q1i = p.q1[i]; sumi = p.sum_len[i]; }
+        if constexpr (kEUC) { q2i = p.q2[i]; normi = p.norm[i]; }
+        const int64_t row_off = RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int64_t j = j0 + tx + 16 * c;
+            if (j >= p.col_end || (RECT ? j < p.col_offset : j <= i)) continue;
+            const int64_t idx = row_off + j;
+            if constexpr (kRF) {
+                const int den = si + sj[c];
+                double v = (double)(den - 2 * common[r][c]);
+                if (p.normalise) v = den ? v / (double)den : 0.0;
+                p.out[0][idx] = v;
+            }
+            if constexpr (kWeighted) {
+                // acc = E + leaf; the per-tree totals complete the sum: (Q_i + Q_j) + E + leaf
+                double t1 = 0.0, t2 = 0.0;
+                if constexpr (kWRF) t1 = (q1i + q1j[c]) + acc1[r][c];
+                if constexpr (kEUC) t2 = (q2i + q2j[c]) + acc2[r][c];
+                if (risky >> (2 * r + c) & 1u) exact_pair(p, i, j, t1, t2);
+                if constexpr (kWRF) {
+                    double v = t1;
+                    if (p.normalise) { const double den = sumi + sumj[c]; v = den != 0.0 ? v / den : 0.0; }
+                    p.out[1][idx] = v;
+                }
+                if constexpr (kEUC) {
+                    double v = sqrt(t2);
+                    if (p.normalise) { const double den = normi + normj[c]; v = den != 0.0 ? v / den : 0.0; }
+                    p.out[2][idx] = v;
+                }
+            }
+        }
+    }
+}
+
+template <uint32_t MASK, bool RECT>
+cudaError_t launch_one(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    auto k = pairjoin_kernel<MASK, RECT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, NT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool RECT>
+cudaError_t launch_mask(uint32_t mask, const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (mask & 7u) {
+        case 1: return launch_one<1, RECT>(p, grid, smem, st);
+        case 2: return launch_one<2, RECT>(p, grid, smem, st);
+        case 3: return launch_one<3, RECT>(p, grid, smem, st);
+        case 4: return launch_one<4, RECT>(p, grid, smem, st);
+        case 5: return launch_one<5, RECT>(p, grid, smem, st);
+        case 6: return launch_one<6, RECT>(p, grid, smem, st);
+        case 7: return launch_one<7, RECT>(p, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int pairjoin_table_slots(int max_shared)
+{
+    int slots = 512;
+    while (slots < 2 * TC * max_shared) slots *= 2;
+    return slots;
+}
+
+size_t pairjoin_smem_bytes(uint32_t mask, int table_slots)
+{
+    size_t s = (size_t)table_slots * 5 + TR * TC;
+    if (mask & 6u) s += (size_t)table_slots * sizeof(double) + 2 * KC * (TR + TC) * sizeof(double);
+    if (mask & 2u) s += TR * TC * sizeof(double);
+    if (mask & 4u) s += TR * TC * sizeof(double);
+    return s;
+}
+
+// Triangular: rows [row_begin,row_end) -> 64-row tiles from p.tile_row0 (set here); rect: rows [0,row_end), columns from `split`.
+cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, cudaStream_t st)
+{
+    const size_t smem = pairjoin_smem_bytes(mask, p.table_slots);
+    const int64_t col_tiles_total = (p.N + TC - 1) / TC;
+    p.tile_row0 = (int)(p.row_begin / TR);
+    const int64_t tile_rows = (p.row_end + TR - 1) / TR - p.tile_row0;
+    int64_t grid;
+    if (rect) {
+        p.col_tile0 = (int)(p.col_offset / TC);
+        p.tiles_x = (int)(col_tiles_total - p.col_tile0);
+        grid = tile_rows * p.tiles_x;
+    } else {
+        p.col_tile0 = 0;
+        p.tiles_x = (int)col_tiles_total;
+        const int64_t L0 = col_tiles_total - 2 * p.tile_row0;
+        // rows whose first column tile lies beyond the last one contribute nothing (only when N is not a multiple of 64)
+        int64_t rows = tile_rows;
+        while (rows > 0 && L0 - 2 * (rows - 1) <= 0) rows--;
+        grid = rows * L0 - rows * (rows - 1);
+    }
+    if (grid <= 0) return cudaSuccess;
+    return rect ? launch_mask<true>(mask, p, (unsigned)grid, smem, st) : launch_mask<false>(mask, p, (unsigned)grid, smem, st);
+}
+
+}  // namespace td

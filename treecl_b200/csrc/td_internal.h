@@ -34,6 +34,8 @@ struct HostSet {
     std::vector<uint64_t> leafmask;            // [N][W]
     std::vector<double> sum_len, norm;         // all edges incl. leaves: sum l, sqrt(sum l^2)
     std::vector<double> single_l1, single_l2;  // sums over splits held by this tree only: sum |l|, sum l^2
+    std::vector<double> q1, q2;                // sums over ALL internal splits: sum |l|, sum l^2
+    double mean_common = 0.0;                  // expected number of common splits of a random pair of the set
 
     // full lists, rows sorted by split id (uniform sets) or by mask (otherwise); stride max_splits
     std::vector<uint64_t> masks;               // [N][max_splits][W]
