@@ -56,6 +56,26 @@ class TestTreeDistanceGoldens:
         assert (dm.values == dm.values.T).all() and (np.diag(dm.values) == 0).all()
 
 
+class TestPartialOverlapGoldens:
+    """reference tests/test.py:280-294: trees pruned to different leaf sets -> distance on the intersection."""
+
+    @pytest.fixture(autouse=True)
+    def setup(self, td, golden_scalars):
+        self.c = td.Collection(trees_dir=os.path.join(GOLDEN, 'trees'), show_progress=False)
+        po = golden_scalars['partial_overlap']
+        self.c[0].parameters.ml_tree = td.Tree(self.c[0].parameters.ml_tree).prune_to_subset(set(po['keep_0'])).newick
+        self.c[1].parameters.ml_tree = td.Tree(self.c[1].parameters.ml_tree).prune_to_subset(set(po['keep_1'])).newick
+        self.po = po
+
+    def test_intertree_partial_overlap(self):
+        dm = self.c.get_inter_tree_distances('geo', show_progress=False)
+        assert dm.values[0, 1] == pytest.approx(self.po['geo'], rel=RTOL)
+
+    def test_intertree_partial_overlap_value_replacement(self):
+        dm = self.c.get_inter_tree_distances('geo', min_overlap=5, overlap_fail_value=-1, show_progress=False)
+        assert dm.values[0, 1] == -1
+
+
 class TestGeodesicMatrixGolden:
     """reference tests/test.py:320-326 and ParallelTests :437-467 (every jobhandler gives the same checksum)."""
 
@@ -151,6 +171,47 @@ def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     assert_close(got, want)
     st = ts.geo_stats()
     assert st['pairs'] == n_trees * (n_trees - 1) // 2 and st['ratios'] >= 0
+
+
+@pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30)])
+@pytest.mark.parametrize('norm', [False, True])
+def test_different_leaf_sets_vs_oracle(td, oracle_mod, n_taxa, n_trees, norm):
+    """Pairs with different leaf sets (restrict-then-join kernel) against the oracle's tree-level pruning.
+    UNPINNED by the reference for rf/wrf/euc (only the geodesic has a golden)."""
+    from treecl_b200 import _lib, synth
+    rng = np.random.default_rng(n_taxa)
+    full = synth.uniform_trees(n_trees, n_taxa, seed=77 + n_taxa)
+    labels = synth.taxon_labels(n_taxa)
+    trees = []
+    for k, t in enumerate(full):
+        if k % 4 == 0:
+            trees.append(t)                                   # some complete trees
+        else:
+            keep = rng.choice(n_taxa, size=int(rng.integers(max(4, n_taxa // 2), n_taxa + 1)), replace=False)
+            trees.append(td.Tree(t).prune_to_subset({labels[i] for i in keep}).newick)
+    ts = _lib.TreeSet(trees)
+    assert ts.info.uniform == 0
+    mo = max(4, n_taxa // 2)                                 # some pairs fall under min_overlap
+    got = ts.pairwise(('rf', 'wrf', 'euc', 'geo'), normalise=norm, min_overlap=mo, overlap_fail_value=-7.5)
+    n_fail = 0
+    for metric in ('rf', 'wrf', 'euc', 'geo'):
+        want = oracle_mod.matrix(trees, metric, normalise=norm, min_overlap=mo, overlap_fail_value=-7.5, nthreads=8)
+        n_fail += int((want == -7.5).sum())
+        if metric == 'rf':
+            assert np.array_equal(got[metric], want)
+        else:
+            assert_close(got[metric], want)
+    # sharded rows give the same bytes
+    a = ts.pairwise(('geo',), normalise=norm, min_overlap=mo, overlap_fail_value=-7.5, row_begin=3, row_end=n_trees - 2)['geo']
+    p0, p1 = _lib.condensed_offset(n_trees, 3), _lib.condensed_offset(n_trees, n_trees - 2)
+    assert np.array_equal(a, got['geo'][p0:p1])
+
+
+def test_mixed_rooting_is_refused(td):
+    from treecl_b200 import _lib
+    ts = _lib.TreeSet(['((A:1,B:1):1,(C:1,D:1):1);', '((A:1,B:1):1,C:1,D:1);', '((A:1,C:1):1,B:1,D:1);'])
+    with pytest.raises(ValueError):
+        ts.pairwise(('rf',))
 
 
 def test_polytomies_and_rooted_trees(td, oracle_mod):

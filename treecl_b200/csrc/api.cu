@@ -28,7 +28,8 @@ struct DeviceSet {
     double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr, *q1 = nullptr, *q2 = nullptr;
     uint32_t *ids = nullptr;
     double *lens = nullptr;
-    uint64_t *masks = nullptr;
+    uint64_t *masks = nullptr, *leafmask = nullptr;
+    int32_t *rooted = nullptr;
     unsigned long long *work_counter = nullptr, *stats = nullptr;   // work_counter: ring of kCounters, one per launch in flight
     std::atomic<uint32_t> next_counter{0};
     int *error_flag = nullptr;
@@ -103,6 +104,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     if ((rc = dev_alloc(d, &d->ids, N * d->stride))) return rc;
     if ((rc = dev_alloc(d, &d->lens, N * d->stride))) return rc;
     if ((rc = dev_alloc(d, &d->masks, N * d->stride * d->W))) return rc;
+    if ((rc = dev_alloc(d, &d->leafmask, N * d->W))) return rc;
+    if ((rc = dev_alloc(d, &d->rooted, N))) return rc;
     if ((rc = dev_alloc(d, &d->work_counter, kCounters))) return rc;
     if ((rc = dev_alloc(d, &d->stats, 4))) return rc;
     if ((rc = dev_alloc(d, &d->error_flag, 1))) return rc;
@@ -134,6 +137,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->leafmask, h.leafmask.data(), N * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->rooted, h.tree_rooted.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (h.n_taxa > 0) {
         CUDA_TRY(launch_transpose_leaf(d->leaflen, d->leafT, h.N, h.n_taxa, d->Npad, st));
         launch_counter_add(1);
@@ -183,11 +188,33 @@ static int pick_tile(const DeviceSet *d, bool weighted)
     return 0;
 }
 
-static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, bool rect, int64_t split, int64_t row_begin,
-                        int64_t row_end, void *const d_out[4], cudaStream_t st)
+static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
+                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
     const HostSet &h = ts->host;
-    if (!h.uniform) { set_error("trees with differing leaf sets / rootedness need the restrict-then-join path, which this build does not have yet"); return TD_ERR_UNSUPPORTED; }
+    if (!h.uniform) {
+        // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
+        if (h.max_splits > 64 || h.W > 2) { set_error("the restrict-then-join kernel holds at most 64 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
+        CUDA_TRY(cudaSetDevice(d->device));
+        GeoParams g{};
+        g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
+        g.leafmask = d->leafmask; g.rooted = d->rooted;
+        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise;
+        g.metric_mask = mask; g.min_overlap = min_overlap; g.fail_value = fail_value;
+        for (int m = 0; m < 4; m++) {
+            g.outs[m] = (double *)d_out[m];
+            if ((mask >> m & 1u) && !g.outs[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+        }
+        g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
+        if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
+        else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
+        if (g.p_end > g.p_begin) {
+            CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+            CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : 64, d->sm_count, st));
+            launch_counter_add(1);
+        }
+        return TD_OK;
+    }
     CUDA_TRY(cudaSetDevice(d->device));
     const uint32_t m3 = mask & 7u;
     if (m3) {
@@ -350,7 +377,6 @@ int64_t td_condensed_offset(int64_t n_trees, int64_t row) { return condensed_off
 int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
                        int64_t row_begin, int64_t row_end, void *const d_out[4], void *stream)
 {
-    (void)min_overlap; (void)overlap_fail_value;     // only reachable for non-uniform sets
     if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
     const int64_t N = ts->host.N;
     if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
@@ -359,7 +385,7 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
     int device, rc; DeviceSet *d;
     if ((rc = device_of(d_out, metric_mask, &device))) return rc;
     if ((rc = check_ready(ts, device, &d))) return rc;
-    return run_pairwise(ts, d, metric_mask, normalise, false, 0, row_begin, row_end, d_out, (cudaStream_t)stream);
+    return run_pairwise(ts, d, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, row_begin, row_end, d_out, (cudaStream_t)stream);
 }
 
 int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4], void *stream)
@@ -371,7 +397,7 @@ int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask,
     int device, rc; DeviceSet *d;
     if ((rc = device_of(d_out, metric_mask, &device))) return rc;
     if ((rc = check_ready(ts, device, &d))) return rc;
-    return run_pairwise(ts, d, metric_mask, normalise, true, split, 0, split, d_out, (cudaStream_t)stream);
+    return run_pairwise(ts, d, metric_mask, normalise, 4, 0.0, true, split, 0, split, d_out, (cudaStream_t)stream);
 }
 
 int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
@@ -403,9 +429,11 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
-    if (metric_mask & TD_MASK(TD_GEO)) {
+    {
         int flag = 0; cudaMemcpy(&flag, dset->error_flag, sizeof flag, cudaMemcpyDeviceToHost);
-        if (flag) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
+        if (flag) cudaMemset(dset->error_flag, 0, sizeof flag);
+        if (flag & 2) { set_error("cannot compare a rooted with an unrooted tree (undefined in the reference as well)"); return TD_ERR_MIXED_ROOTING; }
+        if (flag & 1) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
     }
     return TD_OK;
 }

@@ -43,21 +43,29 @@ struct GeoParams {
     const int32_t *nsplits;   // [N]
     const double *leaflen;    // [N][n_taxa] tree-major
     const double *norm;       // [N]
+    const uint64_t *leafmask; // [N][W] taxa present in each tree (general kernel)
+    const int32_t *rooted;    // [N]
     int64_t N;
     int stride, n_taxa, W;
     int64_t p_begin, p_end, p_base;      // condensed pair range (triangular) ...
     int64_t rect_split, rect_cols;       // ... or rectangular: rows [0,split) x cols [split, split+cols); p = a*cols + b
     int rect;
     int normalise;
-    double *out;
+    double *out;              // geodesic kernel (uniform sets)
+    double *outs[4];          // general kernel: one output per metric of metric_mask
+    uint32_t metric_mask;
+    int min_overlap;
+    double fail_value;
     unsigned long long *work_counter;    // dynamic pair scheduler
     unsigned long long *stats;           // [4]: pairs, maxflow solves, final ratios, augmentations
-    int *error_flag;                     // set when an iteration cap was hit
+    int *error_flag;                     // bit 0: an iteration cap was hit; bit 1: rooted vs unrooted pair
 };
 
 // cap: 32 or 64 (max internal edges per tree the warp-per-pair GTP kernel holds in registers/shared memory)
 cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
 size_t geodesic_smem_bytes(int cap, int W, int warps);
+// pairs with different leaf sets (non-uniform sets): restrict-then-join, all four metrics
+cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
 
 uint64_t launch_counter_add(uint64_t n);
 

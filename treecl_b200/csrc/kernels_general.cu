@@ -1,0 +1,263 @@
+// kernels_general.cu -- all four metrics for pairs of trees with DIFFERENT leaf sets: restrict-then-join, one warp per pair.
+//
+// Restates on the split level what the reference does on the tree level for such a pair (treeCl/treedist.py:63-68):
+//     if t1 ^ t2:  if len(t1 & t2) < min_overlap: return overlap_fail_value
+//                  else: t1, t2 = prune both to the intersection          (Tree.prune_to_subset, treeCl/tree.py:989-1001)
+// Pruning a tree to a leaf subset M and re-encoding it (dendropy retain_taxa + suppress_unifurcations +
+// collapse_basal_bifurcation, then PhyloTree) is, in split terms: intersect every split mask with M; drop splits with an
+// empty side; a split with a one-leaf side becomes part of that leaf's edge (lengths add); re-canonicalise against the
+// lowest taxon of M; equal masks merge and their lengths ADD (pinned by the reference's partial-overlap golden,
+// tests/test.py:280-286).  After that the pair is an ordinary same-leaf-set pair; the GTP part is geo_core.cuh.
+// Used for every pair of a non-uniform tree set (slow path: a few thousand pairs/s per SM, but on the GPU).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "geo_core.cuh"
+#include "kernels.h"
+
+namespace td {
+
+namespace {
+
+using namespace geo;
+
+template <int H, int W>
+struct GeneralSmem {
+    WarpSmem<H, W> core;                     // flow, lenB, maskB, idA/idB (unused here), stack
+    uint64_t maskA[32 * H * W];
+    double lenA[32 * H];
+    double leafA[64 * W], leafB[64 * W];     // restricted leaf-edge lengths (taxa outside the intersection stay 0)
+};
+
+template <int W> __device__ __forceinline__ bool mask_eq(const uint64_t *a, const uint64_t (&b)[W])
+{
+    bool e = true;
+#pragma unroll
+    for (int w = 0; w < W; w++) e &= (a[w] == b[w]);
+    return e;
+}
+
+// restrict my split(s) of one tree to the common leaf set M; leaf folds go to `leaf`, internal splits (deduplicated, lengths
+// summed in ascending slot order) stay lane-owned: mine[h] (valid representative), m[h], len[h].  Returns the valid set.
+template <int H, int W>
+__device__ __forceinline__ Bits<H> restrict_tree(const GeoParams &p, int64_t t, const uint64_t (&M)[W], int nM, int ref, int rooted,
+                                                 uint64_t *smask, double *slen, double *leaf, int lane,
+                                                 uint64_t (&m)[H][W], double (&len)[H])
+{
+    const int S = p.nsplits[t];
+    Bits<H> valid;
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int s = lane + 32 * h;
+        bool internal = false; int leaf_k = -1; len[h] = 0.0;
+        if (s < S) {
+            len[h] = p.lens[t * p.stride + s];
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) { m[h][w] = p.masks[(t * p.stride + s) * W + w] & M[w]; c += __popcll(m[h][w]); }
+            const int cc = nM - c;
+            if (c == 0 || cc == 0) { /* edge inside a pruned region, or the stem above the new root */ }
+            else if (c == 1 || (!rooted && cc == 1)) {
+                if (c != 1) {
+#pragma unroll
+                    for (int w = 0; w < W; w++) m[h][w] = M[w] & ~m[h][w];
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++) if (m[h][w]) leaf_k = 64 * w + __ffsll((long long)m[h][w]) - 1;
+            } else {
+                internal = true;
+                if (!rooted && ((m[h][ref >> 6] >> (ref & 63)) & 1ull)) {
+#pragma unroll
+                    for (int w = 0; w < W; w++) m[h][w] = M[w] & ~m[h][w];
+                }
+            }
+        }
+        // leaf folds, in slot order (one writer at a time -> deterministic sums)
+        uint32_t folds = __ballot_sync(FULL, leaf_k >= 0);
+        while (folds) {
+            const int src = __ffs(folds) - 1; folds &= folds - 1;
+            const int k = __shfl_sync(FULL, leaf_k, src); const double l = __shfl_sync(FULL, len[h], src);
+            if (lane == 0) leaf[k] += l;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < W; w++) smask[s * W + w] = internal ? m[h][w] : 0ull;
+        slen[s] = len[h];
+        valid.w[h] = __ballot_sync(FULL, internal);
+    }
+    __syncwarp();
+    // merge equal masks: the lowest slot is the representative and takes the sum
+    Bits<H> reps;
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const int s = lane + 32 * h;
+        bool rep = valid.mine(h, lane);
+        double sum = len[h];
+        if (rep) {
+            Bits<H> it = valid;
+            while (it.any()) {
+                const int t2 = it.first(); it.reset(t2);
+                if (t2 == s || !mask_eq<W>(&smask[t2 * W], m[h])) continue;
+                if (t2 < s) { rep = false; break; }
+                sum += slen[t2];
+            }
+        }
+        len[h] = rep ? sum : 0.0;
+        reps.w[h] = __ballot_sync(FULL, rep);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < H; h++) slen[lane + 32 * h] = len[h];
+    __syncwarp();
+    return reps;
+}
+
+template <int H, int W>
+__global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GeneralSmem<H, W> &sm = reinterpret_cast<GeneralSmem<H, W> *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    Counters st;
+    bool failed = false;
+    const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+
+    for (;;) {
+        unsigned long long wk = 0;
+        if (lane == 0) wk = atomicAdd(p.work_counter, 1ull);
+        wk = __shfl_sync(FULL, wk, 0);
+        const int64_t pidx = p.p_begin + (int64_t)wk;
+        if (pidx >= p.p_end) break;
+        int64_t ti, tj;
+        if (p.rect) { ti = pidx / p.rect_cols; tj = p.rect_split + pidx % p.rect_cols; }
+        else {
+            const double Nd = (double)p.N;
+            int64_t i = (int64_t)floor(((2.0 * Nd - 1.0) - sqrt((2.0 * Nd - 1.0) * (2.0 * Nd - 1.0) - 8.0 * (double)pidx)) * 0.5);
+            if (i < 0) i = 0; if (i > p.N - 2) i = p.N - 2;
+            while (i + 1 <= p.N - 2 && tri_row_start(i + 1, p.N) <= pidx) i++;
+            while (i > 0 && tri_row_start(i, p.N) > pidx) i--;
+            ti = i; tj = pidx - tri_row_start(i, p.N) + i + 1;
+        }
+        st.pairs++;
+        const int64_t o = pidx - p.p_base;
+        auto write_all = [&](double v) {
+            if (lane == 0) for (int m = 0; m < 4; m++) if ((p.metric_mask >> m & 1u) && p.outs[m]) p.outs[m][o] = v;
+        };
+
+        // ---- common leaf set -----------------------------------------------------------------------------------------
+        uint64_t M[W]; bool same = true; int nM = 0, ref = -1;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const uint64_t a = p.leafmask[ti * W + w], b = p.leafmask[tj * W + w];
+            same &= (a == b); M[w] = a & b; nM += __popcll(M[w]);
+        }
+#pragma unroll
+        for (int w = W - 1; w >= 0; w--) if (M[w]) ref = 64 * w + __ffsll((long long)M[w]) - 1;
+        const int rooted = p.rooted[ti];
+        if (rooted != p.rooted[tj]) { write_all(kNaN); if (lane == 0) atomicOr(p.error_flag, 2); continue; }
+        if (!same && nM < p.min_overlap) { write_all(p.fail_value); continue; }       // treeCl/treedist.py:64-65
+
+        // ---- restricted leaf lengths, then both trees' restricted split lists ---------------------------------------------------
+        __syncwarp();
+        for (int k = lane; k < 64 * W; k += 32) {
+            const bool in = k < p.n_taxa && ((M[k >> 6] >> (k & 63)) & 1ull);
+            sm.leafA[k] = in ? p.leaflen[ti * p.n_taxa + k] : 0.0;
+            sm.leafB[k] = in ? p.leaflen[tj * p.n_taxa + k] : 0.0;
+        }
+        __syncwarp();
+        uint64_t mA[H][W], mB[H][W]; double lenA[H], lenB[H];
+        const Bits<H> validA = restrict_tree<H, W>(p, ti, M, nM, ref, rooted, sm.maskA, sm.lenA, sm.leafA, lane, mA, lenA);
+        const Bits<H> validB = restrict_tree<H, W>(p, tj, M, nM, ref, rooted, sm.core.maskB, sm.core.lenB, sm.leafB, lane, mB, lenB);
+
+        // ---- leaf terms and per-tree normalisers ---------------------------------------------------------------------------------
+        double l1 = 0, l2 = 0, sumA = 0, sumB = 0, sqA = 0, sqB = 0;
+        for (int k = lane; k < 64 * W; k += 32) {
+            const double a = sm.leafA[k], b = sm.leafB[k], d = a - b;
+            l1 += fabs(d); l2 = fma(d, d, l2); sumA += a; sumB += b; sqA = fma(a, a, sqA); sqB = fma(b, b, sqB);
+        }
+        // ---- common splits: equal restricted masks --------------------------------------------------------------------------------
+        Bits<H> setA, setB;
+        double c1 = 0, c2 = 0, o1 = 0, o2 = 0;      // common: |la-lb|, (la-lb)^2 ; one-sided: |l|, l^2
+        double la2[H], lb2[H];
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            bool ncA = false, ncB = false;
+            la2[h] = lenA[h] * lenA[h]; lb2[h] = lenB[h] * lenB[h];
+            if (validA.mine(h, lane)) {
+                sumA += lenA[h]; sqA += la2[h];
+                int partner = -1;
+                Bits<H> it = validB;
+                while (it.any()) { const int b = it.first(); it.reset(b); if (mask_eq<W>(&sm.core.maskB[b * W], mA[h])) { partner = b; break; } }
+                if (partner >= 0) { const double d = lenA[h] - sm.core.lenB[partner]; c1 += fabs(d); c2 = fma(d, d, c2); }
+                else { ncA = true; o1 += fabs(lenA[h]); o2 += la2[h]; }
+            }
+            if (validB.mine(h, lane)) {
+                sumB += lenB[h]; sqB += lb2[h];
+                bool found = false;
+                Bits<H> it = validA;
+                while (it.any()) { const int a = it.first(); it.reset(a); if (mask_eq<W>(&sm.maskA[a * W], mB[h])) { found = true; break; } }
+                if (!found) { ncB = true; o1 += fabs(lenB[h]); o2 += lb2[h]; }
+            }
+            setA.w[h] = __ballot_sync(FULL, ncA); setB.w[h] = __ballot_sync(FULL, ncB);
+        }
+        const int rf = setA.count() + setB.count(), rf_den = validA.count() + validB.count();
+        l1 = warp_sum(l1); l2 = warp_sum(l2); c1 = warp_sum(c1); c2 = warp_sum(c2); o1 = warp_sum(o1); o2 = warp_sum(o2);
+        sumA = warp_sum(sumA); sumB = warp_sum(sumB); sqA = warp_sum(sqA); sqB = warp_sum(sqB);
+
+        double geo2 = 0.0;
+        if (p.metric_mask & 8u) {
+            double part = 0.0;
+            const double total = gtp_noncommon<H, W>(sm.core, mA, setA, setB, la2, lb2, lane, part, st, failed);
+            geo2 = warp_sum(part) + total + c2 + l2;
+        }
+        if (lane == 0) {
+            const double nden = sqrt(sqA) + sqrt(sqB);
+            if ((p.metric_mask & 1u) && p.outs[0]) { double v = (double)rf; if (p.normalise) v = rf_den ? v / (double)rf_den : 0.0; p.outs[0][o] = v; }
+            if ((p.metric_mask & 2u) && p.outs[1]) { double v = (c1 + o1) + l1; if (p.normalise) { const double den = sumA + sumB; v = den != 0.0 ? v / den : 0.0; } p.outs[1][o] = v; }
+            if ((p.metric_mask & 4u) && p.outs[2]) { double v = sqrt((c2 + o2) + l2); if (p.normalise) v = nden != 0.0 ? v / nden : 0.0; p.outs[2][o] = v; }
+            if ((p.metric_mask & 8u) && p.outs[3]) {
+                double v = sqrt(geo2); if (p.normalise) v = nden != 0.0 ? v / nden : 0.0;
+                if (failed) v = kNaN;
+                p.outs[3][o] = v;
+            }
+        }
+        if (failed) { if (lane == 0) atomicOr(p.error_flag, 1); failed = false; }
+    }
+    if (lane == 0 && p.stats) {
+        atomicAdd(&p.stats[0], st.pairs); atomicAdd(&p.stats[1], st.flows);
+        atomicAdd(&p.stats[2], st.ratios); atomicAdd(&p.stats[3], st.aug);
+    }
+}
+
+template <int H, int W>
+cudaError_t launch_gen(const GeoParams &p, int n_sms, cudaStream_t st)
+{
+    auto k = general_kernel<H, W>;
+    const size_t smem = sizeof(GeneralSmem<H, W>) * GEO_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, GEO_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t pairs = p.p_end - p.p_begin;
+    int64_t blocks = (int64_t)n_sms * per_sm;
+    const int64_t need = (pairs + GEO_WARPS - 1) / GEO_WARPS;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    k<<<(unsigned)blocks, GEO_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st)
+{
+    if (cap <= 32 && p.W == 1) return launch_gen<1, 1>(p, n_sms, st);
+    if (cap <= 64 && p.W == 1) return launch_gen<2, 1>(p, n_sms, st);
+    if (cap <= 64 && p.W == 2) return launch_gen<2, 2>(p, n_sms, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace td

@@ -18,125 +18,22 @@
 
 #include <cstdint>
 
+#include "geo_core.cuh"
 #include "kernels.h"
 
 namespace td {
 
 namespace {
 
-constexpr unsigned FULL = 0xffffffffu;
-constexpr int GEO_WARPS = 4;
-constexpr double FLOW_TOL = 1e-13;
-constexpr double SPLIT_TOL = 1e-12;
-
-template <int H>
-struct Bits {
-    uint32_t w[H];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int h = 0; h < H; h++) w[h] = 0; }
-    __device__ __forceinline__ bool any() const { uint32_t x = 0;
-#pragma unroll
-        for (int h = 0; h < H; h++) x |= w[h]; return x != 0; }
-    __device__ __forceinline__ int count() const { int c = 0;
-#pragma unroll
-        for (int h = 0; h < H; h++) c += __popc(w[h]); return c; }
-    // i is warp-uniform; the word is picked by selects so that w[] stays in registers
-    __device__ __forceinline__ bool test(int i) const { uint32_t x = w[0];
-#pragma unroll
-        for (int h = 1; h < H; h++) if ((i >> 5) == h) x = w[h]; return (x >> (i & 31)) & 1u; }
-    __device__ __forceinline__ bool mine(int h, int lane) const { return (w[h] >> lane) & 1u; }   // h compile-time
-    __device__ __forceinline__ int first() const {
-        int r = -1;
-#pragma unroll
-        for (int h = H - 1; h >= 0; h--) if (w[h]) r = 32 * h + __ffs(w[h]) - 1;
-        return r; }
-    __device__ __forceinline__ void reset(int i) {
-#pragma unroll
-        for (int h = 0; h < H; h++) if ((i >> 5) == h) w[h] &= ~(1u << (i & 31)); }
-    __device__ __forceinline__ void set(int i) {
-#pragma unroll
-        for (int h = 0; h < H; h++) if ((i >> 5) == h) w[h] |= 1u << (i & 31); }
-    __device__ __forceinline__ bool equals(const Bits &o) const { bool e = true;
-#pragma unroll
-        for (int h = 0; h < H; h++) e &= (w[h] == o.w[h]); return e; }
-};
-template <int H> __device__ __forceinline__ Bits<H> operator&(const Bits<H> &a, const Bits<H> &b) { Bits<H> r; for (int h = 0; h < H; h++) r.w[h] = a.w[h] & b.w[h]; return r; }
-template <int H> __device__ __forceinline__ Bits<H> andnot(const Bits<H> &a, const Bits<H> &b) { Bits<H> r; for (int h = 0; h < H; h++) r.w[h] = a.w[h] & ~b.w[h]; return r; }
-
-// value owned by lane (idx & 31), slot (idx >> 5); idx is warp-uniform
-template <int H>
-__device__ __forceinline__ double fetch_d(const double (&v)[H], int idx)
-{
-    double r = __shfl_sync(FULL, v[0], idx & 31);
-    if (H > 1) { const double r1 = __shfl_sync(FULL, v[H - 1], idx & 31); if (idx >> 5) r = r1; }
-    return r;
-}
-template <int H>
-__device__ __forceinline__ int fetch_i(const int (&v)[H], int idx)
-{
-    int r = __shfl_sync(FULL, v[0], idx & 31);
-    if (H > 1) { const int r1 = __shfl_sync(FULL, v[H - 1], idx & 31); if (idx >> 5) r = r1; }
-    return r;
-}
-template <int H>
-__device__ __forceinline__ Bits<H> fetch_bits(const Bits<H> (&v)[H], int idx)
-{
-    Bits<H> r;
-    for (int k = 0; k < H; k++) {
-        uint32_t x = __shfl_sync(FULL, v[0].w[k], idx & 31);
-        if (H > 1) { const uint32_t x1 = __shfl_sync(FULL, v[H - 1].w[k], idx & 31); if (idx >> 5) x = x1; }
-        r.w[k] = x;
-    }
-    return r;
-}
-
-template <int H>
-__device__ __forceinline__ void owner_store(double (&v)[H], int idx, int lane, double val)
-{
-#pragma unroll
-    for (int h = 0; h < H; h++) if ((idx >> 5) == h && lane == (idx & 31)) v[h] = val;
-}
-template <int H>
-__device__ __forceinline__ void owner_sub(double (&v)[H], int idx, int lane, double val)
-{
-#pragma unroll
-    for (int h = 0; h < H; h++) if ((idx >> 5) == h && lane == (idx & 31)) v[h] -= val;
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-    return v;
-}
-
-__device__ __forceinline__ int find_id(const uint32_t *arr, int n, uint32_t key)
-{
-    int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (arr[mid] < key) lo = mid + 1; else hi = mid; }
-    return (lo < n && arr[lo] == key) ? lo : -1;
-}
-
-__device__ __forceinline__ int64_t tri_row_start(int64_t i, int64_t N) { return i * N - i * (i + 1) / 2; }
-
-template <int H, int W>
-struct WarpSmem {
-    static constexpr int CAP = 32 * H, FS = CAP + 1;
-    double flow[CAP * FS];
-    double lenB[CAP];
-    uint64_t maskB[CAP * W];
-    uint32_t idA[CAP], idB[CAP];
-    uint32_t stack[CAP + 2][2 * H];
-};
+using namespace geo;
 
 template <int H, int W>
 __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParams p)
 {
-    constexpr int CAP = 32 * H, FS = CAP + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem<H, W> &sm = reinterpret_cast<WarpSmem<H, W> *>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    unsigned long long st_pairs = 0, st_flows = 0, st_ratios = 0, st_aug = 0;
+    Counters st;
     bool failed = false;
 
     for (;;) {
@@ -155,7 +52,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
             while (i > 0 && tri_row_start(i, p.N) > pidx) i--;
             ti = i; tj = pidx - tri_row_start(i, p.N) + i + 1;
         }
-        st_pairs++;
+        st.pairs++;
 
         // ---- 1. leaf term + load both trees' split lists ---------------------------------------------------------
         double part = 0.0;     // per-lane partial of common + extended-common + leaf terms
@@ -195,189 +92,8 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
             setA.w[h] = __ballot_sync(FULL, ncA); setB.w[h] = __ballot_sync(FULL, ncB);
         }
 
-        // ---- 3. incompatibility bit matrix: inc[h] row of my split a over B; incT[h] row of my split b over A ----
-        Bits<H> inc[H], incT[H];
-#pragma unroll
-        for (int h = 0; h < H; h++) { inc[h].clear(); incT[h].clear(); }
-        {
-            Bits<H> it = setB;
-            while (it.any()) {
-                const int b = it.first(); it.reset(b);
-                uint64_t mb[W];
-#pragma unroll
-                for (int w = 0; w < W; w++) mb[w] = sm.maskB[b * W + w];
-#pragma unroll
-                for (int h = 0; h < H; h++) {
-                    bool disjoint = true, asub = true, bsub = true;
-#pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        const uint64_t x = mA[h][w] & mb[w];
-                        disjoint &= (x == 0); asub &= (x == mA[h][w]); bsub &= (x == mb[w]);
-                    }
-                    const bool incompatible = setA.mine(h, lane) && !(disjoint || asub || bsub);
-                    if (incompatible) inc[h].set(b);
-                    const uint32_t col = __ballot_sync(FULL, incompatible);     // column b over A, half h
-#pragma unroll
-                    for (int hb = 0; hb < H; hb++) if ((b >> 5) == hb && lane == (b & 31)) incT[hb].w[h] = col;
-                }
-            }
-        }
-        // ---- 4. extended common-edge rule ------------------------------------------------------------------------
-#pragma unroll
-        for (int h = 0; h < H; h++) {
-            const bool extA = setA.mine(h, lane) && !inc[h].any();
-            const bool extB = setB.mine(h, lane) && !incT[h].any();
-            if (extA) part += la2[h];
-            if (extB) part += lb2[h];
-            setA.w[h] &= ~__ballot_sync(FULL, extA); setB.w[h] &= ~__ballot_sync(FULL, extB);
-        }
-
-        // ---- 5. GTP ----------------------------------------------------------------------------------------------
-        double total = 0.0;
-        int sp = 0;
-        if (setA.any() && setB.any()) {
-            if (lane == 0) { for (int h = 0; h < H; h++) { sm.stack[0][h] = setA.w[h]; sm.stack[0][H + h] = setB.w[h]; } }
-            sp = 1;
-        }
-        __syncwarp();
-        int guard = 0;
-        while (sp > 0) {
-            sp--;
-            Bits<H> RA, RB;
-            for (int h = 0; h < H; h++) { RA.w[h] = sm.stack[sp][h]; RB.w[h] = sm.stack[sp][H + h]; }
-            __syncwarp();
-            double sa = 0.0, sb = 0.0;
-#pragma unroll
-            for (int h = 0; h < H; h++) { if (RA.mine(h, lane)) sa += la2[h]; if (RB.mine(h, lane)) sb += lb2[h]; }
-            sa = warp_sum(sa); sb = warp_sum(sb);
-            bool split = false;
-            Bits<H> CA, CB; CA.clear(); CB.clear();
-            if (RA.count() + RB.count() > 2 && sa > 0.0 && sb > 0.0) {
-                st_flows++;
-                // vertex weights -> residual capacities of the source / sink edges
-                double ra[H], rb[H], wa[H], wb[H];
-#pragma unroll
-                for (int h = 0; h < H; h++) {
-                    wa[h] = RA.mine(h, lane) ? la2[h] / sa : 0.0;
-                    wb[h] = RB.mine(h, lane) ? lb2[h] / sb : 0.0;
-                    ra[h] = wa[h]; rb[h] = wb[h];
-                    if (RA.mine(h, lane)) {                             // zero my row of the flow matrix (only edges of the graph)
-                        Bits<H> nb = inc[h] & RB;
-                        while (nb.any()) { const int b = nb.first(); nb.reset(b); sm.flow[(lane + 32 * h) * FS + b] = 0.0; }
-                    }
-                }
-                __syncwarp();
-                // greedy saturation: push every source edge into its neighbours' sink edges, in split order
-                {
-                    Bits<H> it = RA;
-                    while (it.any()) {
-                        const int a = it.first(); it.reset(a);
-                        double x = fetch_d<H>(ra, a);
-                        const Bits<H> nbm = fetch_bits<H>(inc, a) & RB;
-#pragma unroll
-                        for (int h = 0; h < H; h++) {
-                            if (!(x > FLOW_TOL) || nbm.w[h] == 0) continue;       // warp-uniform
-                            const double avail = ((nbm.w[h] >> lane) & 1u) ? rb[h] : 0.0;
-                            double incl = avail;
-#pragma unroll
-                            for (int d = 1; d < 32; d <<= 1) { const double t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-                            const double tot = __shfl_sync(FULL, incl, 31);
-                            const double take = fmin(avail, fmax(0.0, x - (incl - avail)));
-                            if (take > 0.0) { rb[h] -= take; sm.flow[a * FS + lane + 32 * h] = take; }
-                            x = fmax(0.0, x - tot);
-                        }
-                        owner_store<H>(ra, a, lane, x);
-                    }
-                }
-                __syncwarp();
-                // augmenting paths by BFS over warp-uniform frontier bitmasks
-                Bits<H> visA, visB;
-                for (;;) {
-                    if (++guard > 20000) { failed = true; break; }
-                    int parA[H], parB[H];
-                    Bits<H> frontA;
-#pragma unroll
-                    for (int h = 0; h < H; h++) { parA[h] = -1; parB[h] = -1; frontA.w[h] = __ballot_sync(FULL, ra[h] > FLOW_TOL); }
-                    visA = frontA; visB.clear();
-                    int sink = -1;
-                    while (frontA.any()) {
-                        Bits<H> newB; bool mine_sink[H];
-#pragma unroll
-                        for (int h = 0; h < H; h++) {
-                            const Bits<H> reach = incT[h] & frontA;
-                            const bool nb = RB.mine(h, lane) && !visB.mine(h, lane) && reach.any();
-                            if (nb) parB[h] = reach.first();
-                            newB.w[h] = __ballot_sync(FULL, nb);
-                            mine_sink[h] = nb && rb[h] > FLOW_TOL;
-                        }
-                        if (!newB.any()) break;
-#pragma unroll
-                        for (int h = 0; h < H; h++) visB.w[h] |= newB.w[h];
-                        Bits<H> sinks;
-#pragma unroll
-                        for (int h = 0; h < H; h++) sinks.w[h] = __ballot_sync(FULL, mine_sink[h]);
-                        if (sinks.any()) { sink = sinks.first(); break; }
-                        // B -> A through edges that carry flow
-                        Bits<H> newA;
-#pragma unroll
-                        for (int h = 0; h < H; h++) {
-                            const int s = lane + 32 * h;
-                            bool found = false;
-                            if (RA.mine(h, lane) && !visA.mine(h, lane)) {
-                                Bits<H> cand = inc[h] & newB;
-                                while (cand.any()) { const int b = cand.first(); cand.reset(b); if (sm.flow[s * FS + b] > FLOW_TOL) { parA[h] = b; found = true; break; } }
-                            }
-                            newA.w[h] = __ballot_sync(FULL, found);
-                        }
-#pragma unroll
-                        for (int h = 0; h < H; h++) visA.w[h] |= newA.w[h];
-                        frontA = newA;
-                    }
-                    if (sink < 0) break;            // no augmenting path: (visA, visB) is the source side of a min cut
-                    st_aug++;
-                    // bottleneck along sink <- ... <- source
-                    double delta = fetch_d<H>(rb, sink);
-                    int b = sink;
-                    for (int hop = 0; hop < 2 * CAP + 2; hop++) {
-                        const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
-                        if (pb < 0) { delta = fmin(delta, fetch_d<H>(ra, a)); break; }
-                        delta = fmin(delta, sm.flow[a * FS + pb]); b = pb;
-                    }
-                    owner_sub<H>(rb, sink, lane, delta);
-                    b = sink;
-                    for (int hop = 0; hop < 2 * CAP + 2; hop++) {
-                        const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
-                        if (lane == 0) sm.flow[a * FS + b] += delta;
-                        if (pb < 0) { owner_sub<H>(ra, a, lane, delta); break; }
-                        if (lane == 0) sm.flow[a * FS + pb] -= delta;
-                        b = pb;
-                    }
-                    __syncwarp();
-                }
-                if (failed) break;
-                // min-weight vertex cover = (A not reachable) + (B reachable)
-                CA = andnot(RA, visA); CB = visB & RB;
-                double cw = 0.0;
-#pragma unroll
-                for (int h = 0; h < H; h++) { if (CA.mine(h, lane)) cw += wa[h]; if (CB.mine(h, lane)) cw += wb[h]; }
-                cw = warp_sum(cw);
-                split = cw < 1.0 - SPLIT_TOL && CA.any() && !CA.equals(RA) && CB.any() && !CB.equals(RB);
-            }
-            if (split) {
-                // (C&A, B\C) precedes (A\C, C&B) in the ratio sequence; the sum does not depend on the order
-                if (lane == 0) {
-                    for (int h = 0; h < H; h++) {
-                        sm.stack[sp][h] = RA.w[h] & ~CA.w[h]; sm.stack[sp][H + h] = CB.w[h];
-                        sm.stack[sp + 1][h] = CA.w[h]; sm.stack[sp + 1][H + h] = RB.w[h] & ~CB.w[h];
-                    }
-                }
-                sp += 2;
-                __syncwarp();
-            } else {
-                const double s = sqrt(sa) + sqrt(sb);
-                total = fma(s, s, total); st_ratios++;
-            }
-        }
+        // ---- 3-5. incompatibilities, extended common edges, GTP ratio sequence (geo_core.cuh) ---------------------
+        const double total = gtp_noncommon<H, W>(sm, mA, setA, setB, la2, lb2, lane, part, st, failed);
         part = warp_sum(part);
         if (lane == 0) {
             double d = sqrt(part + total);
@@ -385,11 +101,11 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
             if (failed) d = __longlong_as_double(0x7ff8000000000000ll);
             p.out[pidx - p.p_base] = d;
         }
-        if (failed) { if (lane == 0) atomicExch(p.error_flag, 1); failed = false; }
+        if (failed) { if (lane == 0) atomicOr(p.error_flag, 1); failed = false; }
     }
     if (lane == 0 && p.stats) {
-        atomicAdd(&p.stats[0], st_pairs); atomicAdd(&p.stats[1], st_flows);
-        atomicAdd(&p.stats[2], st_ratios); atomicAdd(&p.stats[3], st_aug);
+        atomicAdd(&p.stats[0], st.pairs); atomicAdd(&p.stats[1], st.flows);
+        atomicAdd(&p.stats[2], st.ratios); atomicAdd(&p.stats[3], st.aug);
     }
 }
 
