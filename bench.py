@@ -259,7 +259,7 @@ def run_ours(args):
                        'dict_size': int(info.dict_size), 'dict_shared': int(info.dict_shared), 'max_shared': int(info.max_shared)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
-                         'algorithmic_bytes_per_launch': alg, 'kernel': 'pairwise_kernel<{}>'.format('|'.join(METRICS))},
+                         'algorithmic_bytes_per_launch': alg, 'kernel': 'pairjoin_persistent<{}> (tile hash join + fp64 leaf GEMM)'.format('|'.join(METRICS))},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(h2d_bytes),
                     'd2h_bytes_per_step': int(my_pairs * 8 * len(METRICS)),

@@ -140,7 +140,7 @@ def pair_kernel(request, monkeypatch):
 
 @pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
 @pytest.mark.parametrize('norm', [False, True])
-@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile'], indirect=True)
 def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_kernel):
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)

@@ -17,6 +17,8 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_counter_add(uint64_t n) { return g_launches.fetch_add(n) + n; }
 
 constexpr int kCounters = 64;
+constexpr int kWorklists = 8;
+constexpr unsigned kWorklistCap = 1u << 20;
 
 struct DeviceSet {
     int device = -1, sm_count = 148;
@@ -32,6 +34,9 @@ struct DeviceSet {
     int32_t *rooted = nullptr;
     unsigned long long *work_counter = nullptr, *stats = nullptr;   // work_counter: ring of kCounters, one per launch in flight
     std::atomic<uint32_t> next_counter{0};
+    int2 *wl_pairs = nullptr;          // kWorklists rings of kWorklistCap pairs for the persistent hash-join kernel
+    unsigned *wl_count = nullptr;
+    std::atomic<uint32_t> next_worklist{0};
     int *error_flag = nullptr;
     size_t max_smem_optin = 0;
     td_geo_stats geo_stats{};
@@ -109,6 +114,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     if ((rc = dev_alloc(d, &d->work_counter, kCounters))) return rc;
     if ((rc = dev_alloc(d, &d->stats, 4))) return rc;
     if ((rc = dev_alloc(d, &d->error_flag, 1))) return rc;
+    if ((rc = dev_alloc(d, &d->wl_pairs, (size_t)kWorklists * kWorklistCap))) return rc;
+    if ((rc = dev_alloc(d, &d->wl_count, kWorklists))) return rc;
 
     CUDA_TRY(cudaMemsetAsync(d->leafT, 0, (size_t)d->n_k * Npad * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(d->nsplits, 0, Npad * sizeof(int32_t), st));
@@ -225,7 +232,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         const bool join_fits = h.max_shared <= 255 && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         bool use_join = join_fits && h.mean_common <= 6.0;
         if (force && !strcmp(force, "merge")) use_join = false;
-        if (force && !strcmp(force, "join") && join_fits) use_join = true;
+        if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) use_join = true;
         const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
@@ -247,9 +254,14 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         p.tile_row0 = (int)(row_begin / tile);
         const int64_t tile_rows = (row_end + tile - 1) / tile - p.tile_row0;
         if (tile_rows > 0 && tile_cols > 0) {
-            if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, st));
+            if (use_join) {
+                const uint32_t w = d->next_worklist.fetch_add(1) % kWorklists;
+                p.wl_pairs = d->wl_pairs + (size_t)w * kWorklistCap; p.wl_count = d->wl_count + w; p.wl_capacity = kWorklistCap;
+                CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
+            }
+            if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
             else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
-            launch_counter_add(1);
+            launch_counter_add(use_join && weighted ? 2 : 1);
         }
     }
     if (mask & TD_MASK(TD_GEO)) {

@@ -18,6 +18,9 @@ struct PairParams {
     const double *sum_len, *norm, *single_l1, *single_l2;   // [Npad]
     const double *q1, *q2;    // [Npad] totals over ALL internal edges: sum |l|, sum l^2 (hash-join kernel)
     int table_slots, tiles_x; // hash-join kernel: power-of-two table size; tile columns of the grid
+    long long n_tiles;        // persistent hash-join kernel: length of the tile list
+    int2 *wl_pairs;           // persistent hash-join kernel: pairs to recompute exactly (work list)
+    unsigned *wl_count; unsigned wl_capacity;
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
     int64_t row_begin, row_end, p_base;
@@ -33,7 +36,7 @@ cudaError_t launch_pairwise(uint32_t mask, bool rect, PairParams p, int64_t tile
                             cudaStream_t st);
 int pairjoin_table_slots(int max_shared);
 size_t pairjoin_smem_bytes(uint32_t mask, int table_slots);
-cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, cudaStream_t st);
+cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
 
 struct GeoParams {

@@ -293,6 +293,356 @@ __global__ void __launch_bounds__(NT, 3) pairjoin_kernel(const PairParams p)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version.  384 threads: warps 0-7 are CONSUMERS (leaf GEMM + epilogue of tile t), warps
+// 8-11 are PRODUCERS (hash join of tile t+1: table init, build, probe into the per-cell slots).  Here the probe runs
+// over ALL entries of the 64 row trees in parallel and accumulates with shared-memory atomics.  That keeps results
+// reproducible because (a) the counts are integers, (b) a cell that received one or two corrections holds their exact
+// commutative sum, and (c) cells with three or more corrections - or with a correction that nearly cancels Q_i + Q_j -
+// are queued on a work list and recomputed by exact_fixup_kernel with the additive merge (fixed order).
+// Each CTA walks a contiguous range of the tile list; the two groups hand the per-cell slots over with named barriers:
+//   FULL  (producers arrive, consumers wait): slots of the next tile are complete
+//   EMPTY (consumers arrive, producers wait): consumers have copied their cells to registers and cleared them
+// so the join of the next tile runs under the fp64 work of the current one and no warp waits at a CTA-wide barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NCONS = 256, NPROD = 128, NTP = NCONS + NPROD;
+constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_PROD = 3, BAR_CONS = 4;
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool RECT>
+__device__ __forceinline__ void decode_tile(const PairParams &p, long long t, int &tile_r, int &tile_c)
+{
+    if (RECT) {
+        tile_r = (int)(t / p.tiles_x) + p.tile_row0;
+        tile_c = (int)(t % p.tiles_x) + p.col_tile0;
+    } else {
+        const long long L0 = p.tiles_x - 2 * p.tile_row0;
+        const double b = (double)L0 + 1.0;
+        long long u = (long long)floor((b - sqrt(b * b - 4.0 * (double)t)) * 0.5);
+        if (u < 0) u = 0;
+        while (u * L0 - u * (u - 1) > t) u--;
+        while ((u + 1) * L0 - (u + 1) * u <= t) u++;
+        tile_r = (int)u + p.tile_row0;
+        tile_c = 2 * tile_r + (int)(t - (u * L0 - u * (u - 1)));
+    }
+}
+
+template <uint32_t MASK, bool RECT>
+__global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p)
+{
+    constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
+    constexpr bool kWeighted = kWRF || kEUC;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t slots = p.table_slots, smask = slots - 1;
+    unsigned char *cur = smem_raw;
+    double *tab_len = nullptr, *E1 = nullptr, *E2 = nullptr, *leaf = nullptr;
+    if constexpr (kWeighted) { tab_len = reinterpret_cast<double *>(cur); cur += (size_t)slots * sizeof(double); }
+    if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
+    if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
+    if constexpr (kWeighted) { leaf = reinterpret_cast<double *>(cur); cur += 2 * KC * (TR + TC) * sizeof(double); }
+    uint32_t *tab_id = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);
+    unsigned char *tab_col = cur; cur += slots;
+    unsigned char *cnt = cur;
+
+    const int tid = threadIdx.x;
+    const long long t_begin = p.n_tiles * (long long)blockIdx.x / gridDim.x;
+    const long long t_end = p.n_tiles * ((long long)blockIdx.x + 1) / gridDim.x;
+
+    // per-cell slots start cleared; afterwards every consumer clears the cells it has just read
+    {
+        if constexpr (kWRF) { double2 *z = reinterpret_cast<double2 *>(E1); for (int e = tid; e < TR * TC / 2; e += NTP) z[e] = make_double2(0.0, 0.0); }
+        if constexpr (kEUC) { double2 *z = reinterpret_cast<double2 *>(E2); for (int e = tid; e < TR * TC / 2; e += NTP) z[e] = make_double2(0.0, 0.0); }
+        uint32_t *z = reinterpret_cast<uint32_t *>(cnt);
+        for (int e = tid; e < TR * TC / 4; e += NTP) z[e] = 0u;
+    }
+    __syncthreads();
+    if (t_begin >= t_end) return;
+
+    if (tid >= NCONS) {
+        // ================================================= PRODUCERS ====================================================
+        // Lane mappings avoid divisions and keep every loop warp-uniform (all 32 lanes iterate together and vote with
+        // __any_sync), so the warps never split into per-thread paths:
+        //   build : thread -> column (ptid & 31), entries quarter (ptid >> 5) + 4k of that column tree
+        //   probe : thread -> row (ptid & 63), entries half (ptid >> 6) + 2k of that row tree
+        const int ptid = tid - NCONS;
+        uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
+        for (long long t = t_begin; t < t_end; t++) {
+            int tile_r, tile_c;
+            decode_tile<RECT>(p, t, tile_r, tile_c);
+            const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
+            // the table is private to the producers: rebuild it while the consumers still work on the previous tile
+            bar_sync(BAR_PROD, NPROD);           // every producer is done probing the previous table
+            {
+                uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);
+                for (uint32_t e = ptid; e < slots / 4; e += NPROD) t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            }
+            bar_sync(BAR_PROD, NPROD);
+            {
+                const int col = ptid & (TC - 1);
+                const int64_t j = j0 + col;
+                const int n = p.nshared[j];
+                const SplitRec *B = p.shared + j * p.sh_stride;
+                int pos = ptid >> 5;                                   // 0..3
+                while (__any_sync(0xffffffffu, pos < n)) {
+                    const bool have = pos < n;
+                    SplitRec b = have ? B[pos] : SplitRec{kSentinelId, 0, 0.0};
+                    uint32_t h = hash_id(b.id, smask);
+                    bool pending = have;
+                    while (__any_sync(0xffffffffu, pending)) {
+                        if (pending) {
+                            if (atomicCAS(&tab_id[h], kEmpty, b.id) == kEmpty) {
+                                tab_col[h] = (unsigned char)col;
+                                if constexpr (kWeighted) tab_len[h] = b.len;
+                                pending = false;
+                            } else h = (h + 1) & smask;
+                        }
+                    }
+                    pos += NPROD / TC;
+                }
+            }
+            bar_sync(BAR_PROD, NPROD);
+            bar_sync(BAR_EMPTY, NTP);            // consumers have released the slots of the previous tile
+            {
+                const int row = ptid & (TR - 1);
+                const int64_t i = i0 + row;
+                const int n = p.nshared[i];
+                const SplitRec *A = p.shared + i * p.sh_stride;
+                const int first_col = RECT ? 0 : (int)(i - j0) + 1;     // columns below are on or under the diagonal
+                int pos = ptid >> 6;                                   // 0..1
+                while (__any_sync(0xffffffffu, pos < n)) {
+                    const bool have = pos < n;
+                    const SplitRec a = have ? A[pos] : SplitRec{kSentinelId, 0, 0.0};
+                    uint32_t h = hash_id(a.id, smask);
+                    bool walking = have;
+                    while (__any_sync(0xffffffffu, walking)) {
+                        if (walking) {
+                            const uint32_t sid = tab_id[h];
+                            if (sid == kEmpty) walking = false;
+                            else {
+                                if (sid == a.id) {
+                                    const int col = tab_col[h];
+                                    if (col >= first_col) {
+                                        const int cell = row * TC + col;
+                                        atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
+                                        if constexpr (kWeighted) {
+                                            const double lb = tab_len[h];
+                                            if constexpr (kEUC) atomicAdd(&E2[cell], -2.0 * a.len * lb);
+                                            if constexpr (kWRF) atomicAdd(&E1[cell], fabs(a.len - lb) - fabs(a.len) - fabs(lb));
+                                        }
+                                    }
+                                }
+                                h = (h + 1) & smask;
+                            }
+                        }
+                    }
+                    pos += NPROD / TR;
+                }
+            }
+            __threadfence_block();
+            bar_arrive(BAR_FULL, NTP);
+        }
+        return;
+    }
+
+    // ===================================================== CONSUMERS ========================================================
+    const int tx = tid % 16, ty = tid / 16;
+    bar_arrive(BAR_EMPTY, NTP);                 // initial credit: the slots are free
+    for (long long t = t_begin; t < t_end; t++) {
+        int tile_r, tile_c;
+        decode_tile<RECT>(p, t, tile_r, tile_c);
+        const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
+
+        const int n_chunks = kWeighted ? p.n_k / KC : 0;
+        auto load_chunk = [&](int chunk, int stage) {
+            double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
+            constexpr int PA = KC * TR / 2, PB = KC * TC / 2;
+            for (int e = tid; e < PA + PB; e += NCONS) {
+                if (e < PA) {
+                    const int kk = e / (TR / 2), c2 = e % (TR / 2);
+                    cp_async16(sA + kk * TR + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + i0 + 2 * c2);
+                } else {
+                    const int f = e - PA, kk = f / (TC / 2), c2 = f % (TC / 2);
+                    cp_async16(sB + kk * TC + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + j0 + 2 * c2);
+                }
+            }
+        };
+        if constexpr (kWeighted) {
+            if (n_chunks > 0) load_chunk(0, 0);
+            cp_async_commit();
+            if (n_chunks > 1) load_chunk(1, 1);
+            cp_async_commit();
+        }
+
+        // per-tree scalars of my rows / columns (global, L1/L2 hits) while the producers finish the join
+        int si[4], sj[2]; double q1i[4], q2i[4], q1j[2], q2j[2];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int64_t i = i0 + 4 * ty + r;
+            si[r] = p.nsplits[i];
+            if constexpr (kWRF) q1i[r] = p.q1[i];
+            if constexpr (kEUC) q2i[r] = p.q2[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int64_t j = j0 + tx + 16 * c;
+            sj[c] = p.nsplits[j];
+            if constexpr (kWRF) q1j[c] = p.q1[j];
+            if constexpr (kEUC) q2j[c] = p.q2[j];
+        }
+
+        bar_sync(BAR_FULL, NTP);                 // slots of this tile are complete
+        double acc1[4][2], acc2[4][2];
+        int common[4][2];
+        uint32_t risky = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int cell = (4 * ty + r) * TC + tx + 16 * c;
+                common[r][c] = cnt[cell]; cnt[cell] = 0;
+                acc1[r][c] = 0.0; acc2[r][c] = 0.0;
+                bool rk = false;
+                if constexpr (kWRF) { acc1[r][c] = E1[cell]; E1[cell] = 0.0; rk |= (-acc1[r][c] > kRisk * (q1i[r] + q1j[c])); }
+                if constexpr (kEUC) { acc2[r][c] = E2[cell]; E2[cell] = 0.0; rk |= (-acc2[r][c] > kRisk * (q2i[r] + q2j[c])); }
+                if constexpr (kWeighted) rk |= common[r][c] >= 3;     // sum order of >= 3 atomic adds is not fixed
+                risky |= (rk ? 1u : 0u) << (2 * r + c);
+            }
+        if (t + 1 < t_end) { __threadfence_block(); bar_arrive(BAR_EMPTY, NTP); }    // producers may fill the next tile
+
+        if constexpr (kWeighted) {
+            for (int chunk = 0; chunk < n_chunks; chunk++) {
+                const int stage = chunk & 1;
+                cp_async_wait<1>();
+                bar_sync(BAR_CONS, NCONS);
+                const double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
+#pragma unroll
+                for (int kk = 0; kk < KC; kk++) {
+                    const double2 a01 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty + 2);
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double bv[2] = {sB[kk * TC + tx], sB[kk * TC + tx + 16]};
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            const double d = av[r] - bv[c];
+                            if constexpr (kWRF) acc1[r][c] += fabs(d);
+                            if constexpr (kEUC) acc2[r][c] = fma(d, d, acc2[r][c]);
+                        }
+                }
+                bar_sync(BAR_CONS, NCONS);
+                if (chunk + 2 < n_chunks) load_chunk(chunk + 2, stage);
+                cp_async_commit();
+            }
+        }
+
+        // epilogue
+        double sumj[2], normj[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int64_t j = j0 + tx + 16 * c;
+            if constexpr (kWRF) sumj[c] = p.sum_len[j];
+            if constexpr (kEUC) normj[c] = p.norm[j];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int64_t i = i0 + 4 * ty + r;
+            if (i < p.row_begin || i >= p.row_end) continue;
+            double sumi = 0, normi = 0;
+            if constexpr (kWRF) sumi = p.sum_len[i];
+            if constexpr (kEUC) normi = p.norm[i];
+            const int64_t row_off = RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int64_t j = j0 + tx + 16 * c;
+                if (j >= p.col_end || (RECT ? j < p.col_offset : j <= i)) continue;
+                const int64_t idx = row_off + j;
+                if constexpr (kRF) {
+                    const int den = si[r] + sj[c];
+                    double v = (double)(den - 2 * common[r][c]);
+                    if (p.normalise) v = den ? v / (double)den : 0.0;
+                    p.out[0][idx] = v;
+                }
+                if constexpr (kWeighted) {
+                    double t1 = 0.0, t2 = 0.0;
+                    if constexpr (kWRF) t1 = (q1i[r] + q1j[c]) + acc1[r][c];
+                    if constexpr (kEUC) t2 = (q2i[r] + q2j[c]) + acc2[r][c];
+                    if (risky >> (2 * r + c) & 1u) {
+                        // recomputed exactly by exact_fixup_kernel (same stream, right after this kernel)
+                        const unsigned slot = atomicAdd(p.wl_count, 1u);
+                        if (slot < p.wl_capacity) p.wl_pairs[slot] = make_int2((int)i, (int)j);
+                        else exact_pair(p, i, j, t1, t2);
+                    }
+                    if constexpr (kWRF) {
+                        double v = t1;
+                        if (p.normalise) { const double den = sumi + sumj[c]; v = den != 0.0 ? v / den : 0.0; }
+                        p.out[1][idx] = v;
+                    }
+                    if constexpr (kEUC) {
+                        double v = sqrt(t2);
+                        if (p.normalise) { const double den = normi + normj[c]; v = den != 0.0 ? v / den : 0.0; }
+                        p.out[2][idx] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+
+// Recompute the queued pairs with the additive merge (exact_pair) and overwrite their wrf / euc entries.
+template <bool RECT>
+__global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, const uint32_t mask)
+{
+    const unsigned n = min(*p.wl_count, p.wl_capacity);
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        const int2 ij = p.wl_pairs[w];
+        const int64_t i = ij.x, j = ij.y;
+        double t1, t2;
+        exact_pair(p, i, j, t1, t2);
+        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
+        if (mask & 2u) {
+            double v = t1;
+            if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
+            p.out[1][idx] = v;
+        }
+        if (mask & 4u) {
+            double v = sqrt(t2);
+            if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
+            p.out[2][idx] = v;
+        }
+    }
+}
+
+template <uint32_t MASK, bool RECT>
+cudaError_t launch_one_persistent(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    auto k = pairjoin_persistent<MASK, RECT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, NTP, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool RECT>
+cudaError_t launch_mask_persistent(uint32_t mask, const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    switch (mask & 7u) {
+        case 1: return launch_one_persistent<1, RECT>(p, grid, smem, st);
+        case 2: return launch_one_persistent<2, RECT>(p, grid, smem, st);
+        case 3: return launch_one_persistent<3, RECT>(p, grid, smem, st);
+        case 4: return launch_one_persistent<4, RECT>(p, grid, smem, st);
+        case 5: return launch_one_persistent<5, RECT>(p, grid, smem, st);
+        case 6: return launch_one_persistent<6, RECT>(p, grid, smem, st);
+        case 7: return launch_one_persistent<7, RECT>(p, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <uint32_t MASK, bool RECT>
 cudaError_t launch_one(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
@@ -337,7 +687,7 @@ size_t pairjoin_smem_bytes(uint32_t mask, int table_slots)
 }
 
 // Triangular: rows [row_begin,row_end) -> 64-row tiles from p.tile_row0 (set here); rect: rows [0,row_end), columns from `split`.
-cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, cudaStream_t st)
+cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st)
 {
     const size_t smem = pairjoin_smem_bytes(mask, p.table_slots);
     const int64_t col_tiles_total = (p.N + TC - 1) / TC;
@@ -358,6 +708,17 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, cudaStream_t
         grid = rows * L0 - rows * (rows - 1);
     }
     if (grid <= 0) return cudaSuccess;
+    if (persistent) {
+        p.n_tiles = grid;
+        int64_t ctas = 2 * (int64_t)n_sms;                    // two 384-thread CTAs per SM
+        if (ctas > grid) ctas = grid;
+        cudaError_t e = rect ? launch_mask_persistent<true>(mask, p, (unsigned)ctas, smem, st)
+                             : launch_mask_persistent<false>(mask, p, (unsigned)ctas, smem, st);
+        if (e != cudaSuccess || !(mask & 6u)) return e;
+        if (rect) exact_fixup_kernel<true><<<2 * n_sms, 128, 0, st>>>(p, mask);
+        else exact_fixup_kernel<false><<<2 * n_sms, 128, 0, st>>>(p, mask);
+        return cudaGetLastError();
+    }
     return rect ? launch_mask<true>(mask, p, (unsigned)grid, smem, st) : launch_mask<false>(mask, p, (unsigned)grid, smem, st);
 }
 
