@@ -229,7 +229,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         // kernel choice: sparse sharing -> tile hash join (work ~ entries + matches); dense sharing -> merge-join
         const int slots = pairjoin_table_slots(h.max_shared);
         const char *force = getenv("TREEDIST_PAIR_KERNEL");
-        const bool join_fits = h.max_shared <= 255 && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
+        const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         bool use_join = join_fits && h.mean_common <= 6.0;
         if (force && !strcmp(force, "merge")) use_join = false;
         if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) use_join = true;

@@ -36,6 +36,7 @@ cudaError_t launch_pairwise(uint32_t mask, bool rect, PairParams p, int64_t tile
                             cudaStream_t st);
 int pairjoin_table_slots(int max_shared);
 size_t pairjoin_smem_bytes(uint32_t mask, int table_slots);
+size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_stride);
 cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
 

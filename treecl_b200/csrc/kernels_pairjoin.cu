@@ -308,6 +308,37 @@ __global__ void __launch_bounds__(NT, 3) pairjoin_kernel(const PairParams p)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int NCONS = 256, NPROD = 128, NTP = NCONS + NPROD;
 constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_PROD = 3, BAR_CONS = 4;
+constexpr uint32_t kEventCap = 2048;
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(32);                           // do not burn issue slots that the consumer warps need
+        if (spins > (1u << 24)) __trap();          // watchdog: never hang the GPU on a lost transaction
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -339,14 +370,18 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t slots = p.table_slots, smask = slots - 1;
     unsigned char *cur = smem_raw;
-    double *tab_len = nullptr, *E1 = nullptr, *E2 = nullptr, *leaf = nullptr;
-    if constexpr (kWeighted) { tab_len = reinterpret_cast<double *>(cur); cur += (size_t)slots * sizeof(double); }
+    double *E1 = nullptr, *E2 = nullptr, *leaf = nullptr;
     if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
     if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
     if constexpr (kWeighted) { leaf = reinterpret_cast<double *>(cur); cur += 2 * KC * (TR + TC) * sizeof(double); }
-    uint32_t *tab_id = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);
-    unsigned char *tab_col = cur; cur += slots;
-    unsigned char *cnt = cur;
+    uint32_t *tab_id = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);      // split id or kEmpty
+    uint32_t *tab_mask = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);    // column trees holding it
+    unsigned char *cnt = cur; cur += TR * TC;
+    SplitRec *stageA = reinterpret_cast<SplitRec *>(cur); cur += (size_t)TR * p.sh_stride * sizeof(SplitRec);   // row trees' lists
+    SplitRec *stageB = reinterpret_cast<SplitRec *>(cur); cur += (size_t)TC * p.sh_stride * sizeof(SplitRec);   // column trees' lists
+    uint32_t *events = reinterpret_cast<uint32_t *>(cur); cur += kEventCap * sizeof(uint32_t);          // row | col<<8 | pos<<16
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(cur); cur += 8;
+    uint32_t *ev_count = reinterpret_cast<uint32_t *>(cur);
 
     const int tid = threadIdx.x;
     const long long t_begin = p.n_tiles * (long long)blockIdx.x / gridDim.x;
@@ -359,88 +394,112 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
         uint32_t *z = reinterpret_cast<uint32_t *>(cnt);
         for (int e = tid; e < TR * TC / 4; e += NTP) z[e] = 0u;
     }
+    if (tid == NCONS) mbar_init(mbar, 1);
     __syncthreads();
     if (t_begin >= t_end) return;
 
     if (tid >= NCONS) {
         // ================================================= PRODUCERS ====================================================
-        // Lane mappings avoid divisions and keep every loop warp-uniform (all 32 lanes iterate together and vote with
-        // __any_sync), so the warps never split into per-thread paths:
-        //   build : thread -> column (ptid & 31), entries quarter (ptid >> 5) + 4k of that column tree
-        //   probe : thread -> row (ptid & 63), entries half (ptid >> 6) + 2k of that row tree
+        // Per tile: (1) TMA bulk copies stage the column trees' lists (and, when the tile row changes, the row trees')
+        // in shared memory, completing on an mbarrier; (2) build: table id -> 32-bit mask of the column trees that hold
+        // the split (atomicCAS claims / finds the slot, atomicOr sets the column bit), so every split occupies ONE slot;
+        // (3) probe: each row-tree entry finds its slot in ~1 step; matches become events (row, col, pos) in a queue;
+        // (4) events: all producer threads resolve the queue in parallel - binary search of the partner length in the
+        // column tree's staged list, then shared-memory atomics on the cell.  In (2) and (3) every lane advances through
+        // its own entries independently inside one warp-uniform loop, so a long chain in one lane does not stall the others.
         const int ptid = tid - NCONS;
         uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
+        uint32_t parity = 0;
+        int staged_row = -1;
+        const int stride = p.sh_stride;
+        const uint32_t bytesA = (uint32_t)(TR * stride * sizeof(SplitRec)), bytesB = (uint32_t)(TC * stride * sizeof(SplitRec));
+        auto resolve = [&](uint32_t ev) {
+            const int row = ev & 0xFF, col = (ev >> 8) & 0xFF, pos = ev >> 16;
+            const int cell = row * TC + col;
+            atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
+            if constexpr (kWeighted) {
+                const SplitRec a = stageA[(size_t)row * stride + pos];
+                const SplitRec *B = stageB + (size_t)col * stride;
+                int lo = 0, hi = stride - 1;                         // sentinels (0xFFFFFFFF) keep the padded list sorted
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid].id < a.id) lo = mid + 1; else hi = mid; }
+                const double lb = B[lo].len;
+                if constexpr (kEUC) atomicAdd(&E2[cell], -2.0 * a.len * lb);
+                if constexpr (kWRF) atomicAdd(&E1[cell], fabs(a.len - lb) - fabs(a.len) - fabs(lb));
+            }
+        };
         for (long long t = t_begin; t < t_end; t++) {
             int tile_r, tile_c;
             decode_tile<RECT>(p, t, tile_r, tile_c);
             const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
-            // the table is private to the producers: rebuild it while the consumers still work on the previous tile
-            bar_sync(BAR_PROD, NPROD);           // every producer is done probing the previous table
+            bar_sync(BAR_PROD, NPROD);           // every producer is done with the previous table, queue and staging buffers
+            if (ptid == 0) {
+                *ev_count = 0;
+                fence_proxy_async();             // generic-proxy reads of the staging buffers precede the async-proxy writes
+                mbar_expect_tx(mbar, bytesB + (tile_r != staged_row ? bytesA : 0u));
+                bulk_g2s(stageB, p.shared + j0 * stride, bytesB, mbar);
+                if (tile_r != staged_row) bulk_g2s(stageA, p.shared + i0 * stride, bytesA, mbar);
+            }
+            staged_row = tile_r;
             {
-                uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);
-                for (uint32_t e = ptid; e < slots / 4; e += NPROD) t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+                uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);           // ids then masks are contiguous
+                for (uint32_t e = ptid; e < slots / 4; e += NPROD) { t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty); t4[slots / 4 + e] = make_uint4(0, 0, 0, 0); }
             }
             bar_sync(BAR_PROD, NPROD);
+            mbar_wait(mbar, parity); parity ^= 1u;
+            // ---- build: thread -> column (ptid & 31), entries (ptid >> 5) + 4k ----------------------------------------------
             {
                 const int col = ptid & (TC - 1);
-                const int64_t j = j0 + col;
-                const int n = p.nshared[j];
-                const SplitRec *B = p.shared + j * p.sh_stride;
-                int pos = ptid >> 5;                                   // 0..3
-                while (__any_sync(0xffffffffu, pos < n)) {
-                    const bool have = pos < n;
-                    SplitRec b = have ? B[pos] : SplitRec{kSentinelId, 0, 0.0};
-                    uint32_t h = hash_id(b.id, smask);
-                    bool pending = have;
-                    while (__any_sync(0xffffffffu, pending)) {
-                        if (pending) {
-                            if (atomicCAS(&tab_id[h], kEmpty, b.id) == kEmpty) {
-                                tab_col[h] = (unsigned char)col;
-                                if constexpr (kWeighted) tab_len[h] = b.len;
-                                pending = false;
-                            } else h = (h + 1) & smask;
-                        }
+                const uint32_t *B = reinterpret_cast<const uint32_t *>(stageB + (size_t)col * stride);     // id of entry k at B[4k]
+                int pos = ptid >> 5;
+                uint32_t id = pos < stride ? B[4 * pos] : kSentinelId;
+                uint32_t h = hash_id(id, smask);
+                while (__any_sync(0xffffffffu, id != kSentinelId)) {
+                    if (id != kSentinelId) {
+                        const uint32_t old = atomicCAS(&tab_id[h], kEmpty, id);
+                        if (old == kEmpty || old == id) {
+                            atomicOr(&tab_mask[h], 1u << col);
+                            pos += NPROD / TC;
+                            id = pos < stride ? B[4 * pos] : kSentinelId;
+                            h = hash_id(id, smask);
+                        } else h = (h + 1) & smask;
                     }
-                    pos += NPROD / TC;
                 }
             }
             bar_sync(BAR_PROD, NPROD);
             bar_sync(BAR_EMPTY, NTP);            // consumers have released the slots of the previous tile
+            // ---- probe: thread -> row (ptid & 63), entries (ptid >> 6) + 2k --------------------------------------------------
             {
                 const int row = ptid & (TR - 1);
-                const int64_t i = i0 + row;
-                const int n = p.nshared[i];
-                const SplitRec *A = p.shared + i * p.sh_stride;
-                const int first_col = RECT ? 0 : (int)(i - j0) + 1;     // columns below are on or under the diagonal
-                int pos = ptid >> 6;                                   // 0..1
-                while (__any_sync(0xffffffffu, pos < n)) {
-                    const bool have = pos < n;
-                    const SplitRec a = have ? A[pos] : SplitRec{kSentinelId, 0, 0.0};
-                    uint32_t h = hash_id(a.id, smask);
-                    bool walking = have;
-                    while (__any_sync(0xffffffffu, walking)) {
-                        if (walking) {
-                            const uint32_t sid = tab_id[h];
-                            if (sid == kEmpty) walking = false;
-                            else {
-                                if (sid == a.id) {
-                                    const int col = tab_col[h];
-                                    if (col >= first_col) {
-                                        const int cell = row * TC + col;
-                                        atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
-                                        if constexpr (kWeighted) {
-                                            const double lb = tab_len[h];
-                                            if constexpr (kEUC) atomicAdd(&E2[cell], -2.0 * a.len * lb);
-                                            if constexpr (kWRF) atomicAdd(&E1[cell], fabs(a.len - lb) - fabs(a.len) - fabs(lb));
-                                        }
-                                    }
-                                }
-                                h = (h + 1) & smask;
+                const int first_col = RECT ? 0 : (int)(i0 + row - j0) + 1;      // columns below are on or under the diagonal
+                const uint32_t colvalid = first_col <= 0 ? 0xFFFFFFFFu : (first_col >= 32 ? 0u : (0xFFFFFFFFu << first_col));
+                const uint32_t *A = reinterpret_cast<const uint32_t *>(stageA + (size_t)row * stride);
+                int pos = ptid >> 6;
+                uint32_t id = pos < stride ? A[4 * pos] : kSentinelId;
+                uint32_t h = hash_id(id, smask);
+                while (__any_sync(0xffffffffu, id != kSentinelId)) {
+                    if (id != kSentinelId) {
+                        const uint32_t sid = tab_id[h];
+                        if (sid != kEmpty && sid != id) h = (h + 1) & smask;
+                        else {
+                            uint32_t m = (sid == id) ? (tab_mask[h] & colvalid) : 0u;
+                            while (m) {
+                                const int col = __ffs(m) - 1; m &= m - 1;
+                                const uint32_t ev = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)pos << 16);
+                                const uint32_t slot = atomicAdd(ev_count, 1u);
+                                if (slot < kEventCap) events[slot] = ev; else resolve(ev);
                             }
+                            pos += NPROD / TR;
+                            id = pos < stride ? A[4 * pos] : kSentinelId;
+                            h = hash_id(id, smask);
                         }
                     }
-                    pos += NPROD / TR;
                 }
+            }
+            bar_sync(BAR_PROD, NPROD);
+            // ---- events: resolve the queue in parallel ---------------------------------------------------------------------------
+            {
+                const uint32_t n_ev = min(*ev_count, kEventCap);
+                for (uint32_t e = ptid; e < n_ev; e += NPROD) resolve(events[e]);
             }
             __threadfence_block();
             bar_arrive(BAR_FULL, NTP);
@@ -541,20 +600,24 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
         }
 
         // epilogue
-        double sumj[2], normj[2];
+        double sumj[2] = {0.0, 0.0}, normj[2] = {0.0, 0.0};
+        if (p.normalise) {
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int64_t j = j0 + tx + 16 * c;
-            if constexpr (kWRF) sumj[c] = p.sum_len[j];
-            if constexpr (kEUC) normj[c] = p.norm[j];
+            for (int c = 0; c < 2; c++) {
+                const int64_t j = j0 + tx + 16 * c;
+                if constexpr (kWRF) sumj[c] = p.sum_len[j];
+                if constexpr (kEUC) normj[c] = p.norm[j];
+            }
         }
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int64_t i = i0 + 4 * ty + r;
             if (i < p.row_begin || i >= p.row_end) continue;
             double sumi = 0, normi = 0;
-            if constexpr (kWRF) sumi = p.sum_len[i];
-            if constexpr (kEUC) normi = p.norm[i];
+            if (p.normalise) {
+                if constexpr (kWRF) sumi = p.sum_len[i];
+                if constexpr (kEUC) normi = p.norm[i];
+            }
             const int64_t row_off = RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base);
 #pragma unroll
             for (int c = 0; c < 2; c++) {
@@ -677,6 +740,15 @@ int pairjoin_table_slots(int max_shared)
     return slots;
 }
 
+size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_stride)
+{
+    size_t s = (size_t)table_slots * 8 + TR * TC + (size_t)(TR + TC) * sh_stride * sizeof(SplitRec) + kEventCap * 4 + 16;
+    if (mask & 6u) s += 2 * KC * (TR + TC) * sizeof(double);
+    if (mask & 2u) s += TR * TC * sizeof(double);
+    if (mask & 4u) s += TR * TC * sizeof(double);
+    return s;
+}
+
 size_t pairjoin_smem_bytes(uint32_t mask, int table_slots)
 {
     size_t s = (size_t)table_slots * 5 + TR * TC;
@@ -709,6 +781,7 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, b
     }
     if (grid <= 0) return cudaSuccess;
     if (persistent) {
+        const size_t smem = pairjoin_persistent_smem_bytes(mask, p.table_slots, p.sh_stride);
         p.n_tiles = grid;
         int64_t ctas = 2 * (int64_t)n_sms;                    // two 384-thread CTAs per SM
         if (ctas > grid) ctas = grid;
