@@ -32,6 +32,11 @@ BASE_TREES, N_TAXA = 5000, 50
 SEED = 0xCA55E77E + 1          # treeCl RANDOM_SEED + config index
 
 
+# BASELINE.json configs (index -> trees, taxa, metrics); configs[1] is the bench line, the others are for experiments
+CONFIGS = {0: (200, 20, ('rf', 'wrf', 'euc')), 1: (5000, 50, ('rf', 'euc')), 2: (20000, 100, ('wrf', 'euc')),
+           4: (2000, 30, ('geo',))}
+
+
 def workload(n_gpus, n_trees=None, n_taxa=None):
     from treecl_b200 import synth
     nt = n_trees or int(round(BASE_TREES * math.sqrt(n_gpus)))
@@ -253,7 +258,7 @@ def run_ours(args):
             'metric': 'tree-pairs/sec ({} matrices)'.format('+'.join(METRICS)), 'value': value, 'unit': 'pairs/s', 'n_gpus': n_gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} uniform random {}-taxon trees, rf+euc condensed matrices, one fused launch per step'.format(nt, nx),
+            'config': {'workload': '{} uniform random {}-taxon trees, {} condensed matrices, one fused launch per step'.format(nt, nx, '+'.join(METRICS)),
                        'pairs': pairs_total, 'pairs_per_gpu': my_pairs, 'parallelism': 'rows sharded x{}'.format(n_gpus),
                        'l2': '256 MiB memset between timed steps (outside the event pairs); outputs (200 MB/step) exceed L2',
                        'dict_size': int(info.dict_size), 'dict_shared': int(info.dict_shared), 'max_shared': int(info.max_shared)},
@@ -290,8 +295,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--metrics', default=None, help='comma list overriding rf,euc (experiments)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--config', type=int, default=1, help='BASELINE.json configs index (experiments; default 1 = bench line)')
     args = ap.parse_args()
-    global METRICS
+    global METRICS, BASE_TREES, N_TAXA, SEED
+    if args.config != 1:
+        BASE_TREES, N_TAXA, METRICS = CONFIGS[args.config]
+        SEED = 0xCA55E77E + args.config
     if args.metrics:
         METRICS = tuple(args.metrics.split(','))
     if args.impl == 'reference':

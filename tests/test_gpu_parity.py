@@ -307,3 +307,35 @@ def test_properties_at_bench_size(td):
     blk = np.concatenate([np.arange(p(i, i + 1), p(i, 299) + 1) for i in range(299)])
     assert np.array_equal(sub['rf'], rf[blk])
     assert_close(sub['euc'], euc[blk], rtol=1e-12)
+
+
+@pytest.mark.parametrize('kind,n_trees,n_taxa', [('structured', 300, 40), ('structured', 257, 100), ('structured', 130, 200),
+                                                 ('uniform', 200, 20), ('uniform', 129, 64)])
+def test_rf_incidence_tcgen05(td, kind, n_trees, n_taxa):
+    """int8 tcgen05 contraction X * X^T over the shared-split dictionary: bit-identical to the join / merge RF."""
+    import torch
+    from treecl_b200 import _lib
+    trees = make(kind, n_trees, n_taxa, seed=900 + n_taxa)
+    ts = _lib.TreeSet(trees)
+    want = ts.pairwise(('rf',))['rf']
+    want_n = ts.pairwise(('rf',), normalise=True)['rf']
+    pairs = want.size
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.full((pairs,), -1.0, dtype=torch.float64, device='cuda:0')
+    ts.rf_incidence_device(out.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    ts.rf_incidence_device(out.data_ptr(), normalise=True, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want_n)
+    out16 = torch.zeros(pairs, dtype=torch.int16, device='cuda:0')
+    ts.rf_incidence_device(out16.data_ptr(), out_is_u16=True, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out16.cpu().numpy().astype(np.float64), want)
+    # a row shard
+    r0, r1 = 37, n_trees - 5
+    p0, p1 = _lib.condensed_offset(n_trees, r0), _lib.condensed_offset(n_trees, r1)
+    part = torch.zeros(p1 - p0, dtype=torch.float64, device='cuda:0')
+    ts.rf_incidence_device(part.data_ptr(), row_begin=r0, row_end=r1, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(part.cpu().numpy(), want[p0:p1])

@@ -169,6 +169,13 @@ class TreeSet(object):
         check(self._lib.td_pairwise_rect_device(self._h, int(split), mask, int(bool(normalise)), _c_void_p4(*table),
                                                 ctypes.c_void_p(stream)))
 
+    def rf_incidence_device(self, d_out_ptr, out_is_u16=False, normalise=False, row_begin=0, row_end=None, stream=0):
+        """Exact RF through the int8 tcgen05 split-incidence contraction; d_out_ptr: device pointer (u16 or f64 condensed)."""
+        if row_end is None:
+            row_end = self.n_trees
+        check(self._lib.td_rf_incidence_device(self._h, int(bool(normalise)), int(row_begin), int(row_end),
+                                               ctypes.c_void_p(d_out_ptr), int(bool(out_is_u16)), ctypes.c_void_p(stream)))
+
     def pairwise(self, metrics, normalise=False, min_overlap=4, overlap_fail_value=0.0, row_begin=0, row_end=None,
                  device=0, out=None):
         """End to end with host buffers: returns {metric: condensed float64 ndarray} for rows [row_begin,row_end)."""

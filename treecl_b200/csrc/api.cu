@@ -37,6 +37,10 @@ struct DeviceSet {
     int2 *wl_pairs = nullptr;          // kWorklists rings of kWorklistCap pairs for the persistent hash-join kernel
     unsigned *wl_count = nullptr;
     std::atomic<uint32_t> next_worklist{0};
+    int8_t *X = nullptr;               // split-incidence matrix [rows_x][d_pad] for the int8 tcgen05 RF path (built on demand)
+    int64_t d_pad = 0, rows_x = 0;
+    alignas(64) unsigned char tmap[128];
+    std::mutex x_mu;
     int *error_flag = nullptr;
     size_t max_smem_optin = 0;
     td_geo_stats geo_stats{};
@@ -452,10 +456,40 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
 
 int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16, void *stream)
 {
-    (void)normalise; (void)row_begin; (void)row_end; (void)d_out; (void)out_is_u16; (void)stream;
-    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
-    set_error("int8 tcgen05 split-incidence path is not built yet");
-    return TD_ERR_UNSUPPORTED;
+    if (!ts || !d_out) { set_error("null argument"); return TD_ERR_ARG; }
+    const HostSet &h = ts->host;
+    if (!h.uniform) { set_error("the incidence path needs one shared leaf set"); return TD_ERR_UNSUPPORTED; }
+    if (row_begin < 0 || row_end > h.N || row_begin > row_end) { set_error("row range outside [0,N]"); return TD_ERR_ARG; }
+    if (out_is_u16 && normalise) { set_error("normalised RF needs the double output"); return TD_ERR_ARG; }
+    if (h.max_splits > 32767) { set_error("too many splits per tree for the u16 / int32 epilogue"); return TD_ERR_UNSUPPORTED; }
+    cudaPointerAttributes attr;
+    CUDA_TRY(cudaPointerGetAttributes(&attr, d_out));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { set_error("output pointer is not device memory"); return TD_ERR_ARG; }
+    DeviceSet *d; int rc;
+    if ((rc = check_ready(ts, attr.device, &d))) return rc;
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        std::lock_guard<std::mutex> guard(d->x_mu);
+        if (!d->X) {
+            const int bk = incidence_bk(), tile = incidence_tile();
+            const int64_t d_pad = std::max<int64_t>((h.dict_shared + bk - 1) / bk * bk, bk);
+            const int64_t rows = (h.N + tile - 1) / tile * tile;
+            if ((double)d_pad * (double)rows > 64e9) { set_error("incidence matrix of %lld x %lld bytes is too large: the set shares too few splits for this path (use td_pairwise_device)", (long long)rows, (long long)d_pad); return TD_ERR_UNSUPPORTED; }
+            int8_t *X = nullptr;
+            if ((rc = dev_alloc(d, &X, (size_t)rows * d_pad))) return rc;
+            CUDA_TRY(cudaMemsetAsync(X, 0, (size_t)rows * d_pad, st));
+            CUDA_TRY(launch_build_incidence(d->shared, d->sh_stride, h.N, d_pad, X, st));
+            launch_counter_add(1);
+            cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap);
+            if (e != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+            d->X = X; d->d_pad = d_pad; d->rows_x = rows;
+        }
+    }
+    CUDA_TRY(launch_rf_incidence(d->tmap, d->nsplits, h.N, d->d_pad, row_begin, row_end, condensed_offset(h.N, row_begin), normalise,
+                                 out_is_u16, d_out, st));
+    launch_counter_add(1);
+    return TD_OK;
 }
 
 int td_geo_get_stats(td_treeset *ts, td_geo_stats *out)

@@ -9,9 +9,11 @@
 #include <algorithm>
 #include <atomic>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -335,6 +337,9 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, N / 8));
 
+    const bool timing = getenv("TREEDIST_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (!timing) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[encode] %-12s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_last).count()); t_last = n; };
     std::vector<TreeEnc> enc(N);
     TaxonTable tab;
     std::atomic<int> status{TD_OK};
@@ -378,6 +383,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         run_pass();
     }
     if (status != TD_OK) { set_error("%s", err_msg.c_str()); return status; }
+    lap("parse+encode");
 
     // ---- pack ------------------------------------------------------------------------------------------
     const int n_taxa = (int)tab.labels.size(), W = std::max(1, (n_taxa + 63) / 64);
@@ -405,6 +411,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         memcpy(&hs.leaflen[(size_t)i * n_taxa], enc[i].leaflen.data(), (size_t)n_taxa * 8);
     });
 
+    lap("pack");
     // ---- global split dictionary (exact: ties on the 64-bit hash are resolved by comparing the masks) --------
     struct Ent { uint64_t h; uint32_t tree, slot; };
     std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0);
@@ -458,6 +465,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
             }
         });
     }
+    lap("dictionary");
     // ---- per-tree lists sorted by dictionary id; shared-split lists ------------------------------------------
     std::vector<int32_t> nsh(N, 0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
@@ -481,6 +489,16 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
     hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
     hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
+    // compact index of every shared split (column of the incidence matrix X): rank among the shared dictionary ids
+    std::vector<uint32_t> sid_of((size_t)std::max<int64_t>(hs.dict_size, 1), kSentinelId);
+    {
+        std::vector<uint8_t> is_shared(sid_of.size(), 0);
+        for (int64_t i = 0; i < N; i++)
+            for (int s = 0; s < hs.n_splits[i]; s++)
+                if (mult_of[(size_t)i * stride + s] >= 2) is_shared[id_of[(size_t)i * stride + s]] = 1;
+        uint32_t next = 0;
+        for (size_t d = 0; d < sid_of.size(); d++) if (is_shared[d]) sid_of[d] = next++;
+    }
     parallel_for(N, n_threads, [&](int64_t i, int) {
         const int S = hs.n_splits[i]; int k = 0;
         // mult_of is indexed by the pre-sort slot: recover through the id (ids are unique inside one tree)
@@ -488,8 +506,12 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         for (int s = 0; s < S; s++) m[s] = {id_of[(size_t)i * stride + s], mult_of[(size_t)i * stride + s]};
         std::sort(m.begin(), m.end());
         for (int s = 0; s < S; s++)
-            if (m[s].second >= 2) hs.shared[(size_t)i * hs.sh_stride + k++] = SplitRec{hs.ids[(size_t)i * stride + s], 0, hs.lens[(size_t)i * stride + s]};
+            if (m[s].second >= 2) {
+                const uint32_t id = hs.ids[(size_t)i * stride + s];
+                hs.shared[(size_t)i * hs.sh_stride + k++] = SplitRec{id, sid_of[id], hs.lens[(size_t)i * stride + s]};
+            }
     });
+    lap("lists");
     return TD_OK;
 }
 

@@ -71,6 +71,15 @@ size_t geodesic_smem_bytes(int cap, int W, int warps);
 // pairs with different leaf sets (non-uniform sets): restrict-then-join, all four metrics
 cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
 
+// int8 tcgen05 split-incidence RF (kernels_incidence.cu)
+size_t incidence_smem_bytes();
+int incidence_tile();
+int incidence_bk();
+cudaError_t launch_build_incidence(const SplitRec *shared, int sh_stride, int64_t N, int64_t ldx, int8_t *X, cudaStream_t st);
+cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx, void *tmap_out);
+cudaError_t launch_rf_incidence(const void *tmap, const int32_t *nsplits, int64_t N, int64_t d_pad, int64_t row_begin, int64_t row_end,
+                                int64_t p_base, int normalise, int out_u16, void *out, cudaStream_t st);
+
 uint64_t launch_counter_add(uint64_t n);
 
 }  // namespace td

@@ -657,26 +657,57 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 }
 
 
-// Recompute the queued pairs with the additive merge (exact_pair) and overwrite their wrf / euc entries.
+// Recompute the queued pairs additively (no Q + E subtraction) and overwrite their wrf / euc entries.  One warp per pair:
+// lanes stride over the taxa and over both trees' shared-split lists (membership by binary search in the other list);
+// fixed lane assignment + shuffle-tree reduction => the same bits on every run.
 template <bool RECT>
 __global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, const uint32_t mask)
 {
     const unsigned n = min(*p.wl_count, p.wl_capacity);
-    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned w = warp; w < n; w += n_warps) {
         const int2 ij = p.wl_pairs[w];
         const int64_t i = ij.x, j = ij.y;
-        double t1, t2;
-        exact_pair(p, i, j, t1, t2);
-        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
-        if (mask & 2u) {
-            double v = t1;
-            if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
-            p.out[1][idx] = v;
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = lane; k < p.n_k; k += 32) {
+            const double d = p.leafT[(size_t)k * p.ldT + i] - p.leafT[(size_t)k * p.ldT + j];
+            s1 += fabs(d); s2 = fma(d, d, s2);
         }
-        if (mask & 4u) {
-            double v = sqrt(t2);
-            if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
-            p.out[2][idx] = v;
+        const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
+        const int hi0 = p.sh_stride - 1;
+        for (int e = lane; e < p.sh_stride; e += 32) {
+            const SplitRec a = A[e];
+            if (a.id != kSentinelId) {
+                int lo = 0, hi = hi0;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid].id < a.id) lo = mid + 1; else hi = mid; }
+                const SplitRec b = B[lo];
+                const double d = (b.id == a.id) ? a.len - b.len : a.len;       // common, or held by i only
+                s1 += fabs(d); s2 = fma(d, d, s2);
+            }
+            const SplitRec b = B[e];
+            if (b.id != kSentinelId) {
+                int lo = 0, hi = hi0;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid].id < b.id) lo = mid + 1; else hi = mid; }
+                if (A[lo].id != b.id) { s1 += fabs(b.len); s2 = fma(b.len, b.len, s2); }          // held by j only
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+        if (lane == 0) {
+            s1 += p.single_l1[i] + p.single_l1[j];
+            s2 += p.single_l2[i] + p.single_l2[j];
+            const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
+            if (mask & 2u) {
+                double v = s1;
+                if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
+                p.out[1][idx] = v;
+            }
+            if (mask & 4u) {
+                double v = sqrt(s2);
+                if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
+                p.out[2][idx] = v;
+            }
         }
     }
 }
@@ -788,8 +819,8 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, b
         cudaError_t e = rect ? launch_mask_persistent<true>(mask, p, (unsigned)ctas, smem, st)
                              : launch_mask_persistent<false>(mask, p, (unsigned)ctas, smem, st);
         if (e != cudaSuccess || !(mask & 6u)) return e;
-        if (rect) exact_fixup_kernel<true><<<2 * n_sms, 128, 0, st>>>(p, mask);
-        else exact_fixup_kernel<false><<<2 * n_sms, 128, 0, st>>>(p, mask);
+        if (rect) exact_fixup_kernel<true><<<8 * n_sms, 128, 0, st>>>(p, mask);
+        else exact_fixup_kernel<false><<<8 * n_sms, 128, 0, st>>>(p, mask);
         return cudaGetLastError();
     }
     return rect ? launch_mask<true>(mask, p, (unsigned)grid, smem, st) : launch_mask<false>(mask, p, (unsigned)grid, smem, st);

@@ -15,7 +15,7 @@ constexpr int kTile = 64;          // trees per tile edge; N is padded to a mult
 // one entry of a per-tree sorted split list as the merge kernels see it (16 B -> one LDS.128 / LDG.128)
 struct SplitRec {
     uint32_t id;
-    uint32_t pad;
+    uint32_t pad;      // compact index among the shared splits (column of the incidence matrix)
     double len;
 };
 static_assert(sizeof(SplitRec) == 16, "SplitRec must be 16 bytes");
