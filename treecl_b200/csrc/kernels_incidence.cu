@@ -175,17 +175,35 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row_ok) {
+                const int64_t jb = j0 + c0;
+                if (p.out_u16 && jb > i && jb + 31 < p.N) {
+                    // whole run valid: pack two results per 32-bit store (the condensed offset may be odd)
+                    uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + (row_off + jb);
+                    uint32_t r[32];
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    const int64_t j = j0 + c0 + k;
-                    if (j <= i || j >= p.N) continue;
-                    const int den = si + s_cols[c0 + k];
-                    const int rf = den - 2 * (int)v[k];
-                    if (p.out_u16) reinterpret_cast<uint16_t *>(p.out)[row_off + j] = (uint16_t)rf;
-                    else {
-                        double d = (double)rf;
-                        if (p.normalise) d = den ? d / (double)den : 0.0;
-                        reinterpret_cast<double *>(p.out)[row_off + j] = d;
+                    for (int k = 0; k < 32; k++) r[k] = (uint32_t)(si + s_cols[c0 + k] - 2 * (int)v[k]) & 0xFFFFu;
+                    if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
+#pragma unroll
+                        for (int k = 0; k < 32; k += 2) reinterpret_cast<uint32_t *>(o)[k >> 1] = r[k] | (r[k + 1] << 16);
+                    } else {
+                        o[0] = (uint16_t)r[0];
+#pragma unroll
+                        for (int k = 1; k < 31; k += 2) reinterpret_cast<uint32_t *>(o + 1)[k >> 1] = r[k] | (r[k + 1] << 16);
+                        o[31] = (uint16_t)r[31];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        const int64_t j = jb + k;
+                        if (j <= i || j >= p.N) continue;
+                        const int den = si + s_cols[c0 + k];
+                        const int rf = den - 2 * (int)v[k];
+                        if (p.out_u16) reinterpret_cast<uint16_t *>(p.out)[row_off + j] = (uint16_t)rf;
+                        else {
+                            double d = (double)rf;
+                            if (p.normalise) d = den ? d / (double)den : 0.0;
+                            reinterpret_cast<double *>(p.out)[row_off + j] = d;
+                        }
                     }
                 }
             }

@@ -343,6 +343,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// rare path, kept out of line: queue the pair for exact_fixup_kernel (same stream, right after the main kernel)
+__device__ __noinline__ void queue_exact(const PairParams &p, int64_t i, int64_t j, double &t1, double &t2)
+{
+    const unsigned slot = atomicAdd(p.wl_count, 1u);
+    if (slot < p.wl_capacity) p.wl_pairs[slot] = make_int2((int)i, (int)j);
+    else exact_pair(p, i, j, t1, t2);
+}
+
 template <bool RECT>
 __device__ __forceinline__ void decode_tile(const PairParams &p, long long t, int &tile_r, int &tile_c)
 {
@@ -361,7 +369,7 @@ __device__ __forceinline__ void decode_tile(const PairParams &p, long long t, in
     }
 }
 
-template <uint32_t MASK, bool RECT>
+template <uint32_t MASK, bool RECT, bool NORM>
 __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p)
 {
     constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 
         // epilogue
         double sumj[2] = {0.0, 0.0}, normj[2] = {0.0, 0.0};
-        if (p.normalise) {
+        if constexpr (NORM) {
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const int64_t j = j0 + tx + 16 * c;
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
             const int64_t i = i0 + 4 * ty + r;
             if (i < p.row_begin || i >= p.row_end) continue;
             double sumi = 0, normi = 0;
-            if (p.normalise) {
+            if constexpr (NORM) {
                 if constexpr (kWRF) sumi = p.sum_len[i];
                 if constexpr (kEUC) normi = p.norm[i];
             }
@@ -627,27 +635,22 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
                 if constexpr (kRF) {
                     const int den = si[r] + sj[c];
                     double v = (double)(den - 2 * common[r][c]);
-                    if (p.normalise) v = den ? v / (double)den : 0.0;
+                    if constexpr (NORM) v = den ? v / (double)den : 0.0;
                     p.out[0][idx] = v;
                 }
                 if constexpr (kWeighted) {
                     double t1 = 0.0, t2 = 0.0;
                     if constexpr (kWRF) t1 = (q1i[r] + q1j[c]) + acc1[r][c];
                     if constexpr (kEUC) t2 = (q2i[r] + q2j[c]) + acc2[r][c];
-                    if (risky >> (2 * r + c) & 1u) {
-                        // recomputed exactly by exact_fixup_kernel (same stream, right after this kernel)
-                        const unsigned slot = atomicAdd(p.wl_count, 1u);
-                        if (slot < p.wl_capacity) p.wl_pairs[slot] = make_int2((int)i, (int)j);
-                        else exact_pair(p, i, j, t1, t2);
-                    }
+                    if (risky >> (2 * r + c) & 1u) queue_exact(p, i, j, t1, t2);
                     if constexpr (kWRF) {
                         double v = t1;
-                        if (p.normalise) { const double den = sumi + sumj[c]; v = den != 0.0 ? v / den : 0.0; }
+                        if constexpr (NORM) { const double den = sumi + sumj[c]; v = den != 0.0 ? v / den : 0.0; }
                         p.out[1][idx] = v;
                     }
                     if constexpr (kEUC) {
                         double v = sqrt(t2);
-                        if (p.normalise) { const double den = normi + normj[c]; v = den != 0.0 ? v / den : 0.0; }
+                        if constexpr (NORM) { const double den = normi + normj[c]; v = den != 0.0 ? v / den : 0.0; }
                         p.out[2][idx] = v;
                     }
                 }
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, co
 template <uint32_t MASK, bool RECT>
 cudaError_t launch_one_persistent(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
-    auto k = pairjoin_persistent<MASK, RECT>;
+    auto k = p.normalise ? pairjoin_persistent<MASK, RECT, true> : pairjoin_persistent<MASK, RECT, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, NTP, smem, st>>>(p);
