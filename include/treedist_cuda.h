@@ -74,6 +74,10 @@ typedef struct {
  * root has exactly two children, treeCl/tree.py:858-862).  n_threads <= 0: use all host cores. */
 int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, td_treeset **out);
 
+/* Same, for n_trees NUL-terminated Newick strings stored back to back in one buffer of total_bytes bytes (saves the caller
+ * building a pointer table: the Python binding joins its strings once). */
+int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_trees, int n_threads, td_treeset **out);
+
 void td_treeset_free(td_treeset *ts);
 int td_treeset_info(const td_treeset *ts, td_info *info);
 

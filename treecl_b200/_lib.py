@@ -59,6 +59,7 @@ def load():
     lib.td_version.restype = ctypes.c_char_p
     lib.td_launch_count.restype = ctypes.c_uint64
     lib.td_encode_newick.argtypes = [ctypes.POINTER(ctypes.c_char_p), i64, i32, ctypes.POINTER(vp)]
+    lib.td_encode_newick_joined.argtypes = [ctypes.c_char_p, i64, i64, i32, ctypes.POINTER(vp)]
     lib.td_treeset_free.argtypes = [vp]
     lib.td_treeset_free.restype = None
     lib.td_treeset_info.argtypes = [vp, ctypes.POINTER(td_info)]
@@ -111,10 +112,18 @@ class TreeSet(object):
 
     def __init__(self, newicks, n_threads=0):
         lib = load()
-        newicks = [_b(s) for s in newicks]
-        arr = (ctypes.c_char_p * len(newicks))(*newicks)
+        newicks = list(newicks)
         handle = ctypes.c_void_p()
-        check(lib.td_encode_newick(arr, len(newicks), int(n_threads), ctypes.byref(handle)))
+        if newicks and all(isinstance(s, str) for s in newicks) and not any('\0' in s for s in newicks[:1]):
+            # one join + one encode instead of one bytes object and one pointer per tree
+            joined = ('\0'.join(newicks) + '\0').encode()
+            if joined.count(b'\0') != len(newicks):
+                raise ValueError('Newick strings must not contain NUL characters')
+            check(lib.td_encode_newick_joined(joined, len(joined), len(newicks), int(n_threads), ctypes.byref(handle)))
+        else:
+            raw = [_b(s) for s in newicks]
+            arr = (ctypes.c_char_p * len(raw))(*raw)
+            check(lib.td_encode_newick(arr, len(raw), int(n_threads), ctypes.byref(handle)))
         self._h = handle
         self._lib = lib
         self.n_trees = len(newicks)

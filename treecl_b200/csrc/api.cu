@@ -16,9 +16,60 @@ namespace td {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_counter_add(uint64_t n) { return g_launches.fetch_add(n) + n; }
 
+// ---- per-device block cache: cudaMalloc / cudaFree cost milliseconds, a matrix call must not pay them every time -----------
+struct BlockPool {
+    std::mutex mu;
+    std::vector<std::pair<size_t, void *>> free_blocks;
+    size_t cached = 0;
+};
+static BlockPool g_pools[64];
+constexpr size_t kPoolLimit = 24ull << 30;        // bytes kept per device before blocks really go back to the driver
+
+static cudaError_t pool_alloc(int device, size_t bytes, void **out, size_t *got)
+{
+    bytes = (std::max<size_t>(bytes, 1) + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1);
+    BlockPool &P = g_pools[device & 63];
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        size_t best = (size_t)-1, best_i = 0;
+        for (size_t i = 0; i < P.free_blocks.size(); i++) {
+            const size_t sz = P.free_blocks[i].first;
+            if (sz >= bytes && sz <= 2 * bytes + (64u << 20) && sz < best) { best = sz; best_i = i; }
+        }
+        if (best != (size_t)-1) {
+            *out = P.free_blocks[best_i].second; *got = best; P.cached -= best;
+            P.free_blocks.erase(P.free_blocks.begin() + best_i);
+            return cudaSuccess;
+        }
+    }
+    *got = bytes;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {            // give the cache back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> g(P.mu);
+        for (auto &b : P.free_blocks) cudaFree(b.second);
+        P.free_blocks.clear(); P.cached = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+static void pool_free(int device, void *p, size_t bytes)
+{
+    if (!p) return;
+    BlockPool &P = g_pools[device & 63];
+    std::lock_guard<std::mutex> g(P.mu);
+    if (P.cached + bytes > kPoolLimit) { cudaFree(p); return; }
+    P.free_blocks.emplace_back(bytes, p); P.cached += bytes;
+}
+
+struct DevProps { int sm_count = 0; size_t smem_optin = 0; bool valid = false; };
+static DevProps g_props[64];
+static std::mutex g_props_mu;
+
 constexpr int kCounters = 64;
 constexpr int kWorklists = 8;
-constexpr unsigned kWorklistCap = 1u << 20;
+constexpr unsigned kWorklistCap = 1u << 18;
 
 struct DeviceSet {
     int device = -1, sm_count = 148;
@@ -44,7 +95,7 @@ struct DeviceSet {
     int *error_flag = nullptr;
     size_t max_smem_optin = 0;
     td_geo_stats geo_stats{};
-    std::vector<void *> allocs;
+    std::vector<std::pair<size_t, void *>> allocs;      // pool blocks owned by this set
 };
 
 #define CUDA_TRY(expr)                                                                                   \
@@ -59,9 +110,9 @@ struct DeviceSet {
 template <class T>
 static int dev_alloc(DeviceSet *d, T **ptr, size_t count)
 {
-    void *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    d->allocs.push_back(p); *ptr = reinterpret_cast<T *>(p);
+    void *p = nullptr; size_t got = 0;
+    CUDA_TRY(pool_alloc(d->device, std::max<size_t>(count, 1) * sizeof(T), &p, &got));
+    d->allocs.emplace_back(got, p); *ptr = reinterpret_cast<T *>(p);
     return TD_OK;
 }
 
@@ -70,7 +121,7 @@ static void free_device(DeviceSet *d)
     if (!d) return;
     int cur = -1; cudaGetDevice(&cur);
     if (d->device >= 0) cudaSetDevice(d->device);
-    for (void *p : d->allocs) cudaFree(p);
+    for (auto &b : d->allocs) pool_free(d->device, b.second, b.first);
     if (cur >= 0) cudaSetDevice(cur);
     delete d;
 }
@@ -91,47 +142,48 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     DeviceSet *d = new DeviceSet();
     struct Guard { DeviceSet *d; bool keep = false; ~Guard() { if (!keep) free_device(d); } } own{d};
     d->device = device;
-    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    d->sm_count = prop.multiProcessorCount; d->max_smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        std::lock_guard<std::mutex> g(g_props_mu);
+        DevProps &dp = g_props[device & 63];
+        if (!dp.valid) {
+            int v = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); dp.sm_count = v;
+            CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)); dp.smem_optin = (size_t)v;
+            dp.valid = true;
+        }
+        d->sm_count = dp.sm_count; d->max_smem_optin = dp.smem_optin;
+    }
     d->N = h.N; d->Npad = (h.N + kTile - 1) / kTile * kTile;
     d->n_taxa = h.n_taxa; d->W = h.W; d->stride = std::max(h.max_splits, 1); d->sh_stride = h.sh_stride;
     const int kc = pairwise_kc();
     d->n_k = (h.n_taxa + kc - 1) / kc * kc;
     const size_t N = h.N, Npad = d->Npad;
     int rc;
-    if ((rc = dev_alloc(d, &d->leafT, (size_t)d->n_k * Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->leaflen, N * std::max(h.n_taxa, 1)))) return rc;
-    if ((rc = dev_alloc(d, &d->shared, Npad * d->sh_stride))) return rc;
-    if ((rc = dev_alloc(d, &d->nsplits, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->nshared, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->sum_len, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->norm, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->single_l1, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->single_l2, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->q1, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->q2, Npad))) return rc;
-    if ((rc = dev_alloc(d, &d->ids, N * d->stride))) return rc;
-    if ((rc = dev_alloc(d, &d->lens, N * d->stride))) return rc;
-    if ((rc = dev_alloc(d, &d->masks, N * d->stride * d->W))) return rc;
-    if ((rc = dev_alloc(d, &d->leafmask, N * d->W))) return rc;
-    if ((rc = dev_alloc(d, &d->rooted, N))) return rc;
-    if ((rc = dev_alloc(d, &d->work_counter, kCounters))) return rc;
-    if ((rc = dev_alloc(d, &d->stats, 4))) return rc;
-    if ((rc = dev_alloc(d, &d->error_flag, 1))) return rc;
-    if ((rc = dev_alloc(d, &d->wl_pairs, (size_t)kWorklists * kWorklistCap))) return rc;
-    if ((rc = dev_alloc(d, &d->wl_count, kWorklists))) return rc;
-
-    CUDA_TRY(cudaMemsetAsync(d->leafT, 0, (size_t)d->n_k * Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->nsplits, 0, Npad * sizeof(int32_t), st));
-    CUDA_TRY(cudaMemsetAsync(d->nshared, 0, Npad * sizeof(int32_t), st));
-    CUDA_TRY(cudaMemsetAsync(d->sum_len, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->norm, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->single_l1, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->single_l2, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->q1, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->q2, 0, Npad * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(d->stats, 0, 4 * sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(d->error_flag, 0, sizeof(int), st));
+    // one arena for every array of the set (256-byte aligned pieces): a single pool block, a single memset
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = (off + std::max<size_t>(bytes, 8) + 255) & ~(size_t)255; return o; };
+        const size_t o_leafT = take((size_t)d->n_k * Npad * 8), o_leaflen = take(N * std::max(h.n_taxa, 1) * 8);
+        const size_t o_shared = take(Npad * d->sh_stride * sizeof(SplitRec));
+        const size_t o_nsplits = take(Npad * 4), o_nshared = take(Npad * 4);
+        const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8);
+        const size_t o_ids = take(N * d->stride * 4), o_lens = take(N * d->stride * 8), o_masks = take(N * d->stride * d->W * 8);
+        const size_t o_leafmask = take(N * d->W * 8), o_rooted = take(N * 4);
+        const size_t o_counter = take(kCounters * 8), o_stats = take(4 * 8), o_err = take(4), o_wlc = take(kWorklists * 4);
+        const size_t o_wl = take((size_t)kWorklists * kWorklistCap * sizeof(int2));
+        unsigned char *base = nullptr;
+        if ((rc = dev_alloc(d, &base, off))) return rc;
+        // everything except the work lists starts as zero; the split lists start as sentinels (id = 0xFFFFFFFF)
+        CUDA_TRY(cudaMemsetAsync(base, 0, o_wl, st));
+        d->leafT = (double *)(base + o_leafT); d->leaflen = (double *)(base + o_leaflen); d->shared = (SplitRec *)(base + o_shared);
+        d->nsplits = (int32_t *)(base + o_nsplits); d->nshared = (int32_t *)(base + o_nshared);
+        d->sum_len = (double *)(base + o_sum); d->norm = (double *)(base + o_norm); d->single_l1 = (double *)(base + o_s1);
+        d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2);
+        d->ids = (uint32_t *)(base + o_ids); d->lens = (double *)(base + o_lens); d->masks = (uint64_t *)(base + o_masks);
+        d->leafmask = (uint64_t *)(base + o_leafmask); d->rooted = (int32_t *)(base + o_rooted);
+        d->work_counter = (unsigned long long *)(base + o_counter); d->stats = (unsigned long long *)(base + o_stats);
+        d->error_flag = (int *)(base + o_err); d->wl_count = (unsigned *)(base + o_wlc); d->wl_pairs = (int2 *)(base + o_wl);
+    }
     // sentinel rows for the padded trees: id = 0xFFFFFFFF (the length of a sentinel is never read)
     CUDA_TRY(cudaMemsetAsync(d->shared, 0xFF, Npad * d->sh_stride * sizeof(SplitRec), st));
 
@@ -210,7 +262,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         GeoParams g{};
         g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
         g.leafmask = d->leafmask; g.rooted = d->rooted;
-        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise;
+        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);
         g.metric_mask = mask; g.min_overlap = min_overlap; g.fail_value = fail_value;
         for (int m = 0; m < 4; m++) {
             g.outs[m] = (double *)d_out[m];
@@ -273,7 +325,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (h.max_splits > 64 || h.W > 2) { set_error("geodesic kernel holds at most 64 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         GeoParams g{};
         g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
-        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise;
+        g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);
         g.out = (double *)d_out[TD_GEO]; g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
         if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
@@ -308,6 +360,17 @@ int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, 
     if (rc) { delete ts; return rc; }
     *out = ts;
     return TD_OK;
+}
+
+int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_trees, int n_threads, td_treeset **out)
+{
+    if (!buffer || total_bytes <= 0 || n_trees < 1) { set_error("empty buffer"); return TD_ERR_ARG; }
+    if (buffer[total_bytes - 1] != 0) { set_error("the joined buffer must end with a NUL byte"); return TD_ERR_ARG; }
+    std::vector<const char *> ptrs; ptrs.reserve((size_t)n_trees);
+    const char *p = buffer, *end = buffer + total_bytes;
+    while (p < end && (int64_t)ptrs.size() < n_trees) { ptrs.push_back(p); p = (const char *)memchr(p, 0, (size_t)(end - p)) + 1; }
+    if ((int64_t)ptrs.size() != n_trees) { set_error("buffer holds %lld strings, expected %lld", (long long)ptrs.size(), (long long)n_trees); return TD_ERR_ARG; }
+    return td_encode_newick(ptrs.data(), n_trees, n_threads, out);
 }
 
 void td_treeset_free(td_treeset *ts)
@@ -429,10 +492,11 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     if (pairs <= 0) return TD_OK;
     CUDA_TRY(cudaSetDevice(device));
     void *dbuf[4] = {nullptr, nullptr, nullptr, nullptr};
-    auto cleanup = [&] { for (int m = 0; m < 4; m++) if (dbuf[m]) cudaFree(dbuf[m]); };
+    size_t dsize[4] = {0, 0, 0, 0};
+    auto cleanup = [&] { for (int m = 0; m < 4; m++) if (dbuf[m]) pool_free(device, dbuf[m], dsize[m]); };
     for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u) {
         if (!out[m]) { cleanup(); set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
-        cudaError_t e = cudaMalloc(&dbuf[m], (size_t)pairs * sizeof(double));
+        cudaError_t e = pool_alloc(device, (size_t)pairs * sizeof(double), &dbuf[m], &dsize[m]);
         if (e != cudaSuccess) { cleanup(); set_error("cudaMalloc of %lld bytes failed: %s", (long long)pairs * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
     }
     cudaStream_t st = 0;

@@ -27,10 +27,10 @@ struct Bits {
     __device__ __forceinline__ int count() const { int c = 0;
 #pragma unroll
         for (int h = 0; h < H; h++) c += __popc(w[h]); return c; }
-    // i is warp-uniform; the word is picked by selects so that w[] stays in registers
-    __device__ __forceinline__ bool test(int i) const { uint32_t x = w[0];
+    // i is warp-uniform; every word is touched with a computed mask (no indexing by i, so w[] stays in registers)
+    __device__ __forceinline__ bool test(int i) const { uint32_t x = 0;
 #pragma unroll
-        for (int h = 1; h < H; h++) if ((i >> 5) == h) x = w[h]; return (x >> (i & 31)) & 1u; }
+        for (int h = 0; h < H; h++) x |= w[h] & (0u - (uint32_t)((i >> 5) == h)); return (x >> (i & 31)) & 1u; }
     __device__ __forceinline__ bool mine(int h, int lane) const { return (w[h] >> lane) & 1u; }   // h compile-time
     __device__ __forceinline__ int first() const {
         int r = -1;
@@ -39,16 +39,28 @@ struct Bits {
         return r; }
     __device__ __forceinline__ void reset(int i) {
 #pragma unroll
-        for (int h = 0; h < H; h++) if ((i >> 5) == h) w[h] &= ~(1u << (i & 31)); }
+        for (int h = 0; h < H; h++) w[h] &= ~((uint32_t)((i >> 5) == h) << (i & 31)); }
     __device__ __forceinline__ void set(int i) {
 #pragma unroll
-        for (int h = 0; h < H; h++) if ((i >> 5) == h) w[h] |= 1u << (i & 31); }
+        for (int h = 0; h < H; h++) w[h] |= (uint32_t)((i >> 5) == h) << (i & 31); }
     __device__ __forceinline__ bool equals(const Bits &o) const { bool e = true;
 #pragma unroll
         for (int h = 0; h < H; h++) e &= (w[h] == o.w[h]); return e; }
 };
-template <int H> __device__ __forceinline__ Bits<H> operator&(const Bits<H> &a, const Bits<H> &b) { Bits<H> r; for (int h = 0; h < H; h++) r.w[h] = a.w[h] & b.w[h]; return r; }
-template <int H> __device__ __forceinline__ Bits<H> andnot(const Bits<H> &a, const Bits<H> &b) { Bits<H> r; for (int h = 0; h < H; h++) r.w[h] = a.w[h] & ~b.w[h]; return r; }
+template <int H> __device__ __forceinline__ Bits<H> operator&(const Bits<H> &a, const Bits<H> &b)
+{
+    Bits<H> r;
+#pragma unroll
+    for (int h = 0; h < H; h++) r.w[h] = a.w[h] & b.w[h];
+    return r;
+}
+template <int H> __device__ __forceinline__ Bits<H> andnot(const Bits<H> &a, const Bits<H> &b)
+{
+    Bits<H> r;
+#pragma unroll
+    for (int h = 0; h < H; h++) r.w[h] = a.w[h] & ~b.w[h];
+    return r;
+}
 
 // value owned by lane (idx & 31), slot (idx >> 5); idx is warp-uniform
 template <int H>
@@ -69,6 +81,7 @@ template <int H>
 __device__ __forceinline__ Bits<H> fetch_bits(const Bits<H> (&v)[H], int idx)
 {
     Bits<H> r;
+#pragma unroll
     for (int k = 0; k < H; k++) {
         uint32_t x = __shfl_sync(FULL, v[0].w[k], idx & 31);
         if (H > 1) { const uint32_t x1 = __shfl_sync(FULL, v[H - 1].w[k], idx & 31); if (idx >> 5) x = x1; }
@@ -107,8 +120,7 @@ __device__ __forceinline__ int64_t tri_row_start(int64_t i, int64_t N) { return 
 
 template <int H, int W>
 struct WarpSmem {
-    static constexpr int CAP = 32 * H, FS = CAP + 1;
-    double flow[CAP * FS];
+    static constexpr int CAP = 32 * H;
     double lenB[CAP];
     uint64_t maskB[CAP * W];
     uint32_t idA[CAP], idB[CAP];
@@ -119,15 +131,16 @@ struct WarpSmem {
 struct Counters { unsigned long long pairs = 0, flows = 0, ratios = 0, aug = 0; };
 
 // Steps 3-5 for one pair, executed by a full warp.
+//   flow    : this warp's fp64 flow matrix, rows a (splits of A) x FS columns (FS odd >= splits of B)
 //   mA[h]   : mask of my split (lane + 32h) of tree A (canonical side);  sm.maskB[s] : masks of tree B's splits
 //   setA/B  : non-common splits of each tree;  la2/lb2 : squared lengths of my splits
 // Adds the extended-common-edge terms to `part` (per-lane partial) and returns sum_k (||A_k|| + ||B_k||)^2 (warp-uniform).
 template <int H, int W>
-__device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64_t (&mA)[H][W], Bits<H> setA, Bits<H> setB,
+__device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow, const int FS, const uint64_t (&mA)[H][W], Bits<H> setA, Bits<H> setB,
                                                 const double (&la2)[H], const double (&lb2)[H], const int lane,
                                                 double &part, Counters &st, bool &failed)
 {
-    constexpr int CAP = 32 * H, FS = CAP + 1;
+    constexpr int CAP = 32 * H;
     // ---- 3. incompatibility bit matrix: inc[h] row of my split a over B; incT[h] row of my split b over A ----
     Bits<H> inc[H], incT[H];
 #pragma unroll
@@ -169,7 +182,9 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
     double total = 0.0;
     int sp = 0;
     if (setA.any() && setB.any()) {
-        if (lane == 0) { for (int h = 0; h < H; h++) { sm.stack[0][h] = setA.w[h]; sm.stack[0][H + h] = setB.w[h]; } }
+        if (lane == 0) {
+#pragma unroll
+            for (int h = 0; h < H; h++) { sm.stack[0][h] = setA.w[h]; sm.stack[0][H + h] = setB.w[h]; } }
         sp = 1;
     }
     __syncwarp();
@@ -177,6 +192,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
     while (sp > 0) {
         sp--;
         Bits<H> RA, RB;
+#pragma unroll
         for (int h = 0; h < H; h++) { RA.w[h] = sm.stack[sp][h]; RB.w[h] = sm.stack[sp][H + h]; }
         __syncwarp();
         double sa = 0.0, sb = 0.0;
@@ -196,7 +212,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
                 ra[h] = wa[h]; rb[h] = wb[h];
                 if (RA.mine(h, lane)) {                             // zero my row of the flow matrix (only edges of the graph)
                     Bits<H> nb = inc[h] & RB;
-                    while (nb.any()) { const int b = nb.first(); nb.reset(b); sm.flow[(lane + 32 * h) * FS + b] = 0.0; }
+                    while (nb.any()) { const int b = nb.first(); nb.reset(b); flow[(lane + 32 * h) * FS + b] = 0.0; }
                 }
             }
             __syncwarp();
@@ -216,7 +232,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
                         for (int d = 1; d < 32; d <<= 1) { const double t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
                         const double tot = __shfl_sync(FULL, incl, 31);
                         const double take = fmin(avail, fmax(0.0, x - (incl - avail)));
-                        if (take > 0.0) { rb[h] -= take; sm.flow[a * FS + lane + 32 * h] = take; }
+                        if (take > 0.0) { rb[h] -= take; flow[a * FS + lane + 32 * h] = take; }
                         x = fmax(0.0, x - tot);
                     }
                     owner_store<H>(ra, a, lane, x);
@@ -258,7 +274,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
                         bool found = false;
                         if (RA.mine(h, lane) && !visA.mine(h, lane)) {
                             Bits<H> cand = inc[h] & newB;
-                            while (cand.any()) { const int b = cand.first(); cand.reset(b); if (sm.flow[s * FS + b] > FLOW_TOL) { parA[h] = b; found = true; break; } }
+                            while (cand.any()) { const int b = cand.first(); cand.reset(b); if (flow[s * FS + b] > FLOW_TOL) { parA[h] = b; found = true; break; } }
                         }
                         newA.w[h] = __ballot_sync(FULL, found);
                     }
@@ -274,15 +290,15 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
                 for (int hop = 0; hop < 2 * CAP + 2; hop++) {
                     const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
                     if (pb < 0) { delta = fmin(delta, fetch_d<H>(ra, a)); break; }
-                    delta = fmin(delta, sm.flow[a * FS + pb]); b = pb;
+                    delta = fmin(delta, flow[a * FS + pb]); b = pb;
                 }
                 owner_sub<H>(rb, sink, lane, delta);
                 b = sink;
                 for (int hop = 0; hop < 2 * CAP + 2; hop++) {
                     const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
-                    if (lane == 0) sm.flow[a * FS + b] += delta;
+                    if (lane == 0) flow[a * FS + b] += delta;
                     if (pb < 0) { owner_sub<H>(ra, a, lane, delta); break; }
-                    if (lane == 0) sm.flow[a * FS + pb] -= delta;
+                    if (lane == 0) flow[a * FS + pb] -= delta;
                     b = pb;
                 }
                 __syncwarp();
@@ -299,6 +315,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, const uint64
         if (split) {
             // (C&A, B\C) precedes (A\C, C&B) in the ratio sequence; the sum does not depend on the order
             if (lane == 0) {
+#pragma unroll
                 for (int h = 0; h < H; h++) {
                     sm.stack[sp][h] = RA.w[h] & ~CA.w[h]; sm.stack[sp][H + h] = CB.w[h];
                     sm.stack[sp + 1][h] = CA.w[h]; sm.stack[sp + 1][H + h] = RB.w[h] & ~CB.w[h];

@@ -51,6 +51,7 @@ struct GeoParams {
     const int32_t *rooted;    // [N]
     int64_t N;
     int stride, n_taxa, W;
+    int flow_rows;                       // max internal edges of any tree of the set: the flow matrix is flow_rows x (flow_rows|1)
     int64_t p_begin, p_end, p_base;      // condensed pair range (triangular) ...
     int64_t rect_split, rect_cols;       // ... or rectangular: rows [0,split) x cols [split, split+cols); p = a*cols + b
     int rect;

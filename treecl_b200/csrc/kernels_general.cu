@@ -117,7 +117,11 @@ template <int H, int W>
 __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    GeneralSmem<H, W> &sm = reinterpret_cast<GeneralSmem<H, W> *>(smem_raw)[threadIdx.x >> 5];
+    const int FS = p.flow_rows | 1;
+    const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (size_t)p.flow_rows * FS * sizeof(double);
+    unsigned char *wbase = smem_raw + (size_t)(threadIdx.x >> 5) * warp_bytes;
+    GeneralSmem<H, W> &sm = *reinterpret_cast<GeneralSmem<H, W> *>(wbase);
+    double *flow = reinterpret_cast<double *>(wbase + sizeof(GeneralSmem<H, W>));
     const int lane = threadIdx.x & 31;
     Counters st;
     bool failed = false;
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
         double geo2 = 0.0;
         if (p.metric_mask & 8u) {
             double part = 0.0;
-            const double total = gtp_noncommon<H, W>(sm.core, mA, setA, setB, la2, lb2, lane, part, st, failed);
+            const double total = gtp_noncommon<H, W>(sm.core, flow, FS, mA, setA, setB, la2, lb2, lane, part, st, failed);
             geo2 = warp_sum(part) + total + c2 + l2;
         }
         if (lane == 0) {
@@ -234,7 +238,7 @@ template <int H, int W>
 cudaError_t launch_gen(const GeoParams &p, int n_sms, cudaStream_t st)
 {
     auto k = general_kernel<H, W>;
-    const size_t smem = sizeof(GeneralSmem<H, W>) * GEO_WARPS;
+    const size_t smem = (sizeof(GeneralSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double)) * GEO_WARPS;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;

@@ -31,7 +31,12 @@ template <int H, int W>
 __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem<H, W> &sm = reinterpret_cast<WarpSmem<H, W> *>(smem_raw)[threadIdx.x >> 5];
+    // per warp: fixed part, then the fp64 flow matrix sized for THIS set: flow_rows x FS doubles (FS odd: bank spread)
+    const int FS = p.flow_rows | 1;
+    const size_t warp_bytes = sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * FS * sizeof(double);
+    unsigned char *wbase = smem_raw + (size_t)(threadIdx.x >> 5) * warp_bytes;
+    WarpSmem<H, W> &sm = *reinterpret_cast<WarpSmem<H, W> *>(wbase);
+    double *flow = reinterpret_cast<double *>(wbase + sizeof(WarpSmem<H, W>));
     const int lane = threadIdx.x & 31;
     Counters st;
     bool failed = false;
@@ -93,7 +98,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
         }
 
         // ---- 3-5. incompatibilities, extended common edges, GTP ratio sequence (geo_core.cuh) ---------------------
-        const double total = gtp_noncommon<H, W>(sm, mA, setA, setB, la2, lb2, lane, part, st, failed);
+        const double total = gtp_noncommon<H, W>(sm, flow, FS, mA, setA, setB, la2, lb2, lane, part, st, failed);
         part = warp_sum(part);
         if (lane == 0) {
             double d = sqrt(part + total);
@@ -113,7 +118,7 @@ template <int H, int W>
 cudaError_t launch_geo(const GeoParams &p, int n_sms, cudaStream_t st)
 {
     auto k = geodesic_kernel<H, W>;
-    const size_t smem = sizeof(WarpSmem<H, W>) * GEO_WARPS;
+    const size_t smem = (sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double)) * GEO_WARPS;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -133,8 +138,9 @@ cudaError_t launch_geo(const GeoParams &p, int n_sms, cudaStream_t st)
 
 size_t geodesic_smem_bytes(int cap, int W, int warps)
 {
-    if (cap <= 32) return sizeof(WarpSmem<1, 1>) * warps;
-    return (W == 1 ? sizeof(WarpSmem<2, 1>) : sizeof(WarpSmem<2, 2>)) * warps;
+    const size_t flow = (size_t)cap * (cap | 1) * sizeof(double);
+    if (cap <= 32) return (sizeof(WarpSmem<1, 1>) + flow) * warps;
+    return ((W == 1 ? sizeof(WarpSmem<2, 1>) : sizeof(WarpSmem<2, 2>)) + flow) * warps;
 }
 
 cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t st)
