@@ -339,3 +339,57 @@ def test_rf_incidence_tcgen05(td, kind, n_trees, n_taxa):
     ts.rf_incidence_device(part.data_ptr(), row_begin=r0, row_end=r1, stream=st)
     torch.cuda.synchronize()
     assert np.array_equal(part.cpu().numpy(), want[p0:p1])
+
+
+def test_baseline_config_1_full(td, oracle_mod):
+    """BASELINE configs[0]: 200 random 20-taxon trees, rf / wrf / euc - small enough for the oracle in full."""
+    from treecl_b200 import synth
+    trees = synth.uniform_trees(200, 20, seed=0xCA55E77E)
+    c = td.Collection(records=[td.Record('t%03d' % k, ml_tree=t) for k, t in enumerate(trees)])
+    for metric in ('rf', 'wrf', 'euc'):
+        for norm in (False, True):
+            dm = c.get_inter_tree_distances(metric, jobhandler=td.parutils.ProcesspoolJobHandler(4), normalise=norm,
+                                            batchsize=100, show_progress=False)
+            want = squareform(oracle_mod.matrix(trees, metric, normalise=norm, nthreads=4))
+            if metric == 'rf':
+                assert np.array_equal(dm.values, want)
+            else:
+                assert_close(dm.values, want)
+            assert dm.get_names() == c.names
+
+
+def test_baseline_config_5_full_size(td, oracle_mod):
+    """BASELINE configs[4]: 2,000 random 30-taxon trees, geodesic.  Full matrix on the GPU; the oracle checks a slice
+    (first 30,000 pairs) and size-independent properties cover the rest."""
+    from treecl_b200 import _lib, synth
+    n = 2000
+    trees = synth.uniform_trees(n, 30, seed=0xCA55E77E + 4)
+    ts = _lib.TreeSet(trees)
+    got = ts.pairwise(('geo', 'euc'))
+    geo, euc = got['geo'], got['euc']
+    want = oracle_mod.matrix_range(trees, 'geo', 0, 30000, nthreads=8)
+    assert_close(geo[:30000], want)
+    assert np.isfinite(geo).all() and (geo >= euc * (1 - 1e-12)).all()          # the geodesic is never shorter than the chord
+    st = ts.geo_stats()
+    assert st['pairs'] == n * (n - 1) // 2 and 2.0 < st['ratios'] / st['pairs'] < 4.0
+    # order reversal gives the transposed matrix
+    rev = _lib.TreeSet(trees[::-1]).pairwise(('geo',))['geo']
+    idx = np.random.default_rng(1).integers(0, n, size=(3000, 2)); idx = idx[idx[:, 0] < idx[:, 1]]
+    p = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
+    assert_close(geo[p(idx[:, 0], idx[:, 1])], rev[p(n - 1 - idx[:, 1], n - 1 - idx[:, 0])], rtol=1e-10)
+
+
+def test_baseline_config_3_properties(td, oracle_mod):
+    """BASELINE configs[2] shape (100 taxa, wrf + euc) at a size the test suite can generate quickly (3,000 trees);
+    the oracle checks a slice, sharding and order reversal cover the rest.  The full 20,000-tree set is run by
+    `bench.py --config 2`."""
+    from treecl_b200 import _lib, engine, synth
+    n = 3000
+    trees = synth.uniform_trees(n, 100, seed=0xCA55E77E + 2)
+    ts = _lib.TreeSet(trees)
+    got = ts.pairwise(('wrf', 'euc'))
+    for m in ('wrf', 'euc'):
+        assert_close(got[m][:20000], oracle_mod.matrix_range(trees, m, 0, 20000, nthreads=8))
+    assert (got['wrf'] >= got['euc']).all()
+    parts = [ts.pairwise(('wrf',), row_begin=a, row_end=b)['wrf'] for a, b in engine.balanced_row_ranges(n, 8)]
+    assert np.array_equal(np.concatenate(parts), got['wrf'])
