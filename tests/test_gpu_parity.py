@@ -159,8 +159,8 @@ def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_
 
 @pytest.mark.parametrize('n_trees,n_taxa,kind', [(2, 4, 'uniform'), (3, 5, 'uniform'), (120, 10, 'uniform'),
                                                  (150, 20, 'uniform'), (200, 30, 'uniform'), (60, 35, 'uniform'),
-                                                 (50, 50, 'uniform'), (30, 67, 'uniform'),
-                                                 (150, 30, 'structured'), (60, 60, 'structured')])
+                                                 (50, 50, 'uniform'), (30, 67, 'uniform'), (24, 100, 'uniform'), (16, 131, 'uniform'),
+                                                 (150, 30, 'structured'), (60, 60, 'structured'), (40, 120, 'structured')])
 @pytest.mark.parametrize('norm', [False, True])
 def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     from treecl_b200 import _lib
@@ -173,7 +173,7 @@ def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     assert st['pairs'] == n_trees * (n_trees - 1) // 2 and st['ratios'] >= 0
 
 
-@pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30)])
+@pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30), (110, 16)])
 @pytest.mark.parametrize('norm', [False, True])
 def test_different_leaf_sets_vs_oracle(td, oracle_mod, n_taxa, n_trees, norm):
     """Pairs with different leaf sets (restrict-then-join kernel) against the oracle's tree-level pruning.

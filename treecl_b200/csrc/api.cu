@@ -257,7 +257,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
     const HostSet &h = ts->host;
     if (!h.uniform) {
         // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
-        if (h.max_splits > 64 || h.W > 2) { set_error("the restrict-then-join kernel holds at most 64 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
+        if (h.max_splits > 128 || h.W > 3) { set_error("the restrict-then-join kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         CUDA_TRY(cudaSetDevice(d->device));
         GeoParams g{};
         g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
@@ -273,7 +273,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
         if (g.p_end > g.p_begin) {
             CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
-            CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : 64, d->sm_count, st));
+            CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
             launch_counter_add(1);
         }
         return TD_OK;
@@ -322,7 +322,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
     }
     if (mask & TD_MASK(TD_GEO)) {
         if (!d_out[TD_GEO]) { set_error("output pointer for the geodesic metric is null"); return TD_ERR_ARG; }
-        if (h.max_splits > 64 || h.W > 2) { set_error("geodesic kernel holds at most 64 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
+        if (h.max_splits > 128 || h.W > 3) { set_error("geodesic kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         GeoParams g{};
         g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
         g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);
@@ -331,7 +331,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
         if (g.p_end > g.p_begin) {
             CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
-            CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : 64, d->sm_count, st));
+            CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
             launch_counter_add(1);
         }
     }

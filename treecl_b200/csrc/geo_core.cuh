@@ -67,14 +67,16 @@ template <int H>
 __device__ __forceinline__ double fetch_d(const double (&v)[H], int idx)
 {
     double r = __shfl_sync(FULL, v[0], idx & 31);
-    if (H > 1) { const double r1 = __shfl_sync(FULL, v[H - 1], idx & 31); if (idx >> 5) r = r1; }
+#pragma unroll
+    for (int h = 1; h < H; h++) { const double rh = __shfl_sync(FULL, v[h], idx & 31); if ((idx >> 5) == h) r = rh; }
     return r;
 }
 template <int H>
 __device__ __forceinline__ int fetch_i(const int (&v)[H], int idx)
 {
     int r = __shfl_sync(FULL, v[0], idx & 31);
-    if (H > 1) { const int r1 = __shfl_sync(FULL, v[H - 1], idx & 31); if (idx >> 5) r = r1; }
+#pragma unroll
+    for (int h = 1; h < H; h++) { const int rh = __shfl_sync(FULL, v[h], idx & 31); if ((idx >> 5) == h) r = rh; }
     return r;
 }
 template <int H>
@@ -84,7 +86,8 @@ __device__ __forceinline__ Bits<H> fetch_bits(const Bits<H> (&v)[H], int idx)
 #pragma unroll
     for (int k = 0; k < H; k++) {
         uint32_t x = __shfl_sync(FULL, v[0].w[k], idx & 31);
-        if (H > 1) { const uint32_t x1 = __shfl_sync(FULL, v[H - 1].w[k], idx & 31); if (idx >> 5) x = x1; }
+#pragma unroll
+        for (int h = 1; h < H; h++) { const uint32_t xh = __shfl_sync(FULL, v[h].w[k], idx & 31); if ((idx >> 5) == h) x = xh; }
         r.w[k] = x;
     }
     return r;

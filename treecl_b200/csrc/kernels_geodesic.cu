@@ -118,19 +118,24 @@ template <int H, int W>
 cudaError_t launch_geo(const GeoParams &p, int n_sms, cudaStream_t st)
 {
     auto k = geodesic_kernel<H, W>;
-    const size_t smem = (sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double)) * GEO_WARPS;
+    // warps per CTA: as many (<= GEO_WARPS) as the per-warp shared-memory region allows
+    const size_t warp_bytes = sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double);
+    int warps = GEO_WARPS;
+    while (warps > 1 && warp_bytes * warps > 200 * 1024) warps--;
+    if (warp_bytes > 225 * 1024) return cudaErrorInvalidConfiguration;
+    const size_t smem = warp_bytes * warps;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, GEO_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int64_t pairs = p.p_end - p.p_begin;
     int64_t blocks = (int64_t)n_sms * per_sm;
-    const int64_t need = (pairs + GEO_WARPS - 1) / GEO_WARPS;
+    const int64_t need = (pairs + warps - 1) / warps;
     if (blocks > need) blocks = need;
     if (blocks < 1) blocks = 1;
-    k<<<(unsigned)blocks, GEO_WARPS * 32, smem, st>>>(p);
+    k<<<(unsigned)blocks, warps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -148,6 +153,8 @@ cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t
     if (cap <= 32 && p.W == 1) return launch_geo<1, 1>(p, n_sms, st);
     if (cap <= 64 && p.W == 1) return launch_geo<2, 1>(p, n_sms, st);
     if (cap <= 64 && p.W == 2) return launch_geo<2, 2>(p, n_sms, st);
+    if (cap <= 128 && p.W == 2) return launch_geo<4, 2>(p, n_sms, st);
+    if (cap <= 128 && p.W == 3) return launch_geo<4, 3>(p, n_sms, st);
     return cudaErrorInvalidValue;
 }
 
