@@ -285,7 +285,9 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         // kernel choice: sparse sharing -> tile hash join (work ~ entries + matches); dense sharing -> merge-join
         const int slots = pairjoin_table_slots(h.max_shared);
         const char *force = getenv("TREEDIST_PAIR_KERNEL");
-        const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
+        const int row_slots = pairjoin_row_table_slots(h.max_tile_entries);
+        const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, row_slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024)
+                               && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         bool use_join = join_fits && h.mean_common <= 6.0;
         if (force && !strcmp(force, "merge")) use_join = false;
         if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) use_join = true;
@@ -294,7 +296,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         PairParams p{};
         p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits; p.nshared = d->nshared;
         p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
-        p.q1 = d->q1; p.q2 = d->q2; p.table_slots = slots;
+        p.q1 = d->q1; p.q2 = d->q2; p.table_slots = slots; p.row_table_slots = row_slots;
         p.N = d->N; p.n_k = d->n_k; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
         p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
         for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }

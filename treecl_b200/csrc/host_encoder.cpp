@@ -487,6 +487,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     });
     int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
     hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
+    for (int64_t b = 0; b < N; b += kTile) { int tot = 0; for (int64_t i = b; i < std::min<int64_t>(N, b + kTile); i++) tot += nsh[i]; hs.max_tile_entries = std::max(hs.max_tile_entries, tot); }
     hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
     hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
     // compact index of every shared split (column of the incidence matrix X): rank among the shared dictionary ids

@@ -18,6 +18,7 @@ struct PairParams {
     const double *sum_len, *norm, *single_l1, *single_l2;   // [Npad]
     const double *q1, *q2;    // [Npad] totals over ALL internal edges: sum |l|, sum l^2 (hash-join kernel)
     int table_slots, tiles_x; // hash-join kernel: power-of-two table size; tile columns of the grid
+    int row_table_slots;      // persistent hash-join kernel: table of the 64 row trees
     long long n_tiles;        // persistent hash-join kernel: length of the tile list
     int2 *wl_pairs;           // persistent hash-join kernel: pairs to recompute exactly (work list)
     unsigned *wl_count; unsigned wl_capacity;
@@ -35,6 +36,7 @@ int pairwise_kc();
 cudaError_t launch_pairwise(uint32_t mask, bool rect, PairParams p, int64_t tile_rows, int64_t tile_cols, int tile,
                             cudaStream_t st);
 int pairjoin_table_slots(int max_shared);
+int pairjoin_row_table_slots(int max_tile_entries);
 size_t pairjoin_smem_bytes(uint32_t mask, int table_slots);
 size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_stride);
 cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st);

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(NT, 3) pairjoin_kernel(const PairParams p)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int NCONS = 256, NPROD = 128, NTP = NCONS + NPROD;
 constexpr int BAR_FULL = 1, BAR_EMPTY = 2, BAR_PROD = 3, BAR_CONS = 4;
-constexpr uint32_t kEventCap = 2048;
+constexpr int kEventsPerThread = 8;                   // private queue slots of a producer thread
+constexpr uint32_t kEventCap = NPROD * kEventsPerThread;
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -374,16 +375,18 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 {
     constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
     constexpr bool kWeighted = kWRF || kEUC;
+    constexpr int KCP = (kWRF && kEUC) ? 4 : KC;      // two fp64 slot arrays: smaller k-chunks keep two CTAs per SM
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t slots = p.table_slots, smask = slots - 1;
+    const uint32_t slots = p.row_table_slots, smask = slots - 1;
     unsigned char *cur = smem_raw;
     double *E1 = nullptr, *E2 = nullptr, *leaf = nullptr;
     if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
     if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * TC * sizeof(double); }
-    if constexpr (kWeighted) { leaf = reinterpret_cast<double *>(cur); cur += 2 * KC * (TR + TC) * sizeof(double); }
+    if constexpr (kWeighted) { leaf = reinterpret_cast<double *>(cur); cur += 2 * KCP * (TR + TC) * sizeof(double); }
     uint32_t *tab_id = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);      // split id or kEmpty
-    uint32_t *tab_mask = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);    // column trees holding it
+    uint32_t *tab_lo = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);      // row trees 0-31 holding it
+    uint32_t *tab_hi = reinterpret_cast<uint32_t *>(cur); cur += (size_t)slots * sizeof(uint32_t);      // row trees 32-63
     unsigned char *cnt = cur; cur += TR * TC;
     SplitRec *stageA = reinterpret_cast<SplitRec *>(cur); cur += (size_t)TR * p.sh_stride * sizeof(SplitRec);   // row trees' lists
     SplitRec *stageB = reinterpret_cast<SplitRec *>(cur); cur += (size_t)TC * p.sh_stride * sizeof(SplitRec);   // column trees' lists
@@ -408,13 +411,14 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 
     if (tid >= NCONS) {
         // ================================================= PRODUCERS ====================================================
-        // Per tile: (1) TMA bulk copies stage the column trees' lists (and, when the tile row changes, the row trees')
-        // in shared memory, completing on an mbarrier; (2) build: table id -> 32-bit mask of the column trees that hold
-        // the split (atomicCAS claims / finds the slot, atomicOr sets the column bit), so every split occupies ONE slot;
-        // (3) probe: each row-tree entry finds its slot in ~1 step; matches become events (row, col, pos) in a queue;
-        // (4) events: all producer threads resolve the queue in parallel - binary search of the partner length in the
-        // column tree's staged list, then shared-memory atomics on the cell.  In (2) and (3) every lane advances through
-        // its own entries independently inside one warp-uniform loop, so a long chain in one lane does not stall the others.
+        // The hash table is built from the 64 ROW trees (id -> 64-bit mask of the rows that hold the split; one slot per
+        // split: atomicCAS claims / finds it, atomicOr sets the row bit) and lives as long as the CTA stays in the same tile
+        // row - with contiguous tile ranges that is ~20 tiles.  Per tile only the 32 COLUMN trees' lists are staged by one
+        // TMA bulk copy (mbarrier completion) and probed: every entry finds its slot in ~1 step; matches go to the probing
+        // thread's PRIVATE queue slots (no atomics) and are resolved by that same thread right after the probe: partner
+        // length by binary search in the row tree's staged list, shared-memory atomics on the cell.  Every lane advances
+        // through its own entries independently inside one warp-uniform loop, so a long chain in one lane does not stall
+        // the others.
         const int ptid = tid - NCONS;
         uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
         uint32_t parity = 0;
@@ -426,88 +430,109 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
             const int cell = row * TC + col;
             atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
             if constexpr (kWeighted) {
-                const SplitRec a = stageA[(size_t)row * stride + pos];
-                const SplitRec *B = stageB + (size_t)col * stride;
+                const SplitRec b = stageB[(size_t)col * stride + pos];
+                const SplitRec *A = stageA + (size_t)row * stride;
                 int lo = 0, hi = stride - 1;                         // sentinels (0xFFFFFFFF) keep the padded list sorted
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid].id < a.id) lo = mid + 1; else hi = mid; }
-                const double lb = B[lo].len;
-                if constexpr (kEUC) atomicAdd(&E2[cell], -2.0 * a.len * lb);
-                if constexpr (kWRF) atomicAdd(&E1[cell], fabs(a.len - lb) - fabs(a.len) - fabs(lb));
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid].id < b.id) lo = mid + 1; else hi = mid; }
+                const double la = A[lo].len;
+                if constexpr (kEUC) atomicAdd(&E2[cell], -2.0 * la * b.len);
+                if constexpr (kWRF) atomicAdd(&E1[cell], fabs(la - b.len) - fabs(la) - fabs(b.len));
             }
         };
         for (long long t = t_begin; t < t_end; t++) {
             int tile_r, tile_c;
             decode_tile<RECT>(p, t, tile_r, tile_c);
             const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
-            bar_sync(BAR_PROD, NPROD);           // every producer is done with the previous table, queue and staging buffers
-            if (ptid == 0) {
-                *ev_count = 0;
-                fence_proxy_async();             // generic-proxy reads of the staging buffers precede the async-proxy writes
-                mbar_expect_tx(mbar, bytesB + (tile_r != staged_row ? bytesA : 0u));
-                bulk_g2s(stageB, p.shared + j0 * stride, bytesB, mbar);
-                if (tile_r != staged_row) bulk_g2s(stageA, p.shared + i0 * stride, bytesA, mbar);
-            }
+            const bool new_row = tile_r != staged_row;
             staged_row = tile_r;
-            {
-                uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);           // ids then masks are contiguous
-                for (uint32_t e = ptid; e < slots / 4; e += NPROD) { t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty); t4[slots / 4 + e] = make_uint4(0, 0, 0, 0); }
+            bar_sync(BAR_PROD, NPROD);           // every producer is done with the previous staging buffers (and table)
+            if (ptid == 0) {
+                fence_proxy_async();             // generic-proxy reads of the staging buffers precede the async-proxy writes
+                mbar_expect_tx(mbar, bytesB + (new_row ? bytesA : 0u));
+                bulk_g2s(stageB, p.shared + j0 * stride, bytesB, mbar);
+                if (new_row) bulk_g2s(stageA, p.shared + i0 * stride, bytesA, mbar);
             }
-            bar_sync(BAR_PROD, NPROD);
+            if (new_row) {
+                uint4 *t4 = reinterpret_cast<uint4 *>(tab_id);           // ids, then the two mask arrays, are contiguous
+                for (uint32_t e = ptid; e < slots / 4; e += NPROD) {
+                    t4[e] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+                    t4[slots / 4 + e] = make_uint4(0, 0, 0, 0); t4[slots / 2 + e] = make_uint4(0, 0, 0, 0);
+                }
+                bar_sync(BAR_PROD, NPROD);
+            }
             mbar_wait(mbar, parity); parity ^= 1u;
-            // ---- build: thread -> column (ptid & 31), entries (ptid >> 5) + 4k ----------------------------------------------
-            {
-                const int col = ptid & (TC - 1);
-                const uint32_t *B = reinterpret_cast<const uint32_t *>(stageB + (size_t)col * stride);     // id of entry k at B[4k]
-                int pos = ptid >> 5;
-                uint32_t id = pos < stride ? B[4 * pos] : kSentinelId;
+            if (new_row) {
+                // ---- build: thread -> row (ptid & 63), entries (ptid >> 6) + 2k of that row tree ------------------------------
+                const int row = ptid & (TR - 1);
+                const uint32_t *A = reinterpret_cast<const uint32_t *>(stageA + (size_t)row * stride);     // id of entry k at A[4k]
+                int pos = ptid >> 6;
+                uint32_t id = pos < stride ? A[4 * pos] : kSentinelId;
                 uint32_t h = hash_id(id, smask);
                 while (__any_sync(0xffffffffu, id != kSentinelId)) {
                     if (id != kSentinelId) {
                         const uint32_t old = atomicCAS(&tab_id[h], kEmpty, id);
                         if (old == kEmpty || old == id) {
-                            atomicOr(&tab_mask[h], 1u << col);
-                            pos += NPROD / TC;
-                            id = pos < stride ? B[4 * pos] : kSentinelId;
+                            atomicOr(row < 32 ? &tab_lo[h] : &tab_hi[h], 1u << (row & 31));
+                            pos += NPROD / TR;
+                            id = pos < stride ? A[4 * pos] : kSentinelId;
                             h = hash_id(id, smask);
                         } else h = (h + 1) & smask;
                     }
                 }
+                bar_sync(BAR_PROD, NPROD);
             }
-            bar_sync(BAR_PROD, NPROD);
-            bar_sync(BAR_EMPTY, NTP);            // consumers have released the slots of the previous tile
-            // ---- probe: thread -> row (ptid & 63), entries (ptid >> 6) + 2k --------------------------------------------------
+            // ---- probe: thread -> column (ptid & 31), entries (ptid >> 5) + 4k of that column tree --------------------------
+            int my_events = 0;
+            uint32_t *my_queue = events + ptid * kEventsPerThread;
+            const int col = ptid & (TC - 1);
+            const long long lim = RECT ? 64 : (long long)(j0 + col - i0);        // rows above the diagonal: i0 + row < j0 + col
+            const unsigned long long rowvalid = lim >= 64 ? ~0ull : (lim <= 0 ? 0ull : ((1ull << lim) - 1ull));
+            const uint32_t *B = reinterpret_cast<const uint32_t *>(stageB + (size_t)col * stride);
+            int ovf_pos = -1; unsigned long long ovf_m = 0ull;           // where this thread's private queue filled up (rare)
             {
-                const int row = ptid & (TR - 1);
-                const int first_col = RECT ? 0 : (int)(i0 + row - j0) + 1;      // columns below are on or under the diagonal
-                const uint32_t colvalid = first_col <= 0 ? 0xFFFFFFFFu : (first_col >= 32 ? 0u : (0xFFFFFFFFu << first_col));
-                const uint32_t *A = reinterpret_cast<const uint32_t *>(stageA + (size_t)row * stride);
-                int pos = ptid >> 6;
-                uint32_t id = pos < stride ? A[4 * pos] : kSentinelId;
+                int pos = ptid >> 5;
+                uint32_t id = pos < stride ? B[4 * pos] : kSentinelId;
                 uint32_t h = hash_id(id, smask);
                 while (__any_sync(0xffffffffu, id != kSentinelId)) {
                     if (id != kSentinelId) {
                         const uint32_t sid = tab_id[h];
                         if (sid != kEmpty && sid != id) h = (h + 1) & smask;
                         else {
-                            uint32_t m = (sid == id) ? (tab_mask[h] & colvalid) : 0u;
-                            while (m) {
-                                const int col = __ffs(m) - 1; m &= m - 1;
-                                const uint32_t ev = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)pos << 16);
-                                const uint32_t slot = atomicAdd(ev_count, 1u);
-                                if (slot < kEventCap) events[slot] = ev; else resolve(ev);
+                            unsigned long long m = 0ull;
+                            if (sid == id) m = (((unsigned long long)tab_hi[h] << 32) | tab_lo[h]) & rowvalid;
+                            while (m && my_events < kEventsPerThread) {
+                                const int row = __ffsll((long long)m) - 1; m &= m - 1;
+                                my_queue[my_events++] = (uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)pos << 16);
                             }
-                            pos += NPROD / TR;
-                            id = pos < stride ? A[4 * pos] : kSentinelId;
-                            h = hash_id(id, smask);
+                            if (m) { ovf_pos = pos; ovf_m = m; id = kSentinelId; }      // continue after the cells are free
+                            else {
+                                pos += NPROD / TC;
+                                id = pos < stride ? B[4 * pos] : kSentinelId;
+                                h = hash_id(id, smask);
+                            }
                         }
                     }
                 }
             }
-            bar_sync(BAR_PROD, NPROD);
-            // ---- events: resolve the queue in parallel ---------------------------------------------------------------------------
-            {
-                const uint32_t n_ev = min(*ev_count, kEventCap);
-                for (uint32_t e = ptid; e < n_ev; e += NPROD) resolve(events[e]);
+            // the probe above only reads the table and the staged lists, so it ran while the consumers were still using
+            // the cells of the previous tile; the cell updates below need them released
+            bar_sync(BAR_EMPTY, NTP);
+            for (int e = 0; e < my_events; e++) resolve(my_queue[e]);
+            if (ovf_pos >= 0) {
+                // private queue overflowed (dense sharing): finish this thread's entries, resolving matches directly
+                int pos = ovf_pos; unsigned long long m = ovf_m;
+                for (;;) {
+                    while (m) {
+                        const int row = __ffsll((long long)m) - 1; m &= m - 1;
+                        resolve((uint32_t)row | ((uint32_t)col << 8) | ((uint32_t)pos << 16));
+                    }
+                    pos += NPROD / TC;
+                    if (pos >= stride) break;
+                    const uint32_t id = B[4 * pos];
+                    if (id == kSentinelId) break;
+                    uint32_t h = hash_id(id, smask);
+                    for (;;) { const uint32_t sid = tab_id[h]; if (sid == kEmpty || sid == id) { if (sid == id) m = (((unsigned long long)tab_hi[h] << 32) | tab_lo[h]) & rowvalid; break; } h = (h + 1) & smask; }
+                }
             }
             __threadfence_block();
             bar_arrive(BAR_FULL, NTP);
@@ -523,17 +548,17 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
         decode_tile<RECT>(p, t, tile_r, tile_c);
         const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
 
-        const int n_chunks = kWeighted ? p.n_k / KC : 0;
+        const int n_chunks = kWeighted ? p.n_k / KCP : 0;
         auto load_chunk = [&](int chunk, int stage) {
-            double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
-            constexpr int PA = KC * TR / 2, PB = KC * TC / 2;
+            double *sA = leaf + (size_t)stage * KCP * (TR + TC), *sB = sA + KCP * TR;
+            constexpr int PA = KCP * TR / 2, PB = KCP * TC / 2;
             for (int e = tid; e < PA + PB; e += NCONS) {
                 if (e < PA) {
                     const int kk = e / (TR / 2), c2 = e % (TR / 2);
-                    cp_async16(sA + kk * TR + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + i0 + 2 * c2);
+                    cp_async16(sA + kk * TR + 2 * c2, p.leafT + (size_t)(chunk * KCP + kk) * p.ldT + i0 + 2 * c2);
                 } else {
                     const int f = e - PA, kk = f / (TC / 2), c2 = f % (TC / 2);
-                    cp_async16(sB + kk * TC + 2 * c2, p.leafT + (size_t)(chunk * KC + kk) * p.ldT + j0 + 2 * c2);
+                    cp_async16(sB + kk * TC + 2 * c2, p.leafT + (size_t)(chunk * KCP + kk) * p.ldT + j0 + 2 * c2);
                 }
             }
         };
@@ -585,9 +610,9 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
                 const int stage = chunk & 1;
                 cp_async_wait<1>();
                 bar_sync(BAR_CONS, NCONS);
-                const double *sA = leaf + (size_t)stage * KC * (TR + TC), *sB = sA + KC * TR;
+                const double *sA = leaf + (size_t)stage * KCP * (TR + TC), *sB = sA + KCP * TR;
 #pragma unroll
-                for (int kk = 0; kk < KC; kk++) {
+                for (int kk = 0; kk < KCP; kk++) {
                     const double2 a01 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty);
                     const double2 a23 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty + 2);
                     const double av[4] = {a01.x, a01.y, a23.x, a23.y};
@@ -774,10 +799,19 @@ int pairjoin_table_slots(int max_shared)
     return slots;
 }
 
+// persistent kernel: the table holds the splits of the 64 ROW trees of a tile; `max_tile_entries` is the largest number of
+// shared-list entries of any 64-tree tile (an upper bound of its distinct splits); load factor <= 0.75
+int pairjoin_row_table_slots(int max_tile_entries)
+{
+    int slots = 512;
+    while (3 * slots < 4 * max_tile_entries) slots *= 2;
+    return slots;
+}
+
 size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_stride)
 {
-    size_t s = (size_t)table_slots * 8 + TR * TC + (size_t)(TR + TC) * sh_stride * sizeof(SplitRec) + kEventCap * 4 + 16;
-    if (mask & 6u) s += 2 * KC * (TR + TC) * sizeof(double);
+    size_t s = (size_t)table_slots * 12 + TR * TC + (size_t)(TR + TC) * sh_stride * sizeof(SplitRec) + kEventCap * 4 + 16;
+    if (mask & 6u) s += 2 * ((mask & 6u) == 6u ? 4 : KC) * (TR + TC) * sizeof(double);
     if (mask & 2u) s += TR * TC * sizeof(double);
     if (mask & 4u) s += TR * TC * sizeof(double);
     return s;
@@ -815,7 +849,7 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, b
     }
     if (grid <= 0) return cudaSuccess;
     if (persistent) {
-        const size_t smem = pairjoin_persistent_smem_bytes(mask, p.table_slots, p.sh_stride);
+        const size_t smem = pairjoin_persistent_smem_bytes(mask, p.row_table_slots, p.sh_stride);
         p.n_tiles = grid;
         int64_t ctas = 2 * (int64_t)n_sms;                    // two 384-thread CTAs per SM
         if (ctas > grid) ctas = grid;

@@ -24,6 +24,7 @@ struct HostSet {
     int64_t N = 0;
     int32_t n_taxa = 0, W = 1;
     int32_t max_splits = 0, max_shared = 0;
+    int32_t max_tile_entries = 0;              // largest sum of shared-list lengths over a 64-tree tile
     bool uniform = false;
     int32_t rooted = 0;
     int64_t dict_size = 0, dict_shared = 0, total_splits = 0;
