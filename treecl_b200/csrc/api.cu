@@ -297,7 +297,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits; p.nshared = d->nshared;
         p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
         p.q1 = d->q1; p.q2 = d->q2; p.table_slots = slots; p.row_table_slots = row_slots;
-        p.N = d->N; p.n_k = d->n_k; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
+        p.N = d->N; p.n_k = d->n_k; p.n_taxa = d->n_taxa; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
         p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
         for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
         int64_t tile_cols;

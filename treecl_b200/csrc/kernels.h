@@ -24,6 +24,7 @@ struct PairParams {
     unsigned *wl_count; unsigned wl_capacity;
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
+    int n_taxa;               // rows of leafT beyond n_taxa are zero: the k-loops may stop there
     int64_t row_begin, row_end, p_base;
     int64_t col_offset, n_cols, col_end;   // rectangular variant: columns are trees [col_offset, col_offset + n_cols)
     int tile_row0, col_tile0;

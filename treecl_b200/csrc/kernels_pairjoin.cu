@@ -611,8 +611,7 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
                 cp_async_wait<1>();
                 bar_sync(BAR_CONS, NCONS);
                 const double *sA = leaf + (size_t)stage * KCP * (TR + TC), *sB = sA + KCP * TR;
-#pragma unroll
-                for (int kk = 0; kk < KCP; kk++) {
+                auto step = [&](int kk) {
                     const double2 a01 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty);
                     const double2 a23 = *reinterpret_cast<const double2 *>(sA + kk * TR + 4 * ty + 2);
                     const double av[4] = {a01.x, a01.y, a23.x, a23.y};
@@ -625,6 +624,13 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
                             if constexpr (kWRF) acc1[r][c] += fabs(d);
                             if constexpr (kEUC) acc2[r][c] = fma(d, d, acc2[r][c]);
                         }
+                };
+                const int k_left = p.n_taxa - chunk * KCP;           // the padded rows of the last chunk are zero: skip them
+                if (k_left >= KCP) {
+#pragma unroll
+                    for (int kk = 0; kk < KCP; kk++) step(kk);
+                } else {
+                    for (int kk = 0; kk < k_left; kk++) step(kk);
                 }
                 bar_sync(BAR_CONS, NCONS);
                 if (chunk + 2 < n_chunks) load_chunk(chunk + 2, stage);
