@@ -140,7 +140,7 @@ def pair_kernel(request, monkeypatch):
 
 @pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
 @pytest.mark.parametrize('norm', [False, True])
-@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile', 'split'], indirect=True)
 def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_kernel):
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)
@@ -233,7 +233,7 @@ def test_polytomies_and_rooted_trees(td, oracle_mod):
                 assert_close(got[metric], want)
 
 
-@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join', 'split'], indirect=True)
 def test_identical_trees_give_exact_zero(td, pair_kernel):
     from treecl_b200 import _lib, synth
     trees = synth.uniform_trees(5, 40, seed=9)
@@ -244,7 +244,7 @@ def test_identical_trees_give_exact_zero(td, pair_kernel):
         assert sq[m][0, 2] == 0.0 and sq[m][1, 3] == 0.0 and sq[m][2, 4] == 0.0 and sq[m][0, 1] > 0
 
 
-@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join', 'split'], indirect=True)
 def test_row_sharding_is_byte_identical(td, pair_kernel):
     """Multi-GPU path: any partition of the rows reproduces the one-shot matrix bit for bit."""
     from treecl_b200 import _lib, engine, synth
@@ -265,7 +265,7 @@ def test_row_sharding_is_byte_identical(td, pair_kernel):
     assert np.array_equal(out['rf'], full['rf']) and np.array_equal(out['geo'], full['geo'])
 
 
-@pytest.mark.parametrize('pair_kernel', ['merge', 'join'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['merge', 'join', 'split'], indirect=True)
 def test_rectangular_variant(td, pair_kernel):
     """query x reference distances (treeCl/bootstrap.py:174-218) = a block of the square matrix."""
     import torch

@@ -78,7 +78,10 @@ struct DeviceSet {
     double *leafT = nullptr, *leaflen = nullptr;
     SplitRec *shared = nullptr;
     int32_t *nsplits = nullptr, *nshared = nullptr;
-    double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr, *q1 = nullptr, *q2 = nullptr;
+    double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr, *q1 = nullptr, *q2 = nullptr, *q2t = nullptr;
+    int32_t *post_tree = nullptr, *post_end = nullptr;
+    double *post_len = nullptr;
+    int64_t n_post = 0;
     uint32_t *ids = nullptr;
     double *lens = nullptr;
     uint64_t *masks = nullptr, *leafmask = nullptr;
@@ -92,6 +95,11 @@ struct DeviceSet {
     int64_t d_pad = 0, rows_x = 0;
     alignas(64) unsigned char tmap[128];
     std::mutex x_mu;
+    // event buffers of the two-kernel join (one launch at a time per set: later launches wait on ev_done)
+    std::mutex ev_mu;
+    unsigned char *ev_block = nullptr;
+    size_t ev_block_bytes = 0, ev_block_got = 0;
+    cudaEvent_t ev_done = nullptr;
     int *error_flag = nullptr;
     size_t max_smem_optin = 0;
     td_geo_stats geo_stats{};
@@ -122,6 +130,8 @@ static void free_device(DeviceSet *d)
     int cur = -1; cudaGetDevice(&cur);
     if (d->device >= 0) cudaSetDevice(d->device);
     for (auto &b : d->allocs) pool_free(d->device, b.second, b.first);
+    if (d->ev_done) { cudaEventSynchronize(d->ev_done); cudaEventDestroy(d->ev_done); }
+    if (d->ev_block) pool_free(d->device, d->ev_block, d->ev_block_got);
     if (cur >= 0) cudaSetDevice(cur);
     delete d;
 }
@@ -166,7 +176,9 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         const size_t o_leafT = take((size_t)d->n_k * Npad * 8), o_leaflen = take(N * std::max(h.n_taxa, 1) * 8);
         const size_t o_shared = take(Npad * d->sh_stride * sizeof(SplitRec));
         const size_t o_nsplits = take(Npad * 4), o_nshared = take(Npad * 4);
-        const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8);
+        const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8), o_q2t = take(Npad * 8);
+        const size_t n_post = h.post_tree.size();
+        const size_t o_ptree = take(n_post * 4), o_pend = take(n_post * 4), o_plen = take(n_post * 8);
         const size_t o_ids = take(N * d->stride * 4), o_lens = take(N * d->stride * 8), o_masks = take(N * d->stride * d->W * 8);
         const size_t o_leafmask = take(N * d->W * 8), o_rooted = take(N * 4);
         const size_t o_counter = take(kCounters * 8), o_stats = take(4 * 8), o_err = take(4), o_wlc = take(kWorklists * 4);
@@ -178,7 +190,9 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         d->leafT = (double *)(base + o_leafT); d->leaflen = (double *)(base + o_leaflen); d->shared = (SplitRec *)(base + o_shared);
         d->nsplits = (int32_t *)(base + o_nsplits); d->nshared = (int32_t *)(base + o_nshared);
         d->sum_len = (double *)(base + o_sum); d->norm = (double *)(base + o_norm); d->single_l1 = (double *)(base + o_s1);
-        d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2);
+        d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2); d->q2t = (double *)(base + o_q2t);
+        d->post_tree = (int32_t *)(base + o_ptree); d->post_end = (int32_t *)(base + o_pend); d->post_len = (double *)(base + o_plen);
+        d->n_post = (int64_t)n_post;
         d->ids = (uint32_t *)(base + o_ids); d->lens = (double *)(base + o_lens); d->masks = (uint64_t *)(base + o_masks);
         d->leafmask = (uint64_t *)(base + o_leafmask); d->rooted = (int32_t *)(base + o_rooted);
         d->work_counter = (unsigned long long *)(base + o_counter); d->stats = (unsigned long long *)(base + o_stats);
@@ -197,6 +211,12 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     CUDA_TRY(cudaMemcpyAsync(d->single_l2, h.single_l2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->q1, h.q1.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->q2, h.q2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->q2t, h.q2t.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (d->n_post) {
+        CUDA_TRY(cudaMemcpyAsync(d->post_tree, h.post_tree.data(), d->n_post * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d->post_end, h.post_end.data(), d->n_post * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d->post_len, h.post_len.data(), d->n_post * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -251,6 +271,48 @@ static int pick_tile(const DeviceSet *d, bool weighted)
     return 0;
 }
 
+constexpr size_t kEventBytesMax = 6ull << 30;       // above this the fused (single kernel) hash join is used instead
+
+static size_t split_event_bytes(int64_t capacity, long long tiles)
+{
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    return 2 * up((size_t)(tiles + 1) * 4) + 2 * up((size_t)capacity * 8) + up((size_t)capacity * 2);
+}
+
+// postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
+static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, cudaStream_t st)
+{
+    const long long tiles = pairsplit_tiles(rect, p);
+    if (tiles <= 0) return TD_OK;
+    std::lock_guard<std::mutex> g(d->ev_mu);
+    const size_t need = split_event_bytes(capacity, tiles);
+    if (!d->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+    if (need > d->ev_block_bytes) {
+        CUDA_TRY(cudaEventSynchronize(d->ev_done));
+        if (d->ev_block) pool_free(d->device, d->ev_block, d->ev_block_got);
+        d->ev_block = nullptr; d->ev_block_bytes = 0;
+        void *blk = nullptr; size_t got = 0;
+        CUDA_TRY(pool_alloc(d->device, need, &blk, &got));
+        d->ev_block = (unsigned char *)blk; d->ev_block_bytes = need; d->ev_block_got = got;
+    }
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    unsigned char *b = d->ev_block;
+    p.tile_cnt = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
+    p.tile_off = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
+    p.ev_t2 = (double *)b; b += up((size_t)capacity * 8);
+    p.ev_t1 = (double *)b; b += up((size_t)capacity * 8);
+    p.ev_cell = (uint16_t *)b;
+    p.ev_capacity = (uint32_t)capacity;
+    p.post_tree = d->post_tree; p.post_end = d->post_end; p.post_len = d->post_len; p.n_post = d->n_post; p.q2t = d->q2t;
+    CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
+    CUDA_TRY(cudaMemsetAsync(p.tile_cnt, 0, (size_t)(tiles + 1) * 4, st));
+    int launches = 0;
+    CUDA_TRY(launch_pairsplit(m3, rect, p, d->sm_count, st, &launches));
+    CUDA_TRY(cudaEventRecord(d->ev_done, st));
+    launch_counter_add(launches);
+    return TD_OK;
+}
+
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
@@ -290,7 +352,10 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         bool use_join = join_fits && h.mean_common <= 6.0;
         if (force && !strcmp(force, "merge")) use_join = false;
-        if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) use_join = true;
+        if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile") || !strcmp(force, "split")) && join_fits) use_join = true;
+        const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
+        const bool split_fits = join_fits && ev_capacity < (1ll << 31) && split_event_bytes(ev_capacity, 1) <= kEventBytesMax;
+        const bool use_split = use_join && split_fits && !(force && (!strcmp(force, "join") || !strcmp(force, "join_tile")));
         const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
@@ -317,9 +382,12 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                 p.wl_pairs = d->wl_pairs + (size_t)w * kWorklistCap; p.wl_count = d->wl_count + w; p.wl_capacity = kWorklistCap;
                 CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
             }
-            if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
-            else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
-            launch_counter_add(use_join && weighted ? 2 : 1);
+            if (use_split) { int rc = run_pairsplit(d, m3, rect, p, ev_capacity, st); if (rc) return rc; }
+            else {
+                if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
+                else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
+                launch_counter_add(use_join && weighted ? 2 : 1);
+            }
         }
     }
     if (mask & TD_MASK(TD_GEO)) {

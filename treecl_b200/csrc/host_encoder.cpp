@@ -452,6 +452,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         });
         double cp_total = 0;
         for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; hs.dict_shared += shared[b]; cp_total += copairs[b]; }
+        hs.total_common = (int64_t)(cp_total + 0.5);
         hs.mean_common = N > 1 ? cp_total / (0.5 * (double)N * (double)(N - 1)) : 0.0;
         hs.dict_size = uniq[NB];
         parallel_for(NB, n_threads, [&](int64_t b, int) {
@@ -511,6 +512,29 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
                 const uint32_t id = hs.ids[(size_t)i * stride + s];
                 hs.shared[(size_t)i * hs.sh_stride + k++] = SplitRec{id, sid_of[id], hs.lens[(size_t)i * stride + s]};
             }
+    });
+    // postings: counting sort of the shared-list entries by compact split index (trees visited in ascending order)
+    {
+        std::vector<int64_t> poff((size_t)hs.dict_shared + 2, 0);
+        for (int64_t i = 0; i < N; i++)
+            for (int k = 0; k < nsh[i]; k++) poff[hs.shared[(size_t)i * hs.sh_stride + k].pad + 1]++;
+        for (int64_t d = 0; d <= hs.dict_shared; d++) poff[d + 1] += poff[d];
+        const int64_t n_post = poff[hs.dict_shared];
+        if (n_post >= (1ll << 31)) { set_error("too many shared-split entries (%lld)", (long long)n_post); return TD_ERR_UNSUPPORTED; }
+        hs.post_tree.resize(n_post); hs.post_end.resize(n_post); hs.post_len.resize(n_post);
+        std::vector<int64_t> fill(poff.begin(), poff.end() - 1);
+        for (int64_t i = 0; i < N; i++)
+            for (int k = 0; k < nsh[i]; k++) {
+                const SplitRec &r = hs.shared[(size_t)i * hs.sh_stride + k];
+                const int64_t x = fill[r.pad]++;
+                hs.post_tree[x] = (int32_t)i; hs.post_end[x] = (int32_t)poff[r.pad + 1]; hs.post_len[x] = r.len;
+            }
+    }
+    hs.q2t.assign(N, 0.0);
+    parallel_for(N, n_threads, [&](int64_t i, int) {
+        double s = 0.0;
+        for (int k = 0; k < n_taxa; k++) { const double l = hs.leaflen[(size_t)i * n_taxa + k]; s += l * l; }
+        hs.q2t[i] = hs.q2[i] + s;
     });
     lap("lists");
     return TD_OK;

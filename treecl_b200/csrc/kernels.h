@@ -22,6 +22,16 @@ struct PairParams {
     long long n_tiles;        // persistent hash-join kernel: length of the tile list
     int2 *wl_pairs;           // persistent hash-join kernel: pairs to recompute exactly (work list)
     unsigned *wl_count; unsigned wl_capacity;
+    // postings pipeline (kernels_pairsplit.cu): the common splits of all pairs ("events") are enumerated from the postings of
+    // the shared splits and binned by 64 x 32 tile; events of tile t live in [tile_off[t], tile_off[t + 1])
+    const int32_t *post_tree, *post_end;   // [n_post]
+    const double *post_len;                // [n_post]
+    int64_t n_post;
+    const double *q2t;        // [Npad] sum of squares of ALL edge lengths (internal + leaf)
+    uint16_t *ev_cell;        // row * 32 + column inside the tile
+    double *ev_t1, *ev_t2;    // |la-lb| - |la| - |lb|,  -2 la lb
+    uint32_t *tile_cnt, *tile_off;
+    uint32_t ev_capacity;
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
     int n_taxa;               // rows of leafT beyond n_taxa are zero: the k-loops may stop there
@@ -41,6 +51,10 @@ int pairjoin_row_table_slots(int max_tile_entries);
 size_t pairjoin_smem_bytes(uint32_t mask, int table_slots);
 size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_stride);
 cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st);
+cudaError_t launch_exact_fixup(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st);
+size_t pairsplit_dense_smem_bytes(uint32_t mask);
+long long pairsplit_tiles(bool rect, PairParams &p);
+cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
 
 struct GeoParams {

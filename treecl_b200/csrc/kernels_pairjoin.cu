@@ -832,6 +832,13 @@ size_t pairjoin_smem_bytes(uint32_t mask, int table_slots)
     return s;
 }
 
+cudaError_t launch_exact_fixup(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st)
+{
+    if (rect) exact_fixup_kernel<true><<<8 * n_sms, 128, 0, st>>>(p, mask);
+    else exact_fixup_kernel<false><<<8 * n_sms, 128, 0, st>>>(p, mask);
+    return cudaGetLastError();
+}
+
 // Triangular: rows [row_begin,row_end) -> 64-row tiles from p.tile_row0 (set here); rect: rows [0,row_end), columns from `split`.
 cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st)
 {
@@ -862,9 +869,7 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, b
         cudaError_t e = rect ? launch_mask_persistent<true>(mask, p, (unsigned)ctas, smem, st)
                              : launch_mask_persistent<false>(mask, p, (unsigned)ctas, smem, st);
         if (e != cudaSuccess || !(mask & 6u)) return e;
-        if (rect) exact_fixup_kernel<true><<<8 * n_sms, 128, 0, st>>>(p, mask);
-        else exact_fixup_kernel<false><<<8 * n_sms, 128, 0, st>>>(p, mask);
-        return cudaGetLastError();
+        return launch_exact_fixup(mask, rect, p, n_sms, st);
     }
     return rect ? launch_mask<true>(mask, p, (unsigned)grid, smem, st) : launch_mask<false>(mask, p, (unsigned)grid, smem, st);
 }

@@ -36,6 +36,8 @@ struct HostSet {
     std::vector<double> sum_len, norm;         // all edges incl. leaves: sum l, sqrt(sum l^2)
     std::vector<double> single_l1, single_l2;  // sums over splits held by this tree only: sum |l|, sum l^2
     std::vector<double> q1, q2;                // sums over ALL internal splits: sum |l|, sum l^2
+    std::vector<double> q2t;                   // q2 + sum of squared leaf-edge lengths (dot-product form of the Euclidean kernel)
+    int64_t total_common = 0;                  // sum over all pairs of their number of common splits (exact)
     double mean_common = 0.0;                  // expected number of common splits of a random pair of the set
 
     // full lists, rows sorted by split id (uniform sets) or by mask (otherwise); stride max_splits
@@ -47,6 +49,11 @@ struct HostSet {
     // shared-split lists (splits that occur in >= 2 trees), sentinel padded, stride sh_stride
     int32_t sh_stride = 0;
     std::vector<SplitRec> shared;              // [N][sh_stride]
+
+    // postings of the shared splits: entries grouped by split, trees ascending inside a group.  post_end[x] is the end of x's
+    // group, so "all later holders of the split of entry x" is the range (x, post_end[x]).
+    std::vector<int32_t> post_tree, post_end;  // [n_post]
+    std::vector<double> post_len;              // [n_post]
 };
 
 struct DeviceSet;   // defined in api.cu
