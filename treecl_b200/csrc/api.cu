@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -94,6 +95,8 @@ struct DeviceSet {
     int8_t *X = nullptr;               // split-incidence matrix [rows_x][d_pad] for the int8 tcgen05 RF path (built on demand)
     int64_t d_pad = 0, rows_x = 0;
     alignas(64) unsigned char tmap[128];
+    alignas(64) unsigned char tmap_leaf_a[128], tmap_leaf_b[128];   // TMA descriptors over leafT (postings pipeline)
+    bool leaf_maps = false;
     std::mutex x_mu;
     // event buffers of the two-kernel join (one launch at a time per set: later launches wait on ev_done)
     std::mutex ev_mu;
@@ -226,6 +229,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         CUDA_TRY(launch_transpose_leaf(d->leaflen, d->leafT, h.N, h.n_taxa, d->Npad, st));
         launch_counter_add(1);
     }
+    if (h.n_taxa > 0 && make_leaf_tensor_maps(d->leafT, (int64_t)d->Npad, d->n_k, d->tmap_leaf_a, d->tmap_leaf_b) == cudaSuccess) d->leaf_maps = true;
+    else cudaGetLastError();
     CUDA_TRY(cudaStreamSynchronize(st));
     own.keep = true;
     ts->devs[device] = d;
@@ -273,10 +278,10 @@ static int pick_tile(const DeviceSet *d, bool weighted)
 
 constexpr size_t kEventBytesMax = 6ull << 30;       // above this the fused (single kernel) hash join is used instead
 
-static size_t split_event_bytes(int64_t capacity, long long tiles)
+static size_t split_event_bytes(int64_t capacity, long long tiles, int rec)
 {
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return 2 * up((size_t)(tiles + 1) * 4) + 2 * up((size_t)capacity * 8) + up((size_t)capacity * 2);
+    return 2 * up((size_t)(tiles + 1) * 4) + up((size_t)capacity * rec);
 }
 
 // postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
@@ -285,7 +290,7 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     const long long tiles = pairsplit_tiles(rect, p);
     if (tiles <= 0) return TD_OK;
     std::lock_guard<std::mutex> g(d->ev_mu);
-    const size_t need = split_event_bytes(capacity, tiles);
+    const size_t need = split_event_bytes(capacity, tiles, pairsplit_record_bytes(m3));
     if (!d->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
     if (need > d->ev_block_bytes) {
         CUDA_TRY(cudaEventSynchronize(d->ev_done));
@@ -299,15 +304,24 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     unsigned char *b = d->ev_block;
     p.tile_cnt = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
     p.tile_off = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
-    p.ev_t2 = (double *)b; b += up((size_t)capacity * 8);
-    p.ev_t1 = (double *)b; b += up((size_t)capacity * 8);
-    p.ev_cell = (uint16_t *)b;
+    p.ev = b;
     p.ev_capacity = (uint32_t)capacity;
+    p.tmap_a = d->leaf_maps ? d->tmap_leaf_a : nullptr; p.tmap_b = d->leaf_maps ? d->tmap_leaf_b : nullptr;
     p.post_tree = d->post_tree; p.post_end = d->post_end; p.post_len = d->post_len; p.n_post = d->n_post; p.q2t = d->q2t;
     CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
     CUDA_TRY(cudaMemsetAsync(p.tile_cnt, 0, (size_t)(tiles + 1) * 4, st));
     int launches = 0;
+    unsigned long long *trace = nullptr;
+    const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
+    if (trace_path) { CUDA_TRY(cudaMalloc(&trace, (size_t)tiles * 64)); CUDA_TRY(cudaMemsetAsync(trace, 0, (size_t)tiles * 64, st)); p.trace = trace; }
     CUDA_TRY(launch_pairsplit(m3, rect, p, d->sm_count, st, &launches));
+    if (trace) {
+        std::vector<unsigned long long> host((size_t)tiles * 8);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(host.data(), trace, host.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        if (FILE *f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, host.size(), f); fclose(f); }
+    }
     CUDA_TRY(cudaEventRecord(d->ev_done, st));
     launch_counter_add(launches);
     return TD_OK;
@@ -354,7 +368,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (force && !strcmp(force, "merge")) use_join = false;
         if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile") || !strcmp(force, "split")) && join_fits) use_join = true;
         const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
-        const bool split_fits = join_fits && ev_capacity < (1ll << 31) && split_event_bytes(ev_capacity, 1) <= kEventBytesMax;
+        const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(ev_capacity, 1, 32) <= kEventBytesMax;
         const bool use_split = use_join && split_fits && !(force && (!strcmp(force, "join") || !strcmp(force, "join_tile")));
         const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }

@@ -28,16 +28,18 @@ struct PairParams {
     const double *post_len;                // [n_post]
     int64_t n_post;
     const double *q2t;        // [Npad] sum of squares of ALL edge lengths (internal + leaf)
-    uint16_t *ev_cell;        // row * 32 + column inside the tile
-    double *ev_t1, *ev_t2;    // |la-lb| - |la| - |lb|,  -2 la lb
+    const void *tmap_a, *tmap_b;   // host copies of the CUtensorMaps over leafT (make_leaf_tensor_maps)
+    void *ev;                 // event records (layout depends on the metric mask, see kernels_pairsplit.cu)
     uint32_t *tile_cnt, *tile_off;
     uint32_t ev_capacity;
+    unsigned long long *trace;   // debug builds (-DPS_TRACE): 8 clock stamps per tile
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
     int n_taxa;               // rows of leafT beyond n_taxa are zero: the k-loops may stop there
     int64_t row_begin, row_end, p_base;
     int64_t col_offset, n_cols, col_end;   // rectangular variant: columns are trees [col_offset, col_offset + n_cols)
     int tile_row0, col_tile0;
+    int tri_rows;             // postings pipeline: tile rows of this launch
     int normalise;
     double *out[3];           // rf, wrf, euc (device)
 };
@@ -53,6 +55,8 @@ size_t pairjoin_persistent_smem_bytes(uint32_t mask, int table_slots, int sh_str
 cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, bool persistent, cudaStream_t st);
 cudaError_t launch_exact_fixup(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st);
 size_t pairsplit_dense_smem_bytes(uint32_t mask);
+int pairsplit_record_bytes(uint32_t mask);
+cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, void *tmap_a, void *tmap_b);
 long long pairsplit_tiles(bool rect, PairParams &p);
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);

@@ -18,9 +18,12 @@
 // (Q + E) subtracts; cells whose correction nearly cancels Q, or that received >= 3 events (the order of >= 3 shared-memory
 // atomic adds is not fixed), are queued for exact_fixup_kernel, which recomputes them additively in a fixed order: results are
 // bit-reproducible, independent of the row sharding, and identical trees give exactly 0.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 
 #include <cstdint>
+#include <cstring>
 
 #include "kernels.h"
 
@@ -31,19 +34,50 @@ namespace {
 constexpr int TR = 64, TC = 32;       // tile: rows x columns
 constexpr int NT = 256;
 constexpr int KCH = 16;               // taxa per staged chunk
+#ifndef PS_NSTAGE
+#define PS_NSTAGE 2
+#endif
+#ifndef PS_MINB
+#define PS_MINB 3
+#endif
+constexpr int NSTAGE = PS_NSTAGE;     // chunks in flight
 constexpr int SA = 68, SB = 36;       // row strides (doubles) of the staged leaf chunks: = 4 mod 16 -> conflict-free DMMA fragments
 constexpr int ES = 40;                // row stride (doubles) of the per-cell slots: conflict-free 16-byte accesses of the C fragments
 constexpr double kRisk1 = 0.9;        // wrf: exact recompute when -E1 > kRisk1 * (Q1_i + Q1_j)
 constexpr double kRisk2 = 0.98;       // euc: exact recompute when the result is < 2 % of Q2_i + Q2_j (error amplification <= 50)
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+// ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one TMA request moves a whole box (KCH taxon rows x 68 or 36 trees) of the taxon-major leaf matrix; out-of-range parts arrive as 0
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();          // watchdog: never hang the GPU on a lost transaction
+    }
+}
 
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -51,87 +85,80 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <bool RECT>
-__device__ __forceinline__ void decode_tile(const PairParams &p, long long t, int &tile_r, int &tile_c)
-{
-    if (RECT) {
-        tile_r = (int)(t / p.tiles_x) + p.tile_row0;
-        tile_c = (int)(t % p.tiles_x) + p.col_tile0;
-    } else {
-        // tile row u (from p.tile_row0) holds column tiles 2*tile_r .. tiles_x-1: L0 - 2u of them, L0 = tiles_x - 2*tile_row0
-        const long long L0 = p.tiles_x - 2 * p.tile_row0;
-        const double b = (double)L0 + 1.0;
-        long long u = (long long)floor((b - sqrt(b * b - 4.0 * (double)t)) * 0.5);
-        if (u < 0) u = 0;
-        while (u * L0 - u * (u - 1) > t) u--;
-        while ((u + 1) * L0 - (u + 1) * u <= t) u++;
-        tile_r = (int)u + p.tile_row0;
-        tile_c = 2 * tile_r + (int)(t - (u * L0 - u * (u - 1)));
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------------------
 // events from the postings.  FILL = false: count per tile;  FILL = true: write the events (tile_cnt was cleared by the scan)
 // ------------------------------------------------------------------------------------------------------------------------------
-template <bool WEIGHTED, bool RECT, bool FILL>
+// Event records (array of structures, one aligned store per event):
+//   WMODE 0 (rf only)      4 B  { u32 cell }
+//   WMODE 1 (wrf) / 2 (euc) 16 B { f64 t1 or t2, u32 cell, u32 0 }
+//   WMODE 3 (wrf + euc)    32 B { f64 t2, f64 t1, u32 cell, 12 B pad }
+// cell = row * 32 + column inside the 64 x 32 tile.
+__host__ __device__ constexpr int wmode_of(uint32_t mask) { return (int)((mask >> 1) & 3u); }
+__host__ __device__ constexpr int rec_bytes(int wmode) { return wmode == 0 ? 4 : (wmode == 3 ? 32 : 16); }
+
+template <int WMODE, bool RECT, bool FILL>
 __global__ void __launch_bounds__(256) pair_postings_kernel(const PairParams p)
 {
+    constexpr bool WEIGHTED = WMODE != 0;
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long L0 = p.tiles_x - 2 * p.tile_row0;
-    for (long long x = warp; x < p.n_post; x += n_warps) {
-        const int i = p.post_tree[x];
-        if (i < p.row_begin || i >= p.row_end) continue;
-        const int end = p.post_end[x];
-        const int tile_r = i >> 6;
-        const long long u = tile_r - p.tile_row0;
-        const long long base_t = RECT ? u * p.tiles_x - p.col_tile0 : u * L0 - u * (u - 1) - 2 * tile_r;
-        double la = 0.0;
-        if constexpr (WEIGHTED && FILL) la = p.post_len[x];
-        for (long long b = x + 1 + lane; b < end; b += 32) {
-            const int j = p.post_tree[b];
-            uint32_t *c = p.tile_cnt + (base_t + (j >> 5));
-            if (RECT && j < p.col_offset) {}                       // the other set's own side: not a pair of this launch
-            else if constexpr (!FILL) atomicAdd(c, 1u);
-            else {
-                const uint32_t o = p.tile_off[base_t + (j >> 5)] + atomicAdd(c, 1u);
-                if (o < p.ev_capacity) {
-                    p.ev_cell[o] = (uint16_t)(((i & 63) << 5) | (j & 31));
-                    if constexpr (WEIGHTED) {
-                        const double lb = p.post_len[b];
-                        p.ev_t2[o] = -2.0 * la * lb;
-                        p.ev_t1[o] = fabs(la - lb) - fabs(la) - fabs(lb);
+    long long x = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int i = 0, end = 0; double la = 0.0;
+    if (x < p.n_post) { i = p.post_tree[x]; end = p.post_end[x]; if constexpr (WEIGHTED && FILL) la = p.post_len[x]; }
+    while (x < p.n_post) {
+        // the next entry's header is fetched before this one's group is walked (one global round trip less per entry)
+        const long long xn = x + n_warps;
+        int in = 0, endn = 0; double lan = 0.0;
+        if (xn < p.n_post) { in = p.post_tree[xn]; endn = p.post_end[xn]; if constexpr (WEIGHTED && FILL) lan = p.post_len[xn]; }
+        if (i >= p.row_begin && i < p.row_end) {
+            const int tile_r = i >> 6;
+            const long long u = tile_r - p.tile_row0;
+            const long long base_t = RECT ? u * p.tiles_x - p.col_tile0 : u * L0 - u * (u - 1) - 2 * tile_r;
+            for (long long b = x + 1 + lane; b < end; b += 32) {
+                const int j = p.post_tree[b];
+                uint32_t *c = p.tile_cnt + (base_t + (j >> 5));
+                if (RECT && j < p.col_offset) {}                   // the other set's own side: not a pair of this launch
+                else if constexpr (!FILL) atomicAdd(c, 1u);
+                else {
+                    const uint32_t o = atomicAdd(c, 1u);            // tile_cnt was set to the tile's offset by tile_alloc_kernel
+                    if (o < p.ev_capacity) {
+                        const uint32_t cell = (uint32_t)(((i & 63) << 5) | (j & 31));
+                        if constexpr (WMODE == 0) reinterpret_cast<uint32_t *>(p.ev)[o] = cell;
+                        else {
+                            const double lb = p.post_len[b];
+                            const double t2 = -2.0 * la * lb, t1 = fabs(la - lb) - fabs(la) - fabs(lb);
+                            int4 *dst = reinterpret_cast<int4 *>(p.ev) + (size_t)o * (rec_bytes(WMODE) / 16);
+                            if constexpr (WMODE == 3) {
+                                dst[0] = make_int4(__double2loint(t2), __double2hiint(t2), __double2loint(t1), __double2hiint(t1));
+                                dst[1] = make_int4((int)cell, 0, 0, 0);
+                            } else {
+                                const double t = WMODE == 2 ? t2 : t1;
+                                dst[0] = make_int4(__double2loint(t), __double2hiint(t), (int)cell, 0);
+                            }
+                        }
                     }
                 }
             }
         }
+        x = xn; i = in; end = endn; la = lan;
     }
 }
 
-// exclusive scan of tile_cnt[0..n) into tile_off[0..n], tile_cnt cleared for the fill pass.  One block; every thread owns a
-// contiguous piece.
-__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *cnt, uint32_t *off, long long n)
+// Give every tile its own segment of the event buffer: off[t] = cnt[t] = start of the segment (the fill pass then advances cnt[t]
+// to the segment's end).  Segments are claimed from a cursor (cnt[n]) with one atomicAdd per warp, in no particular order.
+__global__ void __launch_bounds__(256) tile_alloc_kernel(uint32_t *cnt, uint32_t *off, long long n)
 {
-    __shared__ uint32_t warp_sum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long per = (n + 1023) / 1024, lo = tid * per < n ? tid * per : n, hi = lo + per < n ? lo + per : n;
-    uint32_t s = 0;
-    for (long long e = lo; e < hi; e++) s += cnt[e];
-    uint32_t incl = s;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t c = t < n ? cnt[t] : 0u;
+    uint32_t incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sum[lane], wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
-        warp_sum[lane] = wi - w;
-    }
-    __syncthreads();
-    uint32_t run = warp_sum[warp] + incl - s;
-    for (long long e = lo; e < hi; e++) { const uint32_t c = cnt[e]; off[e] = run; run += c; cnt[e] = 0; }
-    if (tid == 1023) off[n] = run;
+    uint32_t base = 0;
+    if (lane == 31 && incl) base = atomicAdd(cnt + n, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (t < n) { off[t] = base + incl - c; cnt[t] = base + incl - c; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -168,21 +195,47 @@ __device__ __noinline__ void queue_exact(const PairParams &p, int64_t i, int64_t
     else exact_pair(p, i, j, t1, t2);
 }
 
+#ifdef PS_TRACE
+#define TRACE(k) do { if (tid == 0 && p.trace) p.trace[t * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRACE(k) do {} while (0)
+#endif
+
+// One CTA per 64 x 32 tile.  Every global read of the tile is requested in the first instructions (segment bounds, per-tree scalars
+// into registers, the first NSTAGE leaf chunks as TMA bulk copies) and consumed as late as possible.
 template <uint32_t MASK, bool RECT, bool NORM>
-__global__ void __launch_bounds__(NT, 3) pair_dense_kernel(const __grid_constant__ PairParams p)
+__global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_constant__ PairParams p, const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b)
 {
     constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
     constexpr bool kWeighted = kWRF || kEUC;
+    constexpr int WMODE = wmode_of(MASK), REC = rec_bytes(WMODE);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // ---- which tile.  Rectangular: blockIdx = (column tile, tile row).  Triangular: tile row u holds L0 - 2u column tiles; rows u
+    // and R-1-u are folded into one grid row of constant length 2 L0 - 2 (R-1), so no CTA has to invert the triangular numbering.
+    int u = blockIdx.y, x = blockIdx.x;
+    const int L0 = p.tiles_x - 2 * p.tile_row0;
+    if (!RECT) {
+        const int len = L0 - 2 * u;
+        if (x >= len) {
+            x -= len; u = p.tri_rows - 1 - u;
+            if (u == (int)blockIdx.y || x >= L0 - 2 * u) return;      // middle row of an odd fold / past the end: nothing here
+        }
+    }
+    const int tile_r = u + p.tile_row0, tile_c = RECT ? x + p.col_tile0 : 2 * tile_r + x;
+    const long long t = RECT ? (long long)u * p.tiles_x + x : (long long)u * L0 - (long long)u * (u - 1) + x;
+    const int i0 = tile_r * TR, j0 = tile_c * TC;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *cur = smem_raw;
     double *E1 = nullptr, *E2 = nullptr, *sA = nullptr, *sB = nullptr, *sQ1 = nullptr, *sQ2 = nullptr;
+    if constexpr (kWeighted) {                                                                             // TMA destinations: 128-byte aligned
+        sA = reinterpret_cast<double *>(cur); cur += NSTAGE * KCH * SA * sizeof(double);
+        sB = reinterpret_cast<double *>(cur); cur += NSTAGE * KCH * SB * sizeof(double);
+    }
     if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * ES * sizeof(double); }
     if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * ES * sizeof(double); }
-    if constexpr (kWeighted) {
-        sA = reinterpret_cast<double *>(cur); cur += 2 * KCH * SA * sizeof(double);
-        sB = reinterpret_cast<double *>(cur); cur += 2 * KCH * SB * sizeof(double);
-    }
+    uint64_t *full = reinterpret_cast<uint64_t *>(cur); cur += NSTAGE * 8;                                 // one mbarrier per stage
     if constexpr (kWRF) { sQ1 = reinterpret_cast<double *>(cur); cur += (TR + TC) * sizeof(double); }     // rows, then columns
     if constexpr (kEUC) { sQ2 = reinterpret_cast<double *>(cur); cur += (TR + TC) * sizeof(double); }
     int *sS = reinterpret_cast<int *>(cur); cur += (TR + TC) * sizeof(int);                                // internal edges per tree
@@ -192,62 +245,74 @@ __global__ void __launch_bounds__(NT, 3) pair_dense_kernel(const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;            // DMMA fragment coordinates
     const int wr = warp >> 1, wc = warp & 1;           // warp tile: rows 16 wr .., columns 16 wc ..
-    const long long t = blockIdx.x;
-    const uint32_t ev0 = p.tile_off[t], ev1 = p.tile_off[t + 1];
-    int tile_r, tile_c;
-    decode_tile<RECT>(p, t, tile_r, tile_c);
-    const int64_t i0 = (int64_t)tile_r * TR, j0 = (int64_t)tile_c * TC;
+    TRACE(0);
 
-    // ---- leaf-length chunks start flowing --------------------------------------------------------------------------------------
+    // ---- leaf-length chunks: two TMA requests per chunk (rows of A, rows of B), issued by one thread ------------------------------------
     const int k_used = kWeighted ? (p.n_taxa + 3) & ~3 : 0;                  // <= n_k; rows >= n_taxa of leafT are zero
     const int n_chunks = (k_used + KCH - 1) / KCH;
-    auto load_chunk = [&](int chunk, int stage) {
-        // 16-byte pieces: KCH rows x (32 of A + 16 of B)
-        for (int e = tid; e < KCH * 48; e += NT) {
-            const int kk = e / 48, c = e % 48, k = chunk * KCH + kk;
-            if (k < k_used) {
-                const double *src = p.leafT + (size_t)k * p.ldT;
-                if (c < 32) cp_async16(sA + (size_t)(stage * KCH + kk) * SA + 2 * c, src + i0 + 2 * c);
-                else cp_async16(sB + (size_t)(stage * KCH + kk) * SB + 2 * (c - 32), src + j0 + 2 * (c - 32));
-            }
-        }
+    auto issue_chunk = [&](int chunk, int stage) {                            // one thread
+        mbar_expect_tx(&full[stage], (uint32_t)(KCH * (SA + SB) * sizeof(double)));
+        tma_load_2d(sA + stage * KCH * SA, &map_a, i0, chunk * KCH, &full[stage]);
+        tma_load_2d(sB + stage * KCH * SB, &map_b, j0, chunk * KCH, &full[stage]);
     };
     if constexpr (kWeighted) {
-        if (n_chunks > 0) load_chunk(0, 0);
-        cp_async_commit();
-        if (n_chunks > 1) load_chunk(1, 1);
-        cp_async_commit();
+        if (tid == 0) {
+            for (int st = 0; st < NSTAGE; st++) mbar_init(&full[st], 1);
+            mbar_init_fence();
+            for (int c = 0; c < NSTAGE && c < n_chunks; c++) issue_chunk(c, c);
+        }
     }
-    // ---- cells start cleared, per-tree scalars go to shared memory -----------------------------------------------------------------
+    const uint32_t ev0 = p.tile_off[t], ev1 = p.tile_cnt[t];
+    // ---- per-tree scalars: requested now (threads 0..95), parked in registers, put into shared memory just before the epilogue -------
+    int sc_s = 0; double sc_q1 = 0.0, sc_q2 = 0.0;
+    if (tid < TR + TC) {
+        const int tree = tid < TR ? i0 + tid : j0 + (tid - TR);
+        sc_s = p.nsplits[tree];
+        if constexpr (kWRF) sc_q1 = p.q1[tree];
+        if constexpr (kEUC) sc_q2 = p.q2t[tree];
+    }
+    // ---- cells start cleared ---------------------------------------------------------------------------------------------------------
     {
         if constexpr (kWRF) { double2 *z = reinterpret_cast<double2 *>(E1); for (int e = tid; e < TR * ES / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
         if constexpr (kEUC) { double2 *z = reinterpret_cast<double2 *>(E2); for (int e = tid; e < TR * ES / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
         for (int e = tid; e < TR * TC / 4; e += NT) cnt32[e] = 0u;
-        if (tid < TR + TC) {
-            const int64_t tree = tid < TR ? i0 + tid : j0 + (tid - TR);
-            sS[tid] = p.nsplits[tree];
-            if constexpr (kWRF) sQ1[tid] = p.q1[tree];
-            if constexpr (kEUC) sQ2[tid] = p.q2t[tree];
-        }
     }
     __syncthreads();
-    // ---- this tile's events ------------------------------------------------------------------------------------------------------
-    for (uint32_t o = ev0 + tid; o < ev1; o += NT) {
-        const int cell = p.ev_cell[o];
+    TRACE(1);
+    // ---- this tile's events: one aligned load per record.  The first EVR records of every thread are requested now and applied after
+    // the first leaf chunks (their latency hides behind the tensor-core work, and the refill of the ring behind the atomics).
+    constexpr int EVR = REC == 32 ? 1 : 2;
+    const uint32_t n_ev = ev1 - ev0;
+    const unsigned char *rec = reinterpret_cast<const unsigned char *>(p.ev) + (size_t)ev0 * REC;
+    int4 pre[EVR][2];
+    auto load_rec = [&](uint32_t o, int4 &v, int4 &w) {
+        if constexpr (REC == 4) v.x = (int)reinterpret_cast<const uint32_t *>(rec)[o];
+        else if constexpr (REC == 16) v = reinterpret_cast<const int4 *>(rec)[o];
+        else { v = reinterpret_cast<const int4 *>(rec)[2 * o]; w = reinterpret_cast<const int4 *>(rec)[2 * o + 1]; }
+    };
+    auto apply_rec = [&](const int4 &v, const int4 &w) {
+        const uint32_t cell = REC == 4 ? (uint32_t)v.x : (REC == 16 ? (uint32_t)v.z : (uint32_t)w.x);
         atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
         const int slot = (cell >> 5) * ES + (cell & 31);
-        if constexpr (kEUC) atomicAdd(&E2[slot], p.ev_t2[o]);
-        if constexpr (kWRF) atomicAdd(&E1[slot], p.ev_t1[o]);
-    }
+        if constexpr (REC == 16) { if constexpr (kEUC) atomicAdd(&E2[slot], __hiloint2double(v.y, v.x)); else atomicAdd(&E1[slot], __hiloint2double(v.y, v.x)); }
+        if constexpr (REC == 32) { atomicAdd(&E2[slot], __hiloint2double(v.y, v.x)); atomicAdd(&E1[slot], __hiloint2double(v.w, v.z)); }
+    };
+#pragma unroll
+    for (int e = 0; e < EVR; e++) { pre[e][0] = make_int4(0, 0, 0, 0); pre[e][1] = pre[e][0]; if (tid + e * NT < n_ev) load_rec(tid + e * NT, pre[e][0], pre[e][1]); }
+    auto apply_events = [&]() {
+#pragma unroll
+        for (int e = 0; e < EVR; e++) if (tid + e * NT < n_ev) apply_rec(pre[e][0], pre[e][1]);
+        for (uint32_t o = EVR * NT + tid; o < n_ev; o += NT) { int4 v = make_int4(0, 0, 0, 0), w = v; load_rec(o, v, w); apply_rec(v, w); }
+    };
+    TRACE(2);
 
     // ---- leaf edges: dot products on the fp64 tensor cores (euc), |a - b| sums on the fp64 pipe (wrf) ------------------------------
     double dot[2][2][2] = {}, l1[2][2][2] = {};        // [row block][column block][element] of the warp's 16 x 16 tile
     if constexpr (kWeighted) {
         for (int chunk = 0; chunk < n_chunks; chunk++) {
-            const int stage = chunk & 1;
-            cp_async_wait<1>();
-            __syncthreads();
-            const double *cA = sA + (size_t)stage * KCH * SA + wr * 16 + g, *cB = sB + (size_t)stage * KCH * SB + wc * 16;
+            const int stage = chunk % NSTAGE;
+            mbar_wait(&full[stage], (chunk / NSTAGE) & 1);
+            const double *cA = sA + stage * KCH * SA + wr * 16 + g, *cB = sB + stage * KCH * SB + wc * 16;
             const int k_here = min(KCH, k_used - chunk * KCH);
             auto step4 = [&](int k0) {
                 if constexpr (kEUC) {
@@ -278,12 +343,23 @@ __global__ void __launch_bounds__(NT, 3) pair_dense_kernel(const __grid_constant
             } else {
                 for (int k0 = 0; k0 < k_here; k0 += 4) step4(k0);
             }
-            __syncthreads();
-            if (chunk + 2 < n_chunks) load_chunk(chunk + 2, stage);
-            cp_async_commit();
+            if (chunk + NSTAGE < n_chunks) {               // refill this stage once every warp is done with it
+                __syncthreads();
+                if (tid == 0) issue_chunk(chunk + NSTAGE, stage);
+            }
+            if (chunk == min(NSTAGE, n_chunks) - 1) apply_events();
         }
-        if (n_chunks == 0) __syncthreads();
-        // fold the leaf sums into the cells this thread owns (all events have landed: every thread passed a barrier after its atomics)
+    }
+    if (!kWeighted || n_chunks == 0) apply_events();
+    TRACE(3);
+    if (tid < TR + TC) {
+        sS[tid] = sc_s;
+        if constexpr (kWRF) sQ1[tid] = sc_q1;
+        if constexpr (kEUC) sQ2[tid] = sc_q2;
+    }
+    __syncthreads();                                       // all event atomics have landed, scalars are in place
+    if constexpr (kWeighted) {
+        // fold the leaf sums into the cells this thread owns (DMMA fragment layout)
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
@@ -298,11 +374,14 @@ __global__ void __launch_bounds__(NT, 3) pair_dense_kernel(const __grid_constant
                     double2 v = *q; v.x += l1[r][c][0]; v.y += l1[r][c][1]; *q = v;
                 }
             }
+        __syncthreads();
     }
-    __syncthreads();
+    TRACE(4);
 
-    // ---- out: warp w writes rows 8w .. 8w+7, lane = column: whole 256-byte row segments ----------------------------------------------
-    const int64_t j = j0 + lane;
+    // ---- out: warp w writes rows 8w .. 8w+7, lane = column: whole 256-byte row segments.  Branch-free over the 8 rows so that the
+    // square roots (long dependent chains) overlap; stores are predicated.
+    const int j = j0 + lane;
+    const bool col_ok = j < p.col_end && (!RECT || j >= p.col_offset);
     const int s_j = sS[TR + lane];
     double q1j = 0.0, q2j = 0.0, sumj = 0.0, normj = 0.0;
     if constexpr (kWRF) q1j = sQ1[TR + lane];
@@ -311,62 +390,86 @@ __global__ void __launch_bounds__(NT, 3) pair_dense_kernel(const __grid_constant
         if constexpr (kWRF) sumj = p.sum_len[j];
         if constexpr (kEUC) normj = p.norm[j];
     }
-#pragma unroll 2
+    const int iw = i0 + warp * 8;
+    // condensed index of (iw, j); row iw + r is at idx0 + r (N - iw - 2) - r (r - 1) / 2   (rectangular: idx0 + r n_cols)
+    const int64_t idx0 = (RECT ? (int64_t)iw * p.n_cols - p.col_offset : ((int64_t)iw * p.N - (int64_t)iw * (iw + 1) / 2 - iw - 1 - p.p_base)) + j;
+    uint32_t ok = 0, risky = 0;
+    double v1[8], v2[8];
+    int common[8];
+#pragma unroll
     for (int rr = 0; rr < 8; rr++) {
-        const int row = warp * 8 + rr;
-        const int64_t i = i0 + row;
-        if (i < p.row_begin || i >= p.row_end) continue;                                   // warp-uniform
-        if (j >= p.col_end || (RECT ? j < p.col_offset : j <= i)) {}
-        else {
-        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
-        const int common = cnt[row * TC + lane];
-        if constexpr (kRF) {
-            const int den = sS[row] + s_j;
-            double v = (double)(den - 2 * common);
-            if constexpr (NORM) v = den ? v / (double)den : 0.0;
-            p.out[0][idx] = v;
+        const int row = warp * 8 + rr, i = iw + rr;
+        ok |= (uint32_t)(col_ok && i >= p.row_begin && i < p.row_end && (RECT || j > i)) << rr;
+        common[rr] = cnt[row * TC + lane];
+        bool rk = common[rr] >= 3;                         // the order of >= 3 atomic adds is not fixed
+        v1[rr] = 0.0; v2[rr] = 0.0;
+        if constexpr (kWRF) {
+            const double q = sQ1[row] + q1j, e = E1[row * ES + lane];
+            rk |= -e > kRisk1 * q;                         // e already holds the (non-negative) leaf sum: only makes the test milder
+            v1[rr] = q + e;
         }
-        if constexpr (kWeighted) {
+        if constexpr (kEUC) {
+            const double q = sQ2[row] + q2j, e = E2[row * ES + lane];
+            rk |= -e > kRisk2 * q;
+            v2[rr] = fmax(q + e, 0.0);
+        }
+        risky |= (uint32_t)rk << rr;
+    }
+    if constexpr (kWeighted) {
+        risky &= ok;
+        while (risky) {                                    // rare: normally overwritten by the fix-up kernel
+            const int rr = __ffs(risky) - 1; risky &= risky - 1;
             double t1 = 0.0, t2 = 0.0;
-            bool risky = common >= 3;                      // the order of >= 3 atomic adds is not fixed
-            if constexpr (kWRF) {
-                const double q = sQ1[row] + q1j, e = E1[row * ES + lane];
-                risky |= -e > kRisk1 * q;                  // e already holds the (non-negative) leaf sum: only makes the test milder
-                t1 = q + e;
-            }
-            if constexpr (kEUC) {
-                const double q = sQ2[row] + q2j, e = E2[row * ES + lane];
-                risky |= -e > kRisk2 * q;
-                t2 = fmax(q + e, 0.0);
-            }
-            if (risky) queue_exact(p, i, j, t1, t2);       // normally overwritten by the fix-up kernel
-            if constexpr (kWRF) {
-                double v = t1;
-                if constexpr (NORM) { const double den = p.sum_len[i] + sumj; v = den != 0.0 ? v / den : 0.0; }
-                p.out[1][idx] = v;
-            }
-            if constexpr (kEUC) {
-                double v = sqrt(t2);
-                if constexpr (NORM) { const double den = p.norm[i] + normj; v = den != 0.0 ? v / den : 0.0; }
-                p.out[2][idx] = v;
-            }
-        }
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (q == rr) { t1 = v1[q]; t2 = v2[q]; }
+            queue_exact(p, iw + rr, j, t1, t2);
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (q == rr) { v1[q] = t1; v2[q] = t2; }
         }
     }
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        const int row = warp * 8 + rr, i = iw + rr;
+        const int64_t idx = idx0 + (RECT ? (int64_t)rr * p.n_cols : (int64_t)rr * (p.N - iw - 2) - rr * (rr - 1) / 2);
+        const bool st = ok >> rr & 1u;
+        if constexpr (kRF) {
+            const int den = sS[row] + s_j;
+            double v = (double)(den - 2 * common[rr]);
+            if constexpr (NORM) v = den ? v / (double)den : 0.0;
+            if (st) p.out[0][idx] = v;
+        }
+        if constexpr (kWRF) {
+            double v = v1[rr];
+            if constexpr (NORM) { const double den = (st ? p.sum_len[i] : 1.0) + sumj; v = den != 0.0 ? v / den : 0.0; }
+            if (st) p.out[1][idx] = v;
+        }
+        if constexpr (kEUC) {
+            double v = sqrt(v2[rr]);
+            if constexpr (NORM) { const double den = (st ? p.norm[i] : 1.0) + normj; v = den != 0.0 ? v / den : 0.0; }
+            if (st) p.out[2][idx] = v;
+        }
+    }
+    TRACE(5);
+#ifdef PS_TRACE
+    if (tid == 0 && p.trace) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.trace[t * 8 + 6] = sm; p.trace[t * 8 + 7] = ev1 - ev0; }
+#endif
 }
 
 template <uint32_t MASK, bool RECT>
-cudaError_t launch_dense(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dense(const PairParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     auto k = p.normalise ? pair_dense_kernel<MASK, RECT, true> : pair_dense_kernel<MASK, RECT, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, NT, smem, st>>>(p);
+    CUtensorMap ma, mb;
+    if (p.tmap_a && p.tmap_b) { memcpy(&ma, p.tmap_a, sizeof ma); memcpy(&mb, p.tmap_b, sizeof mb); }
+    else { if (MASK & 6u) return cudaErrorInvalidValue; memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb); }
+    k<<<grid, NT, smem, st>>>(p, ma, mb);
     return cudaGetLastError();
 }
 
 template <bool RECT>
-cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     switch (mask & 7u) {
         case 1: return launch_dense<1, RECT>(p, grid, smem, st);
@@ -380,23 +483,54 @@ cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, unsigned grid,
     return cudaErrorInvalidValue;
 }
 
-template <bool WEIGHTED, bool RECT>
-cudaError_t launch_postings(const PairParams &p, bool fill, unsigned grid, cudaStream_t st)
+template <bool RECT>
+cudaError_t launch_postings(int wmode, const PairParams &p, bool fill, unsigned grid, cudaStream_t st)
 {
-    if (fill) pair_postings_kernel<WEIGHTED, RECT, true><<<grid, 256, 0, st>>>(p);
-    else pair_postings_kernel<false, RECT, false><<<grid, 256, 0, st>>>(p);
+    if (!fill) pair_postings_kernel<0, RECT, false><<<grid, 256, 0, st>>>(p);
+    else switch (wmode) {
+        case 0: pair_postings_kernel<0, RECT, true><<<grid, 256, 0, st>>>(p); break;
+        case 1: pair_postings_kernel<1, RECT, true><<<grid, 256, 0, st>>>(p); break;
+        case 2: pair_postings_kernel<2, RECT, true><<<grid, 256, 0, st>>>(p); break;
+        default: pair_postings_kernel<3, RECT, true><<<grid, 256, 0, st>>>(p); break;
+    }
     return cudaGetLastError();
 }
 
 }  // namespace
 
+// 2-D tensor maps over the taxon-major leaf matrix leafT [n_k][ldT] (fp64): boxes of KCH taxon rows x 68 (row trees) or 36 (column
+// trees) values.  The 4 surplus values per row only pad the shared-memory row stride to 4 mod 16 doubles (conflict-free fragments).
+cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, void *tmap_a, void *tmap_b)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    const cuuint64_t dims[2] = {(cuuint64_t)ldT, (cuuint64_t)n_k};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldT * sizeof(double)};      // bytes between taxon rows
+    const cuuint32_t estr[2] = {1, 1};
+    for (int which = 0; which < 2; which++) {
+        const cuuint32_t box[2] = {(cuuint32_t)(which ? SB : SA), (cuuint32_t)KCH};
+        CUresult r = encode(reinterpret_cast<CUtensorMap *>(which ? tmap_b : tmap_a), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(leafT), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+
 size_t pairsplit_dense_smem_bytes(uint32_t mask)
 {
-    size_t s = TR * TC + (TR + TC) * sizeof(int);
-    if (mask & 6u) s += 2 * KCH * (SA + SB) * sizeof(double);
+    size_t s = 128 + NSTAGE * 8 + TR * TC + (TR + TC) * sizeof(int);
+    if (mask & 6u) s += NSTAGE * KCH * (SA + SB) * sizeof(double);
     if (mask & 2u) s += (TR * ES + TR + TC) * sizeof(double);
     if (mask & 4u) s += (TR * ES + TR + TC) * sizeof(double);
     return s;
+}
+
+int pairsplit_record_bytes(uint32_t mask) { return rec_bytes(wmode_of(mask));
 }
 
 // number of 64 x 32 tiles of this launch (the length of p.tile_cnt); fills the tile geometry of p
@@ -409,6 +543,7 @@ long long pairsplit_tiles(bool rect, PairParams &p)
     if (rect) {
         p.col_tile0 = (int)(p.col_offset / TC);
         p.tiles_x = (int)(col_tiles_total - p.col_tile0);
+        p.tri_rows = (int)tile_rows;
         grid = tile_rows * p.tiles_x;
     } else {
         p.col_tile0 = 0;
@@ -418,6 +553,7 @@ long long pairsplit_tiles(bool rect, PairParams &p)
         int64_t rows = tile_rows;
         while (rows > 0 && L0 - 2 * (rows - 1) <= 0) rows--;
         grid = rows * L0 - rows * (rows - 1);
+        p.tri_rows = (int)rows;
     }
     p.n_tiles = grid > 0 ? grid : 0;
     return p.n_tiles;
@@ -434,10 +570,12 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         long long blocks = (p.n_post + 7) / 8;                      // one warp per postings entry, capped at a few waves
         if (blocks > 16ll * n_sms) blocks = 16ll * n_sms;
         for (int fill = 0; fill < 2 && e == cudaSuccess; fill++) {
-            if (weighted) e = rect ? launch_postings<true, true>(p, fill, (unsigned)blocks, st) : launch_postings<true, false>(p, fill, (unsigned)blocks, st);
-            else e = rect ? launch_postings<false, true>(p, fill, (unsigned)blocks, st) : launch_postings<false, false>(p, fill, (unsigned)blocks, st);
+            e = rect ? launch_postings<true>(wmode_of(mask), p, fill, (unsigned)blocks, st) : launch_postings<false>(wmode_of(mask), p, fill, (unsigned)blocks, st);
             ++*launches;
-            if (e == cudaSuccess && !fill) { tile_scan_kernel<<<1, 1024, 0, st>>>(p.tile_cnt, p.tile_off, p.n_tiles); e = cudaGetLastError(); ++*launches; }
+            if (e == cudaSuccess && !fill) {
+                tile_alloc_kernel<<<(unsigned)((p.n_tiles + 255) / 256), 256, 0, st>>>(p.tile_cnt, p.tile_off, p.n_tiles);
+                e = cudaGetLastError(); ++*launches;
+            }
         }
         if (e != cudaSuccess) return e;
     } else {
@@ -445,7 +583,10 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         if (e != cudaSuccess) return e;
     }
     const size_t smem_d = pairsplit_dense_smem_bytes(mask);
-    e = rect ? launch_dense_mask<true>(mask, p, (unsigned)p.n_tiles, smem_d, st) : launch_dense_mask<false>(mask, p, (unsigned)p.n_tiles, smem_d, st);
+    // rectangular: (column tiles, tile rows); triangular: tile rows u and R-1-u folded into one grid row
+    const dim3 grid = rect ? dim3((unsigned)p.tiles_x, (unsigned)p.tri_rows)
+                           : dim3((unsigned)(2 * (p.tiles_x - 2 * p.tile_row0) - 2 * (p.tri_rows - 1)), (unsigned)((p.tri_rows + 1) / 2));
+    e = rect ? launch_dense_mask<true>(mask, p, grid, smem_d, st) : launch_dense_mask<false>(mask, p, grid, smem_d, st);
     ++*launches;
     if (e != cudaSuccess || !weighted) return e;
     ++*launches;
