@@ -116,9 +116,7 @@ class TreeSet(object):
         handle = ctypes.c_void_p()
         if newicks and all(isinstance(s, str) for s in newicks) and not any('\0' in s for s in newicks[:1]):
             # one join + one encode instead of one bytes object and one pointer per tree
-            joined = ('\0'.join(newicks) + '\0').encode()
-            if joined.count(b'\0') != len(newicks):
-                raise ValueError('Newick strings must not contain NUL characters')
+            joined = ('\0'.join(newicks) + '\0').encode()        # the library checks that it holds exactly len(newicks) strings
             check(lib.td_encode_newick_joined(joined, len(joined), len(newicks), int(n_threads), ctypes.byref(handle)))
         else:
             raw = [_b(s) for s in newicks]

@@ -453,7 +453,7 @@ int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_t
     std::vector<const char *> ptrs; ptrs.reserve((size_t)n_trees);
     const char *p = buffer, *end = buffer + total_bytes;
     while (p < end && (int64_t)ptrs.size() < n_trees) { ptrs.push_back(p); p = (const char *)memchr(p, 0, (size_t)(end - p)) + 1; }
-    if ((int64_t)ptrs.size() != n_trees) { set_error("buffer holds %lld strings, expected %lld", (long long)ptrs.size(), (long long)n_trees); return TD_ERR_ARG; }
+    if ((int64_t)ptrs.size() != n_trees || p != end) { set_error("the buffer does not hold exactly %lld NUL-terminated strings (embedded NUL?)", (long long)n_trees); return TD_ERR_ARG; }
     return td_encode_newick(ptrs.data(), n_trees, n_threads, out);
 }
 

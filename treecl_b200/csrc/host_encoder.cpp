@@ -414,7 +414,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     lap("pack");
     // ---- global split dictionary (exact: ties on the 64-bit hash are resolved by comparing the masks) --------
     struct Ent { uint64_t h; uint32_t tree, slot; };
-    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0);
+    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0), sid_of((size_t)N * stride, 0);
     if (total > 0) {
         std::vector<int64_t> off(N + 1, 0);
         for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
@@ -430,7 +430,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         { std::vector<int64_t> pos(bstart.begin(), bstart.end() - 1); for (auto &en : ents) sorted[pos[en.h >> 56]++] = en; }
         ents.clear(); ents.shrink_to_fit();
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
-        std::vector<int64_t> uniq(NB + 1, 0), shared(NB, 0);
+        std::vector<int64_t> uniq(NB + 1, 0), shared(NB + 1, 0), shent(NB + 1, 0);
         std::vector<double> copairs(NB, 0.0);
         parallel_for(NB, n_threads, [&](int64_t b, int) {
             auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
@@ -440,28 +440,45 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
                 if (c) return c < 0;
                 return x.tree < y.tree;
             });
-            int64_t u = 0, sh = 0; double cp = 0;
+            int64_t u = 0, sh = 0, she = 0; double cp = 0;
             for (auto it = lo; it != hi;) {
                 auto run = it + 1;
                 while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
-                u++; if (run - it >= 2) sh++;
+                u++; if (run - it >= 2) { sh++; she += run - it; }
                 cp += 0.5 * (double)(run - it) * (double)(run - it - 1);
                 it = run;
             }
-            uniq[b + 1] = u; shared[b] = sh; copairs[b] = cp;
+            uniq[b + 1] = u; shared[b + 1] = sh; shent[b + 1] = she; copairs[b] = cp;
         });
         double cp_total = 0;
-        for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; hs.dict_shared += shared[b]; cp_total += copairs[b]; }
+        for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; shared[b + 1] += shared[b]; shent[b + 1] += shent[b]; cp_total += copairs[b]; }
+        hs.dict_shared = shared[NB];
         hs.total_common = (int64_t)(cp_total + 0.5);
         hs.mean_common = N > 1 ? cp_total / (0.5 * (double)N * (double)(N - 1)) : 0.0;
         hs.dict_size = uniq[NB];
+        const int64_t n_post = shent[NB];
+        if (n_post >= (1ll << 31)) { set_error("too many shared-split entries (%lld)", (long long)n_post); return TD_ERR_UNSUPPORTED; }
+        // ids, multiplicities, the compact index of the shared splits (column of the incidence matrix) and their postings: a run of
+        // equal splits in the sorted bucket IS the posting list of that split (trees ascending)
+        hs.post_tree.resize(n_post); hs.post_end.resize(n_post); hs.post_len.resize(n_post);
         parallel_for(NB, n_threads, [&](int64_t b, int) {
             auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
-            int64_t id = uniq[b];
+            int64_t id = uniq[b], sid = shared[b], x = shent[b];
             for (auto it = lo; it != hi;) {
                 auto run = it + 1;
                 while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
-                for (auto k = it; k != run; k++) { id_of[(size_t)k->tree * stride + k->slot] = (uint32_t)id; mult_of[(size_t)k->tree * stride + k->slot] = (uint32_t)(run - it); }
+                const bool is_shared = run - it >= 2;
+                const int64_t x_end = x + (run - it);
+                for (auto k = it; k != run; k++) {
+                    const size_t at = (size_t)k->tree * stride + k->slot;
+                    id_of[at] = (uint32_t)id; mult_of[at] = (uint32_t)(run - it);
+                    if (is_shared) {
+                        sid_of[at] = (uint32_t)sid;
+                        hs.post_tree[x] = (int32_t)k->tree; hs.post_end[x] = (int32_t)x_end; hs.post_len[x] = enc[k->tree].lens[k->slot];
+                        x++;
+                    }
+                }
+                if (is_shared) sid++;
                 id++; it = run;
             }
         });
@@ -470,6 +487,17 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     // ---- per-tree lists sorted by dictionary id; shared-split lists ------------------------------------------
     std::vector<int32_t> nsh(N, 0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
+        int sh = 0;
+        for (int s = 0; s < hs.n_splits[i]; s++) sh += mult_of[(size_t)i * stride + s] >= 2;
+        nsh[i] = sh;
+    });
+    int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
+    hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
+    for (int64_t b = 0; b < N; b += kTile) { int tot = 0; for (int64_t i = b; i < std::min<int64_t>(N, b + kTile); i++) tot += nsh[i]; hs.max_tile_entries = std::max(hs.max_tile_entries, tot); }
+    hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
+    hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
+    hs.q2t.assign(N, 0.0);
+    parallel_for(N, n_threads, [&](int64_t i, int) {
         const int S = hs.n_splits[i];
         std::vector<int> perm(S);
         for (int s = 0; s < S; s++) perm[s] = s;
@@ -477,64 +505,19 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         int sh = 0; double s1 = 0, s2 = 0, t1 = 0, t2 = 0;
         for (int k = 0; k < S; k++) {
             const int s = perm[k];
+            const size_t at = (size_t)i * stride + s;
+            const double len = enc[i].lens[s];
             memcpy(&hs.masks[((size_t)i * stride + k) * W], &enc[i].masks[(size_t)s * W], W * 8);
-            hs.lens[(size_t)i * stride + k] = enc[i].lens[s];
-            hs.ids[(size_t)i * stride + k] = id_of[(size_t)i * stride + s];
-            t1 += std::fabs(enc[i].lens[s]); t2 += enc[i].lens[s] * enc[i].lens[s];
-            if (mult_of[(size_t)i * stride + s] >= 2) sh++;
-            else { s1 += std::fabs(enc[i].lens[s]); s2 += enc[i].lens[s] * enc[i].lens[s]; }
+            hs.lens[(size_t)i * stride + k] = len;
+            hs.ids[(size_t)i * stride + k] = id_of[at];
+            t1 += std::fabs(len); t2 += len * len;
+            if (mult_of[at] >= 2) hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len};
+            else { s1 += std::fabs(len); s2 += len * len; }
         }
-        nsh[i] = sh; hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2;
-    });
-    int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
-    hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
-    for (int64_t b = 0; b < N; b += kTile) { int tot = 0; for (int64_t i = b; i < std::min<int64_t>(N, b + kTile); i++) tot += nsh[i]; hs.max_tile_entries = std::max(hs.max_tile_entries, tot); }
-    hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
-    hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
-    // compact index of every shared split (column of the incidence matrix X): rank among the shared dictionary ids
-    std::vector<uint32_t> sid_of((size_t)std::max<int64_t>(hs.dict_size, 1), kSentinelId);
-    {
-        std::vector<uint8_t> is_shared(sid_of.size(), 0);
-        for (int64_t i = 0; i < N; i++)
-            for (int s = 0; s < hs.n_splits[i]; s++)
-                if (mult_of[(size_t)i * stride + s] >= 2) is_shared[id_of[(size_t)i * stride + s]] = 1;
-        uint32_t next = 0;
-        for (size_t d = 0; d < sid_of.size(); d++) if (is_shared[d]) sid_of[d] = next++;
-    }
-    parallel_for(N, n_threads, [&](int64_t i, int) {
-        const int S = hs.n_splits[i]; int k = 0;
-        // mult_of is indexed by the pre-sort slot: recover through the id (ids are unique inside one tree)
-        std::vector<std::pair<uint32_t, uint32_t>> m(S);
-        for (int s = 0; s < S; s++) m[s] = {id_of[(size_t)i * stride + s], mult_of[(size_t)i * stride + s]};
-        std::sort(m.begin(), m.end());
-        for (int s = 0; s < S; s++)
-            if (m[s].second >= 2) {
-                const uint32_t id = hs.ids[(size_t)i * stride + s];
-                hs.shared[(size_t)i * hs.sh_stride + k++] = SplitRec{id, sid_of[id], hs.lens[(size_t)i * stride + s]};
-            }
-    });
-    // postings: counting sort of the shared-list entries by compact split index (trees visited in ascending order)
-    {
-        std::vector<int64_t> poff((size_t)hs.dict_shared + 2, 0);
-        for (int64_t i = 0; i < N; i++)
-            for (int k = 0; k < nsh[i]; k++) poff[hs.shared[(size_t)i * hs.sh_stride + k].pad + 1]++;
-        for (int64_t d = 0; d <= hs.dict_shared; d++) poff[d + 1] += poff[d];
-        const int64_t n_post = poff[hs.dict_shared];
-        if (n_post >= (1ll << 31)) { set_error("too many shared-split entries (%lld)", (long long)n_post); return TD_ERR_UNSUPPORTED; }
-        hs.post_tree.resize(n_post); hs.post_end.resize(n_post); hs.post_len.resize(n_post);
-        std::vector<int64_t> fill(poff.begin(), poff.end() - 1);
-        for (int64_t i = 0; i < N; i++)
-            for (int k = 0; k < nsh[i]; k++) {
-                const SplitRec &r = hs.shared[(size_t)i * hs.sh_stride + k];
-                const int64_t x = fill[r.pad]++;
-                hs.post_tree[x] = (int32_t)i; hs.post_end[x] = (int32_t)poff[r.pad + 1]; hs.post_len[x] = r.len;
-            }
-    }
-    hs.q2t.assign(N, 0.0);
-    parallel_for(N, n_threads, [&](int64_t i, int) {
-        double s = 0.0;
-        for (int k = 0; k < n_taxa; k++) { const double l = hs.leaflen[(size_t)i * n_taxa + k]; s += l * l; }
-        hs.q2t[i] = hs.q2[i] + s;
+        hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2;
+        double sl = 0.0;
+        for (int k = 0; k < n_taxa; k++) { const double l = hs.leaflen[(size_t)i * n_taxa + k]; sl += l * l; }
+        hs.q2t[i] = t2 + sl;
     });
     lap("lists");
     return TD_OK;
