@@ -80,7 +80,7 @@ struct DeviceSet {
     SplitRec *shared = nullptr;
     int32_t *nsplits = nullptr, *nshared = nullptr;
     double *sum_len = nullptr, *norm = nullptr, *single_l1 = nullptr, *single_l2 = nullptr, *q1 = nullptr, *q2 = nullptr, *q2t = nullptr;
-    int32_t *post_tree = nullptr, *post_end = nullptr;
+    int32_t *post_tree = nullptr, *post_end = nullptr, *shared_x = nullptr;
     double *post_len = nullptr;
     int64_t n_post = 0;
     uint32_t *ids = nullptr;
@@ -181,7 +181,7 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         const size_t o_nsplits = take(Npad * 4), o_nshared = take(Npad * 4);
         const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8), o_q2t = take(Npad * 8);
         const size_t n_post = h.post_tree.size();
-        const size_t o_ptree = take(n_post * 4), o_pend = take(n_post * 4), o_plen = take(n_post * 8);
+        const size_t o_ptree = take(n_post * 4), o_pend = take(n_post * 4), o_plen = take(n_post * 8), o_shx = take(Npad * d->sh_stride * 4);
         const size_t o_ids = take(N * d->stride * 4), o_lens = take(N * d->stride * 8), o_masks = take(N * d->stride * d->W * 8);
         const size_t o_leafmask = take(N * d->W * 8), o_rooted = take(N * 4);
         const size_t o_counter = take(kCounters * 8), o_stats = take(4 * 8), o_err = take(4), o_wlc = take(kWorklists * 4);
@@ -195,7 +195,7 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         d->sum_len = (double *)(base + o_sum); d->norm = (double *)(base + o_norm); d->single_l1 = (double *)(base + o_s1);
         d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2); d->q2t = (double *)(base + o_q2t);
         d->post_tree = (int32_t *)(base + o_ptree); d->post_end = (int32_t *)(base + o_pend); d->post_len = (double *)(base + o_plen);
-        d->n_post = (int64_t)n_post;
+        d->n_post = (int64_t)n_post; d->shared_x = (int32_t *)(base + o_shx);
         d->ids = (uint32_t *)(base + o_ids); d->lens = (double *)(base + o_lens); d->masks = (uint64_t *)(base + o_masks);
         d->leafmask = (uint64_t *)(base + o_leafmask); d->rooted = (int32_t *)(base + o_rooted);
         d->work_counter = (unsigned long long *)(base + o_counter); d->stats = (unsigned long long *)(base + o_stats);
@@ -206,6 +206,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
 
     CUDA_TRY(cudaMemcpyAsync(d->leaflen, h.leaflen.data(), N * h.n_taxa * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->shared, h.shared.data(), N * d->sh_stride * sizeof(SplitRec), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d->shared_x, 0xFF, Npad * d->sh_stride * sizeof(int32_t), st));
+    CUDA_TRY(cudaMemcpyAsync(d->shared_x, h.shared_x.data(), N * d->sh_stride * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->nsplits, h.n_splits.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->nshared, h.n_shared.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->sum_len, h.sum_len.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -278,10 +280,11 @@ static int pick_tile(const DeviceSet *d, bool weighted)
 
 constexpr size_t kEventBytesMax = 6ull << 30;       // above this the fused (single kernel) hash join is used instead
 
-static size_t split_event_bytes(int64_t capacity, long long tiles, int rec)
+static size_t split_event_bytes(const DeviceSet *d, int64_t capacity, int rec)
 {
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return 2 * up((size_t)(tiles + 1) * 4) + up((size_t)capacity * rec);
+    const size_t groups = (size_t)d->Npad / pairsplit_row_group(), col_tiles = ((size_t)d->N + 31) / 32;
+    return 256 + up(groups * col_tiles * sizeof(uint2)) + up((size_t)capacity * rec);
 }
 
 // postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
@@ -290,7 +293,7 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     const long long tiles = pairsplit_tiles(rect, p);
     if (tiles <= 0) return TD_OK;
     std::lock_guard<std::mutex> g(d->ev_mu);
-    const size_t need = split_event_bytes(capacity, tiles, pairsplit_record_bytes(m3));
+    const size_t need = split_event_bytes(d, capacity, pairsplit_record_bytes(m3));
     if (!d->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
     if (need > d->ev_block_bytes) {
         CUDA_TRY(cudaEventSynchronize(d->ev_done));
@@ -301,15 +304,17 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
         d->ev_block = (unsigned char *)blk; d->ev_block_bytes = need; d->ev_block_got = got;
     }
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t groups = (size_t)d->Npad / pairsplit_row_group(), col_tiles = ((size_t)d->N + 31) / 32;
     unsigned char *b = d->ev_block;
-    p.tile_cnt = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
-    p.tile_off = (uint32_t *)b; b += up((size_t)(tiles + 1) * 4);
+    p.ev_cursor = (uint32_t *)b; b += 256;
+    p.seg = (uint2 *)b; b += up(groups * col_tiles * sizeof(uint2));
     p.ev = b;
     p.ev_capacity = (uint32_t)capacity;
+    p.col_tiles_total = (int)col_tiles; p.rg0 = p.tile_row0 * (64 / pairsplit_row_group());
     p.tmap_a = d->leaf_maps ? d->tmap_leaf_a : nullptr; p.tmap_b = d->leaf_maps ? d->tmap_leaf_b : nullptr;
-    p.post_tree = d->post_tree; p.post_end = d->post_end; p.post_len = d->post_len; p.n_post = d->n_post; p.q2t = d->q2t;
+    p.post_tree = d->post_tree; p.post_end = d->post_end; p.post_len = d->post_len; p.n_post = d->n_post; p.q2t = d->q2t; p.shared_x = d->shared_x;
     CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
-    CUDA_TRY(cudaMemsetAsync(p.tile_cnt, 0, (size_t)(tiles + 1) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(p.ev_cursor, 0, sizeof(uint32_t), st));
     int launches = 0;
     unsigned long long *trace = nullptr;
     const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
@@ -368,7 +373,8 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (force && !strcmp(force, "merge")) use_join = false;
         if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile") || !strcmp(force, "split")) && join_fits) use_join = true;
         const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
-        const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(ev_capacity, 1, 32) <= kEventBytesMax;
+        const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
+                                && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         const bool use_split = use_join && split_fits && !(force && (!strcmp(force, "join") || !strcmp(force, "join_tile")));
         const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }

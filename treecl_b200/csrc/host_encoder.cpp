@@ -414,7 +414,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     lap("pack");
     // ---- global split dictionary (exact: ties on the 64-bit hash are resolved by comparing the masks) --------
     struct Ent { uint64_t h; uint32_t tree, slot; };
-    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0), sid_of((size_t)N * stride, 0);
+    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0), sid_of((size_t)N * stride, 0), x_of((size_t)N * stride, 0);
     if (total > 0) {
         std::vector<int64_t> off(N + 1, 0);
         for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
@@ -473,7 +473,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
                     const size_t at = (size_t)k->tree * stride + k->slot;
                     id_of[at] = (uint32_t)id; mult_of[at] = (uint32_t)(run - it);
                     if (is_shared) {
-                        sid_of[at] = (uint32_t)sid;
+                        sid_of[at] = (uint32_t)sid; x_of[at] = (uint32_t)x;
                         hs.post_tree[x] = (int32_t)k->tree; hs.post_end[x] = (int32_t)x_end; hs.post_len[x] = enc[k->tree].lens[k->slot];
                         x++;
                     }
@@ -496,6 +496,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     for (int64_t b = 0; b < N; b += kTile) { int tot = 0; for (int64_t i = b; i < std::min<int64_t>(N, b + kTile); i++) tot += nsh[i]; hs.max_tile_entries = std::max(hs.max_tile_entries, tot); }
     hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
     hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
+    hs.shared_x.assign((size_t)N * hs.sh_stride, -1);
     hs.q2t.assign(N, 0.0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
         const int S = hs.n_splits[i];
@@ -511,7 +512,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
             hs.lens[(size_t)i * stride + k] = len;
             hs.ids[(size_t)i * stride + k] = id_of[at];
             t1 += std::fabs(len); t2 += len * len;
-            if (mult_of[at] >= 2) hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len};
+            if (mult_of[at] >= 2) { hs.shared_x[(size_t)i * hs.sh_stride + sh] = (int32_t)x_of[at]; hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len}; }
             else { s1 += std::fabs(len); s2 += len * len; }
         }
         hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2;

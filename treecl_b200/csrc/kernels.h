@@ -30,7 +30,10 @@ struct PairParams {
     const double *q2t;        // [Npad] sum of squares of ALL edge lengths (internal + leaf)
     const void *tmap_a, *tmap_b;   // host copies of the CUtensorMaps over leafT (make_leaf_tensor_maps)
     void *ev;                 // event records (layout depends on the metric mask, see kernels_pairsplit.cu)
-    uint32_t *tile_cnt, *tile_off;
+    const int32_t *shared_x;  // [Npad][sh_stride] position of every shared-list entry in the postings (-1: none)
+    uint2 *seg;               // [Npad / 16][col_tiles_total] (offset, count) of the events of (row group, column tile)
+    uint32_t *ev_cursor;      // next free record of the event buffer
+    int col_tiles_total, rg0; // ceil(N / 32); first row group of this launch
     uint32_t ev_capacity;
     unsigned long long *trace;   // debug builds (-DPS_TRACE): 8 clock stamps per tile
     int64_t N;                // trees
@@ -56,6 +59,8 @@ cudaError_t launch_pairjoin(uint32_t mask, bool rect, PairParams p, int n_sms, b
 cudaError_t launch_exact_fixup(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st);
 size_t pairsplit_dense_smem_bytes(uint32_t mask);
 int pairsplit_record_bytes(uint32_t mask);
+size_t pairsplit_events_smem_bytes(uint32_t mask, int sh_stride, int col_tiles_total);
+int pairsplit_row_group();
 cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, void *tmap_a, void *tmap_b);
 long long pairsplit_tiles(bool rect, PairParams &p);
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);

@@ -96,69 +96,138 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 __host__ __device__ constexpr int wmode_of(uint32_t mask) { return (int)((mask >> 1) & 3u); }
 __host__ __device__ constexpr int rec_bytes(int wmode) { return wmode == 0 ? 4 : (wmode == 3 ? 32 : 16); }
 
-template <int WMODE, bool RECT, bool FILL>
-__global__ void __launch_bounds__(256) pair_postings_kernel(const PairParams p)
+constexpr int RG = 16;                // trees per row group: one CTA of pair_events_kernel; a 64-row tile reads 64 / RG segments
+
+// One CTA per ROW GROUP of RG consecutive trees: all events (i, j) with i in the group, binned by column tile j / 32.
+//   entries : the group's shared-list entries, each with its position x in the postings; entry (d, i) owns the events
+//             (i, post_tree[b]) for b in (x, post_end[x])
+//   count   : the events are numbered 0 .. T-1 over all entries (block scan of the entry sizes); thread k takes events k, k + 256, ...
+//             (entry by binary search in the scanned sizes), so all global reads are independent and coalesce along a posting list;
+//             a shared-memory histogram over the column tiles counts them
+//   place   : block scan of the histogram, ONE global atomicAdd claims the group's contiguous range of the event buffer
+//   fill    : the same walk again, slots from shared-memory atomics, one aligned record store per event
+// and the (offset, count) of every (row group, column tile) segment goes to the segment table for pair_dense_kernel.
+// Nothing but the range claim touches a global atomic, and there is no separate count / scan / fill launch.
+constexpr int EVT = 1024;             // threads of pair_events_kernel
+constexpr int EVU = 4;                // events per thread and step of the walks (independent global reads in flight)
+
+template <int WMODE, bool RECT>
+__global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant__ PairParams p)
 {
-    constexpr bool WEIGHTED = WMODE != 0;
-    const int lane = threadIdx.x & 31;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long L0 = p.tiles_x - 2 * p.tile_row0;
-    long long x = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int i = 0, end = 0; double la = 0.0;
-    if (x < p.n_post) { i = p.post_tree[x]; end = p.post_end[x]; if constexpr (WEIGHTED && FILL) la = p.post_len[x]; }
-    while (x < p.n_post) {
-        // the next entry's header is fetched before this one's group is walked (one global round trip less per entry)
-        const long long xn = x + n_warps;
-        int in = 0, endn = 0; double lan = 0.0;
-        if (xn < p.n_post) { in = p.post_tree[xn]; endn = p.post_end[xn]; if constexpr (WEIGHTED && FILL) lan = p.post_len[xn]; }
-        if (i >= p.row_begin && i < p.row_end) {
-            const int tile_r = i >> 6;
-            const long long u = tile_r - p.tile_row0;
-            const long long base_t = RECT ? u * p.tiles_x - p.col_tile0 : u * L0 - u * (u - 1) - 2 * tile_r;
-            for (long long b = x + 1 + lane; b < end; b += 32) {
-                const int j = p.post_tree[b];
-                uint32_t *c = p.tile_cnt + (base_t + (j >> 5));
-                if (RECT && j < p.col_offset) {}                   // the other set's own side: not a pair of this launch
-                else if constexpr (!FILL) atomicAdd(c, 1u);
+    extern __shared__ __align__(16) unsigned char ev_smem[];
+    const int n_ent = RG * p.sh_stride, ct = p.col_tiles_total;
+    double *ent_len = reinterpret_cast<double *>(ev_smem);                                 // [n_ent]     (weighted only, else unused)
+    uint32_t *ent_off = reinterpret_cast<uint32_t *>(ev_smem + (WMODE ? (size_t)n_ent * 8 : 0));   // [n_ent + 1]
+    int *ent_x = reinterpret_cast<int *>(ent_off + n_ent + 1);                             // [n_ent]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ent_x + n_ent);                          // [ct]
+    __shared__ uint32_t warp_sum[EVT / 32];
+    __shared__ uint32_t s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = blockIdx.x + p.rg0, tree0 = rg * RG;
+
+    // block-wide exclusive scan of one value per thread; returns the exclusive prefix, the total through `total`
+    auto block_scan = [&](uint32_t v, uint32_t &total) -> uint32_t {
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        __syncthreads();                                   // warp_sum may still be read from a previous call
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t ws = warp_sum[lane], wi = ws;             // EVT / 32 == 32 warp sums: one per lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+        total = __shfl_sync(0xffffffffu, wi, 31);
+        const uint32_t before = __shfl_sync(0xffffffffu, wi - ws, warp);
+        return before + incl - v;
+    };
+
+    // ---- entries (e = position * RG + local tree) and their sizes ------------------------------------------------------------------------
+    for (int c = tid; c < ct; c += EVT) hist[c] = 0u;
+    const int per = (n_ent + EVT - 1) / EVT, e_lo = min(tid * per, n_ent), e_hi = min(e_lo + per, n_ent);
+    uint32_t mine = 0;
+    for (int e = e_lo; e < e_hi; e++) {
+        const int i = tree0 + (e & (RG - 1)), pos = e / RG;
+        int x = -1;
+        if (i >= p.row_begin && i < p.row_end) x = p.shared_x[(size_t)i * p.sh_stride + pos];
+        uint32_t n = 0;
+        if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[e] = p.post_len[x]; }
+        ent_x[e] = x; ent_off[e] = n; mine += n;
+    }
+    uint32_t T;
+    uint32_t run = block_scan(mine, T);
+    for (int e = e_lo; e < e_hi; e++) { const uint32_t n = ent_off[e]; ent_off[e] = run; run += n; }
+    if (tid == EVT - 1) ent_off[n_ent] = T;
+    __syncthreads();
+
+    auto entry_of = [&](uint32_t k) {                      // last entry e with ent_off[e] <= k (entries of size 0 are skipped over)
+        int lo = 0, hi = n_ent;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ent_off[mid] <= k) lo = mid; else hi = mid; }
+        return lo;
+    };
+    // ---- count: EVU independent reads of the postings per thread and step ---------------------------------------------------------------------
+    for (uint32_t k0 = tid; k0 < T; k0 += EVT * EVU) {
+        int j[EVU];
+#pragma unroll
+        for (int u = 0; u < EVU; u++) {
+            const uint32_t k = k0 + u * EVT;
+            j[u] = -1;
+            if (k < T) { const int e = entry_of(k); j[u] = p.post_tree[ent_x[e] + 1 + (int)(k - ent_off[e])]; }
+        }
+#pragma unroll
+        for (int u = 0; u < EVU; u++)
+            if (j[u] >= (RECT ? (int)p.col_offset : 0)) atomicAdd(&hist[j[u] >> 5], 1u);
+    }
+    __syncthreads();
+    // ---- place: scan the histogram, claim the range, publish the segment table --------------------------------------------------------------
+    {
+        const int cper = (ct + EVT - 1) / EVT, c_lo = min(tid * cper, ct), c_hi = min(c_lo + cper, ct);
+        uint32_t sum = 0;
+        for (int c = c_lo; c < c_hi; c++) sum += hist[c];
+        uint32_t total;
+        uint32_t at = block_scan(sum, total);
+        if (tid == 0) s_base = total ? atomicAdd(p.ev_cursor, total) : 0u;
+        __syncthreads();
+        at += s_base;
+        uint2 *seg = p.seg + (size_t)rg * ct;
+        for (int c = c_lo; c < c_hi; c++) { const uint32_t n = hist[c]; seg[c] = make_uint2(at, n); hist[c] = at; at += n; }
+    }
+    __syncthreads();
+    // ---- fill ----------------------------------------------------------------------------------------------------------------------------
+    for (uint32_t k0 = tid; k0 < T; k0 += EVT * EVU) {
+        int j[EVU], ee[EVU]; double lb[EVU];
+#pragma unroll
+        for (int u = 0; u < EVU; u++) {
+            const uint32_t k = k0 + u * EVT;
+            j[u] = -1; ee[u] = 0; lb[u] = 0.0;
+            if (k < T) {
+                const int e = entry_of(k), b = ent_x[e] + 1 + (int)(k - ent_off[e]);
+                ee[u] = e; j[u] = p.post_tree[b];
+                if constexpr (WMODE) lb[u] = p.post_len[b];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EVU; u++) {
+            uint32_t o = 0xFFFFFFFFu;
+            if (j[u] >= (RECT ? (int)p.col_offset : 0)) o = atomicAdd(&hist[j[u] >> 5], 1u);   // else: no event / the other set's own side
+            if (o < p.ev_capacity) {
+                const uint32_t cell = (uint32_t)((((tree0 + (ee[u] & (RG - 1))) & 63) << 5) | (j[u] & 31));
+                if constexpr (WMODE == 0) reinterpret_cast<uint32_t *>(p.ev)[o] = cell;
                 else {
-                    const uint32_t o = atomicAdd(c, 1u);            // tile_cnt was set to the tile's offset by tile_alloc_kernel
-                    if (o < p.ev_capacity) {
-                        const uint32_t cell = (uint32_t)(((i & 63) << 5) | (j & 31));
-                        if constexpr (WMODE == 0) reinterpret_cast<uint32_t *>(p.ev)[o] = cell;
-                        else {
-                            const double lb = p.post_len[b];
-                            const double t2 = -2.0 * la * lb, t1 = fabs(la - lb) - fabs(la) - fabs(lb);
-                            int4 *dst = reinterpret_cast<int4 *>(p.ev) + (size_t)o * (rec_bytes(WMODE) / 16);
-                            if constexpr (WMODE == 3) {
-                                dst[0] = make_int4(__double2loint(t2), __double2hiint(t2), __double2loint(t1), __double2hiint(t1));
-                                dst[1] = make_int4((int)cell, 0, 0, 0);
-                            } else {
-                                const double t = WMODE == 2 ? t2 : t1;
-                                dst[0] = make_int4(__double2loint(t), __double2hiint(t), (int)cell, 0);
-                            }
-                        }
+                    const double la = ent_len[ee[u]];
+                    const double t2 = -2.0 * la * lb[u], t1 = fabs(la - lb[u]) - fabs(la) - fabs(lb[u]);
+                    int4 *dst = reinterpret_cast<int4 *>(p.ev) + (size_t)o * (rec_bytes(WMODE) / 16);
+                    if constexpr (WMODE == 3) {
+                        dst[0] = make_int4(__double2loint(t2), __double2hiint(t2), __double2loint(t1), __double2hiint(t1));
+                        dst[1] = make_int4((int)cell, 0, 0, 0);
+                    } else {
+                        const double tv = WMODE == 2 ? t2 : t1;
+                        dst[0] = make_int4(__double2loint(tv), __double2hiint(tv), (int)cell, 0);
                     }
                 }
             }
         }
-        x = xn; i = in; end = endn; la = lan;
     }
-}
-
-// Give every tile its own segment of the event buffer: off[t] = cnt[t] = start of the segment (the fill pass then advances cnt[t]
-// to the segment's end).  Segments are claimed from a cursor (cnt[n]) with one atomicAdd per warp, in no particular order.
-__global__ void __launch_bounds__(256) tile_alloc_kernel(uint32_t *cnt, uint32_t *off, long long n)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const uint32_t c = t < n ? cnt[t] : 0u;
-    uint32_t incl = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    uint32_t base = 0;
-    if (lane == 31 && incl) base = atomicAdd(cnt + n, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (t < n) { off[t] = base + incl - c; cnt[t] = base + incl - c; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -262,7 +331,13 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             for (int c = 0; c < NSTAGE && c < n_chunks; c++) issue_chunk(c, c);
         }
     }
-    const uint32_t ev0 = p.tile_off[t], ev1 = p.tile_cnt[t];
+    // this tile's events: one segment per row group
+    uint2 sg[TR / RG];
+    {
+        const uint2 *segp = p.seg + (size_t)(tile_r * (TR / RG)) * p.col_tiles_total + tile_c;
+#pragma unroll
+        for (int q = 0; q < TR / RG; q++) sg[q] = segp[(size_t)q * p.col_tiles_total];
+    }
     // ---- per-tree scalars: requested now (threads 0..95), parked in registers, put into shared memory just before the epilogue -------
     int sc_s = 0; double sc_q1 = 0.0, sc_q2 = 0.0;
     if (tid < TR + TC) {
@@ -282,10 +357,12 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     // ---- this tile's events: one aligned load per record.  The first EVR records of every thread are requested now and applied after
     // the first leaf chunks (their latency hides behind the tensor-core work, and the refill of the ring behind the atomics).
     constexpr int EVR = REC == 32 ? 1 : 2;
-    const uint32_t n_ev = ev1 - ev0;
-    const unsigned char *rec = reinterpret_cast<const unsigned char *>(p.ev) + (size_t)ev0 * REC;
+    static_assert(TR / RG == 4, "four row groups per tile");
+    const uint32_t n0 = sg[0].y, n1 = n0 + sg[1].y, n2 = n1 + sg[2].y, n_ev = n2 + sg[3].y;
+    const unsigned char *rec = reinterpret_cast<const unsigned char *>(p.ev);
     int4 pre[EVR][2];
-    auto load_rec = [&](uint32_t o, int4 &v, int4 &w) {
+    auto load_rec = [&](uint32_t k, int4 &v, int4 &w) {
+        const size_t o = k < n0 ? sg[0].x + k : (k < n1 ? sg[1].x + (k - n0) : (k < n2 ? sg[2].x + (k - n1) : sg[3].x + (k - n2)));
         if constexpr (REC == 4) v.x = (int)reinterpret_cast<const uint32_t *>(rec)[o];
         else if constexpr (REC == 16) v = reinterpret_cast<const int4 *>(rec)[o];
         else { v = reinterpret_cast<const int4 *>(rec)[2 * o]; w = reinterpret_cast<const int4 *>(rec)[2 * o + 1]; }
@@ -451,7 +528,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     }
     TRACE(5);
 #ifdef PS_TRACE
-    if (tid == 0 && p.trace) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.trace[t * 8 + 6] = sm; p.trace[t * 8 + 7] = ev1 - ev0; }
+    if (tid == 0 && p.trace) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.trace[t * 8 + 6] = sm; p.trace[t * 8 + 7] = n_ev; }
 #endif
 }
 
@@ -484,16 +561,20 @@ cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, dim3 grid, siz
 }
 
 template <bool RECT>
-cudaError_t launch_postings(int wmode, const PairParams &p, bool fill, unsigned grid, cudaStream_t st)
+cudaError_t launch_events(int wmode, const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
-    if (!fill) pair_postings_kernel<0, RECT, false><<<grid, 256, 0, st>>>(p);
-    else switch (wmode) {
-        case 0: pair_postings_kernel<0, RECT, true><<<grid, 256, 0, st>>>(p); break;
-        case 1: pair_postings_kernel<1, RECT, true><<<grid, 256, 0, st>>>(p); break;
-        case 2: pair_postings_kernel<2, RECT, true><<<grid, 256, 0, st>>>(p); break;
-        default: pair_postings_kernel<3, RECT, true><<<grid, 256, 0, st>>>(p); break;
+    auto run = [&](auto k) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, EVT, smem, st>>>(p);
+        return cudaGetLastError();
+    };
+    switch (wmode) {
+        case 0: return run(pair_events_kernel<0, RECT>);
+        case 1: return run(pair_events_kernel<1, RECT>);
+        case 2: return run(pair_events_kernel<2, RECT>);
+        default: return run(pair_events_kernel<3, RECT>);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace
@@ -559,27 +640,27 @@ long long pairsplit_tiles(bool rect, PairParams &p)
     return p.n_tiles;
 }
 
-// p must carry the tile geometry (pairsplit_tiles), the postings and the event buffers; tile_cnt must be zero
+size_t pairsplit_events_smem_bytes(uint32_t mask, int sh_stride, int col_tiles_total)
+{
+    const size_t n_ent = (size_t)RG * sh_stride;
+    return (wmode_of(mask) ? n_ent * 8 : 0) + (n_ent + 1) * 4 + n_ent * 4 + (size_t)col_tiles_total * 4 + 16;
+}
+int pairsplit_row_group() { return RG; }
+
+// p must carry the tile geometry (pairsplit_tiles), the postings, the segment table and the event buffer; *ev_cursor must be zero
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches)
 {
     *launches = 0;
     if (p.n_tiles <= 0) return cudaSuccess;
     const bool weighted = (mask & 6u) != 0;
     cudaError_t e = cudaSuccess;
-    if (p.n_post > 0) {
-        long long blocks = (p.n_post + 7) / 8;                      // one warp per postings entry, capped at a few waves
-        if (blocks > 16ll * n_sms) blocks = 16ll * n_sms;
-        for (int fill = 0; fill < 2 && e == cudaSuccess; fill++) {
-            e = rect ? launch_postings<true>(wmode_of(mask), p, fill, (unsigned)blocks, st) : launch_postings<false>(wmode_of(mask), p, fill, (unsigned)blocks, st);
-            ++*launches;
-            if (e == cudaSuccess && !fill) {
-                tile_alloc_kernel<<<(unsigned)((p.n_tiles + 255) / 256), 256, 0, st>>>(p.tile_cnt, p.tile_off, p.n_tiles);
-                e = cudaGetLastError(); ++*launches;
-            }
-        }
-        if (e != cudaSuccess) return e;
-    } else {
-        e = cudaMemsetAsync(p.tile_off, 0, (size_t)(p.n_tiles + 1) * 4, st);
+    {
+        // the row groups of all tile rows of this launch (p.rg0 = first group of the first tile row): the kernel writes their rows of
+        // the segment table completely, rows outside [row_begin, row_end) as empty segments
+        const long long groups = (long long)p.tri_rows * (TR / RG);
+        const size_t smem_e = pairsplit_events_smem_bytes(mask, p.sh_stride, p.col_tiles_total);
+        e = rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, smem_e, st);
+        ++*launches;
         if (e != cudaSuccess) return e;
     }
     const size_t smem_d = pairsplit_dense_smem_bytes(mask);

@@ -49,6 +49,7 @@ struct HostSet {
     // shared-split lists (splits that occur in >= 2 trees), sentinel padded, stride sh_stride
     int32_t sh_stride = 0;
     std::vector<SplitRec> shared;              // [N][sh_stride]
+    std::vector<int32_t> shared_x;             // [N][sh_stride] position of the entry in the postings, -1 = none
 
     // postings of the shared splits: entries grouped by split, trees ascending inside a group.  post_end[x] is the end of x's
     // group, so "all later holders of the split of entry x" is the range (x, post_end[x]).
