@@ -35,7 +35,7 @@ constexpr int TR = 64, TC = 32;       // tile: rows x columns
 constexpr int NT = 256;
 constexpr int KCH = 16;               // taxa per staged chunk
 #ifndef PS_NSTAGE
-#define PS_NSTAGE 2
+#define PS_NSTAGE 4
 #endif
 #ifndef PS_MINB
 #define PS_MINB 3
@@ -77,6 +77,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (done) return;
         if (spins > (1u << 24)) __trap();          // watchdog: never hang the GPU on a lost transaction
     }
+}
+
+// bytes of the per-cell slots (E1, E2, counts) and of the region they share with the ring of leaf chunks
+__host__ __device__ constexpr size_t kCellBytes(uint32_t mask)
+{
+    return ((mask & 2u) ? TR * ES * sizeof(double) : 0) + ((mask & 4u) ? TR * ES * sizeof(double) : 0) + TR * TC;
+}
+__host__ __device__ constexpr size_t kRegionBytes(uint32_t mask)
+{
+    const size_t ring = (mask & 6u) ? (size_t)NSTAGE * KCH * (SA + SB) * sizeof(double) : 0, cells = (kCellBytes(mask) + 127) & ~(size_t)127;
+    return ring > cells ? ring : cells;
 }
 
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
@@ -295,21 +306,27 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     const long long t = RECT ? (long long)u * p.tiles_x + x : (long long)u * L0 - (long long)u * (u - 1) + x;
     const int i0 = tile_r * TR, j0 = tile_c * TC;
 
+    // Shared memory.  The ring of leaf chunks and the per-cell slots share one region: the slots are only needed once the leaf sums are
+    // in registers (the ring holds NSTAGE * KCH = 64 taxa, so up to 64 taxa there is no refill and no barrier inside the k-loop).
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *cur = smem_raw;
     double *E1 = nullptr, *E2 = nullptr, *sA = nullptr, *sB = nullptr, *sQ1 = nullptr, *sQ2 = nullptr;
-    if constexpr (kWeighted) {                                                                             // TMA destinations: 128-byte aligned
-        sA = reinterpret_cast<double *>(cur); cur += NSTAGE * KCH * SA * sizeof(double);
-        sB = reinterpret_cast<double *>(cur); cur += NSTAGE * KCH * SB * sizeof(double);
+    {
+        unsigned char *c2 = cur;                                                                           // cells
+        if constexpr (kWRF) { E1 = reinterpret_cast<double *>(c2); c2 += TR * ES * sizeof(double); }
+        if constexpr (kEUC) { E2 = reinterpret_cast<double *>(c2); c2 += TR * ES * sizeof(double); }
     }
-    if constexpr (kWRF) { E1 = reinterpret_cast<double *>(cur); cur += TR * ES * sizeof(double); }
-    if constexpr (kEUC) { E2 = reinterpret_cast<double *>(cur); cur += TR * ES * sizeof(double); }
+    unsigned char *cnt = cur + kCellBytes(MASK) - TR * TC;                                                 // [TR*TC] common splits
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
+    if constexpr (kWeighted) {                                                                             // ring: TMA destinations, 128-byte aligned
+        sA = reinterpret_cast<double *>(cur);
+        sB = reinterpret_cast<double *>(cur + NSTAGE * KCH * SA * sizeof(double));
+    }
+    cur += kRegionBytes(MASK);
     uint64_t *full = reinterpret_cast<uint64_t *>(cur); cur += NSTAGE * 8;                                 // one mbarrier per stage
     if constexpr (kWRF) { sQ1 = reinterpret_cast<double *>(cur); cur += (TR + TC) * sizeof(double); }     // rows, then columns
     if constexpr (kEUC) { sQ2 = reinterpret_cast<double *>(cur); cur += (TR + TC) * sizeof(double); }
     int *sS = reinterpret_cast<int *>(cur); cur += (TR + TC) * sizeof(int);                                // internal edges per tree
-    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cur);
-    const unsigned char *cnt = cur;                                                                        // [TR*TC] common splits
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;            // DMMA fragment coordinates
@@ -346,16 +363,9 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
         if constexpr (kWRF) sc_q1 = p.q1[tree];
         if constexpr (kEUC) sc_q2 = p.q2t[tree];
     }
-    // ---- cells start cleared ---------------------------------------------------------------------------------------------------------
-    {
-        if constexpr (kWRF) { double2 *z = reinterpret_cast<double2 *>(E1); for (int e = tid; e < TR * ES / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
-        if constexpr (kEUC) { double2 *z = reinterpret_cast<double2 *>(E2); for (int e = tid; e < TR * ES / 2; e += NT) z[e] = make_double2(0.0, 0.0); }
-        for (int e = tid; e < TR * TC / 4; e += NT) cnt32[e] = 0u;
-    }
-    __syncthreads();
     TRACE(1);
     // ---- this tile's events: one aligned load per record.  The first EVR records of every thread are requested now and applied after
-    // the first leaf chunks (their latency hides behind the tensor-core work, and the refill of the ring behind the atomics).
+    // the leaf sums (their latency hides behind the tensor-core work).
     constexpr int EVR = REC == 32 ? 1 : 2;
     static_assert(TR / RG == 4, "four row groups per tile");
     const uint32_t n0 = sg[0].y, n1 = n0 + sg[1].y, n2 = n1 + sg[2].y, n_ev = n2 + sg[3].y;
@@ -424,19 +434,30 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
                 __syncthreads();
                 if (tid == 0) issue_chunk(chunk + NSTAGE, stage);
             }
-            if (chunk == min(NSTAGE, n_chunks) - 1) apply_events();
         }
     }
-    if (!kWeighted || n_chunks == 0) apply_events();
     TRACE(3);
+    __syncthreads();                                       // the ring is drained: its memory now holds the per-cell slots
+    // every thread clears the cells it owns (DMMA fragment layout)
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int row = wr * 16 + r * 8 + g, col = wc * 16 + c * 8 + 2 * t4;
+            if constexpr (kEUC) *reinterpret_cast<double2 *>(E2 + row * ES + col) = make_double2(0.0, 0.0);
+            if constexpr (kWRF) *reinterpret_cast<double2 *>(E1 + row * ES + col) = make_double2(0.0, 0.0);
+            *reinterpret_cast<uint16_t *>(cnt + row * TC + col) = 0;
+        }
     if (tid < TR + TC) {
         sS[tid] = sc_s;
         if constexpr (kWRF) sQ1[tid] = sc_q1;
         if constexpr (kEUC) sQ2[tid] = sc_q2;
     }
-    __syncthreads();                                       // all event atomics have landed, scalars are in place
+    __syncthreads();
+    apply_events();                                        // sums of <= 2 corrections starting from 0 do not depend on the order
+    __syncthreads();                                       // all event atomics have landed
     if constexpr (kWeighted) {
-        // fold the leaf sums into the cells this thread owns (DMMA fragment layout)
+        // fold the leaf sums into the cells this thread owns
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
@@ -604,10 +625,9 @@ cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, voi
 
 size_t pairsplit_dense_smem_bytes(uint32_t mask)
 {
-    size_t s = 128 + NSTAGE * 8 + TR * TC + (TR + TC) * sizeof(int);
-    if (mask & 6u) s += NSTAGE * KCH * (SA + SB) * sizeof(double);
-    if (mask & 2u) s += (TR * ES + TR + TC) * sizeof(double);
-    if (mask & 4u) s += (TR * ES + TR + TC) * sizeof(double);
+    size_t s = 128 + kRegionBytes(mask) + NSTAGE * 8 + (TR + TC) * sizeof(int);
+    if (mask & 2u) s += (TR + TC) * sizeof(double);
+    if (mask & 4u) s += (TR + TC) * sizeof(double);
     return s;
 }
 
