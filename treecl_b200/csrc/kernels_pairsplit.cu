@@ -90,6 +90,22 @@ __host__ __device__ constexpr size_t kRegionBytes(uint32_t mask)
     return ring > cells ? ring : cells;
 }
 
+// Order-independent accumulation of the corrections of one cell: 64-bit fixed point relative to the cell's own magnitude
+// Q = Q_i + Q_j.  Every correction and every partial sum is bounded by Q (2 la lb <= la^2 + lb^2;  | |la-lb| - |la| - |lb| | <= |la| + |lb|),
+// so with the scale 2^(61 - exponent(Q)) nothing overflows, the resolution is Q * 2^-61 (finer than fp64 rounding of Q + E), and integer
+// adds commute: any number of corrections per cell sums to the same bits in any order.
+struct FixScale { double to_fix, from_fix; };
+__device__ __forceinline__ FixScale fix_scale(double q)
+{
+    const int e = (__double2hiint(q) >> 20) & 0x7FF;                  // biased exponent of q (q >= 0)
+    FixScale f;
+    if (e > 61 && e < 2047 - 1) {                                      // normal range with room for both factors
+        f.to_fix = __hiloint2double((1023 + 61 + 1023 - e) << 20, 0);   // 2^(61 - (e - 1023))
+        f.from_fix = __hiloint2double((e - 61) << 20, 0);               // 2^((e - 1023) - 61)
+    } else { f.to_fix = 1.0; f.from_fix = 1.0; }                       // zero / denormal-scale sets: plain integers
+    return f;
+}
+
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -380,9 +396,16 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     auto apply_rec = [&](const int4 &v, const int4 &w) {
         const uint32_t cell = REC == 4 ? (uint32_t)v.x : (REC == 16 ? (uint32_t)v.z : (uint32_t)w.x);
         atomicAdd(&cnt32[cell >> 2], 1u << (8 * (cell & 3)));
-        const int slot = (cell >> 5) * ES + (cell & 31);
-        if constexpr (REC == 16) { if constexpr (kEUC) atomicAdd(&E2[slot], __hiloint2double(v.y, v.x)); else atomicAdd(&E1[slot], __hiloint2double(v.y, v.x)); }
-        if constexpr (REC == 32) { atomicAdd(&E2[slot], __hiloint2double(v.y, v.x)); atomicAdd(&E1[slot], __hiloint2double(v.w, v.z)); }
+        const int row = cell >> 5, col = cell & 31, slot = row * ES + col;
+        if constexpr (REC == 16) {
+            const double tv = __hiloint2double(v.y, v.x);
+            if constexpr (kEUC) atomicAdd(reinterpret_cast<unsigned long long *>(E2 + slot), (unsigned long long)__double2ll_rn(tv * fix_scale(sQ2[row] + sQ2[TR + col]).to_fix));
+            else atomicAdd(reinterpret_cast<unsigned long long *>(E1 + slot), (unsigned long long)__double2ll_rn(tv * fix_scale(sQ1[row] + sQ1[TR + col]).to_fix));
+        }
+        if constexpr (REC == 32) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(E2 + slot), (unsigned long long)__double2ll_rn(__hiloint2double(v.y, v.x) * fix_scale(sQ2[row] + sQ2[TR + col]).to_fix));
+            atomicAdd(reinterpret_cast<unsigned long long *>(E1 + slot), (unsigned long long)__double2ll_rn(__hiloint2double(v.w, v.z) * fix_scale(sQ1[row] + sQ1[TR + col]).to_fix));
+        }
     };
 #pragma unroll
     for (int e = 0; e < EVR; e++) { pre[e][0] = make_int4(0, 0, 0, 0); pre[e][1] = pre[e][0]; if (tid + e * NT < n_ev) load_rec(tid + e * NT, pre[e][0], pre[e][1]); }
@@ -444,7 +467,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const int row = wr * 16 + r * 8 + g, col = wc * 16 + c * 8 + 2 * t4;
-            if constexpr (kEUC) *reinterpret_cast<double2 *>(E2 + row * ES + col) = make_double2(0.0, 0.0);
+            if constexpr (kEUC) *reinterpret_cast<double2 *>(E2 + row * ES + col) = make_double2(0.0, 0.0);     // (all-zero bits: also 0 as int64)
             if constexpr (kWRF) *reinterpret_cast<double2 *>(E1 + row * ES + col) = make_double2(0.0, 0.0);
             *reinterpret_cast<uint16_t *>(cnt + row * TC + col) = 0;
         }
@@ -454,22 +477,32 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
         if constexpr (kEUC) sQ2[tid] = sc_q2;
     }
     __syncthreads();
-    apply_events();                                        // sums of <= 2 corrections starting from 0 do not depend on the order
+    apply_events();                                        // fixed-point integer adds: the order does not matter
     __syncthreads();                                       // all event atomics have landed
     if constexpr (kWeighted) {
-        // fold the leaf sums into the cells this thread owns
+        // the cells this thread owns: fixed point back to fp64, leaf sums folded in
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                const int slot = (wr * 16 + r * 8 + g) * ES + wc * 16 + c * 8 + 2 * t4;
+                const int row = wr * 16 + r * 8 + g, col = wc * 16 + c * 8 + 2 * t4, slot = row * ES + col;
                 if constexpr (kEUC) {
                     double2 *q = reinterpret_cast<double2 *>(E2 + slot);
-                    double2 v = *q; v.x = fma(-2.0, dot[r][c][0], v.x); v.y = fma(-2.0, dot[r][c][1], v.y); *q = v;
+                    const longlong2 a = *reinterpret_cast<const longlong2 *>(q);
+                    const double qi = sQ2[row];
+                    double2 v;
+                    v.x = fma(-2.0, dot[r][c][0], (double)a.x * fix_scale(qi + sQ2[TR + col]).from_fix);
+                    v.y = fma(-2.0, dot[r][c][1], (double)a.y * fix_scale(qi + sQ2[TR + col + 1]).from_fix);
+                    *q = v;
                 }
                 if constexpr (kWRF) {
                     double2 *q = reinterpret_cast<double2 *>(E1 + slot);
-                    double2 v = *q; v.x += l1[r][c][0]; v.y += l1[r][c][1]; *q = v;
+                    const longlong2 a = *reinterpret_cast<const longlong2 *>(q);
+                    const double qi = sQ1[row];
+                    double2 v;
+                    v.x = (double)a.x * fix_scale(qi + sQ1[TR + col]).from_fix + l1[r][c][0];
+                    v.y = (double)a.y * fix_scale(qi + sQ1[TR + col + 1]).from_fix + l1[r][c][1];
+                    *q = v;
                 }
             }
         __syncthreads();
@@ -499,7 +532,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
         const int row = warp * 8 + rr, i = iw + rr;
         ok |= (uint32_t)(col_ok && i >= p.row_begin && i < p.row_end && (RECT || j > i)) << rr;
         common[rr] = cnt[row * TC + lane];
-        bool rk = common[rr] >= 3;                         // the order of >= 3 atomic adds is not fixed
+        bool rk = false;
         v1[rr] = 0.0; v2[rr] = 0.0;
         if constexpr (kWRF) {
             const double q = sQ1[row] + q1j, e = E1[row * ES + lane];
