@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     // the leaf sums (their latency hides behind the tensor-core work).
     constexpr int EVR = REC == 32 ? 1 : 2;
     static_assert(TR / RG == 4, "four row groups per tile");
-    const uint32_t n0 = sg[0].y, n1 = n0 + sg[1].y, n2 = n1 + sg[2].y, n_ev = n2 + sg[3].y;
+    uint32_t n0 = 0, n1 = 0, n2 = 0, n_ev = 0;             // running sizes of the four segments (set when the table entries are first used)
     const unsigned char *rec = reinterpret_cast<const unsigned char *>(p.ev);
     int4 pre[EVR][2];
     auto load_rec = [&](uint32_t k, int4 &v, int4 &w) {
@@ -407,8 +407,13 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             atomicAdd(reinterpret_cast<unsigned long long *>(E1 + slot), (unsigned long long)__double2ll_rn(__hiloint2double(v.w, v.z) * fix_scale(sQ1[row] + sQ1[TR + col]).to_fix));
         }
     };
+    // requested after the first leaf chunk: by then the segment table entries have arrived, and the records arrive under the other chunks
+    auto prefetch_events = [&]() {
+        n0 = sg[0].y; n1 = n0 + sg[1].y; n2 = n1 + sg[2].y; n_ev = n2 + sg[3].y;
 #pragma unroll
-    for (int e = 0; e < EVR; e++) { pre[e][0] = make_int4(0, 0, 0, 0); pre[e][1] = pre[e][0]; if (tid + e * NT < n_ev) load_rec(tid + e * NT, pre[e][0], pre[e][1]); }
+        for (int e = 0; e < EVR; e++) { pre[e][0] = make_int4(0, 0, 0, 0); pre[e][1] = pre[e][0]; if (tid + e * NT < n_ev) load_rec(tid + e * NT, pre[e][0], pre[e][1]); }
+    };
+    if (!kWeighted || n_chunks == 0) prefetch_events();
     auto apply_events = [&]() {
 #pragma unroll
         for (int e = 0; e < EVR; e++) if (tid + e * NT < n_ev) apply_rec(pre[e][0], pre[e][1]);
@@ -453,6 +458,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             } else {
                 for (int k0 = 0; k0 < k_here; k0 += 4) step4(k0);
             }
+            if (chunk == 0) prefetch_events();
             if (chunk + NSTAGE < n_chunks) {               // refill this stage once every warp is done with it
                 __syncthreads();
                 if (tid == 0) issue_chunk(chunk + NSTAGE, stage);
