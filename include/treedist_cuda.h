@@ -64,7 +64,7 @@ typedef struct {
     int64_t dict_shared;     /* distinct splits held by >= 2 trees                                           */
     int64_t total_splits;
     int32_t device;          /* device the set is resident on, -1 if not uploaded                            */
-    int32_t reserved;
+    int32_t n_postings;      /* entries of the shared-split postings (= sum over trees of their shared-list lengths)      */
 } td_info;
 
 /* ---- host side: split encoder ------------------------------------------------------------------------ */
