@@ -80,6 +80,23 @@ def load():
     return lib
 
 
+_glue = False
+
+
+def _pyglue():
+    """The optional CPython helper (csrc/pyglue.c); None when it was not built or TREEDIST_NO_PYGLUE is set."""
+    global _glue
+    if _glue is False:
+        _glue = None
+        if not os.environ.get('TREEDIST_NO_PYGLUE'):
+            try:
+                from . import _pyglue as mod
+                _glue = mod
+            except ImportError:
+                pass
+    return _glue
+
+
 def check(rc):
     if rc == TD_OK:
         return
@@ -114,7 +131,13 @@ class TreeSet(object):
         lib = load()
         newicks = list(newicks)
         handle = ctypes.c_void_p()
-        if newicks and all(isinstance(s, str) for s in newicks) and not any('\0' in s for s in newicks[:1]):
+        glue = _pyglue()
+        if glue is not None and newicks:
+            # the interpreter's own UTF-8 buffers go to the library: no join, no copies
+            rc, h = glue.encode_list(newicks, ctypes.cast(lib.td_encode_newick, ctypes.c_void_p).value, int(n_threads))
+            check(rc)
+            handle = ctypes.c_void_p(h)
+        elif newicks and all(isinstance(s, str) for s in newicks):
             # one join + one encode instead of one bytes object and one pointer per tree
             joined = ('\0'.join(newicks) + '\0').encode()        # the library checks that it holds exactly len(newicks) strings
             check(lib.td_encode_newick_joined(joined, len(joined), len(newicks), int(n_threads), ctypes.byref(handle)))

@@ -369,7 +369,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         const int row_slots = pairjoin_row_table_slots(h.max_tile_entries);
         const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, row_slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024)
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
-        bool use_join = join_fits && h.mean_common <= 6.0;
+        bool use_join = join_fits && h.mean_common <= 9.0;        // measured crossover with the merge kernel: ~10 (tools/kernel_choice.py)
         if (force && !strcmp(force, "merge")) use_join = false;
         if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile") || !strcmp(force, "split")) && join_fits) use_join = true;
         const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
