@@ -118,6 +118,7 @@ CASES = [
     (2, 4, 'uniform'), (3, 5, 'uniform'), (65, 8, 'uniform'), (200, 20, 'uniform'), (130, 50, 'uniform'),
     (97, 64, 'uniform'), (70, 65, 'uniform'), (66, 100, 'uniform'), (40, 200, 'uniform'),
     (150, 30, 'structured'), (100, 100, 'structured'),
+    (333, 12, 'uniform'),          # five tile rows, N not a multiple of 16 / 32 / 64, many common splits per pair
 ]
 
 
@@ -130,7 +131,8 @@ def make(kind, n_trees, n_taxa, seed):
 
 @pytest.fixture
 def pair_kernel(request, monkeypatch):
-    """Force one of the two rf/wrf/euc kernels (hash join for sparse sharing, merge-join for dense) or let the library choose."""
+    """Force one of the rf/wrf/euc kernels (split = postings pipeline + fp64 tensor-core tile kernel, join / join_tile = fused hash
+    join, merge = shared-memory merge-join) or let the library choose."""
     if request.param != 'auto':
         monkeypatch.setenv('TREEDIST_PAIR_KERNEL', request.param)
     else:

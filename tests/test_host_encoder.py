@@ -173,3 +173,60 @@ def test_synthetic_sets_are_deterministic(lib_built):
     assert list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [17] * 6      # binary, trifurcating root: n-3
     s = _lib.TreeSet(synth.structured_trees(64, 30, n_classes=4, lam=0.5, seed=1))
     assert s.info.dict_size < 64 * 27 // 4            # shared structure -> small dictionary
+
+
+def test_marshalling_paths_build_the_same_set(lib_built, monkeypatch):
+    """The optional CPython helper (zero-copy pointer table) and the joined-buffer path must encode identically."""
+    from treecl_b200 import _lib, synth
+    trees = synth.uniform_trees(40, 17, seed=5) + synth.structured_trees(40, 17, n_classes=3, class_nni=3, lam=1.0, seed=6)
+
+    def snapshot():
+        ts = _lib.TreeSet(trees)
+        inf = ts.info
+        return ((inf.n_trees, inf.n_taxa, inf.max_splits, inf.max_shared, inf.dict_size, inf.dict_shared, inf.total_splits, inf.n_postings),
+                ts.get(_lib.TD_GET_IDS, np.uint32).copy(), ts.get(_lib.TD_GET_LENGTHS, np.float64).copy(),
+                ts.get(_lib.TD_GET_MASKS, np.uint64).copy(), ts.get(_lib.TD_GET_LEAFLEN, np.float64).copy())
+
+    monkeypatch.setattr(_lib, '_glue', False)
+    monkeypatch.delenv('TREEDIST_NO_PYGLUE', raising=False)
+    a = snapshot()
+    used_glue = _lib._pyglue() is not None
+    monkeypatch.setattr(_lib, '_glue', False)
+    monkeypatch.setenv('TREEDIST_NO_PYGLUE', '1')
+    b = snapshot()
+    assert _lib._pyglue() is None
+    assert a[0] == b[0]
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y)
+    # bytes input goes through either path as well
+    monkeypatch.setattr(_lib, '_glue', False)
+    monkeypatch.delenv('TREEDIST_NO_PYGLUE', raising=False)
+    ts = _lib.TreeSet([t.encode() for t in trees])
+    assert np.array_equal(ts.get(_lib.TD_GET_IDS, np.uint32), a[1])
+    assert used_glue or True          # the helper is optional; when it was built it has just been exercised
+
+
+@pytest.mark.parametrize('no_glue', ['', '1'])
+def test_embedded_nul_is_refused(lib_built, monkeypatch, no_glue):
+    from treecl_b200 import _lib
+    monkeypatch.setattr(_lib, '_glue', False)
+    if no_glue:
+        monkeypatch.setenv('TREEDIST_NO_PYGLUE', no_glue)
+    else:
+        monkeypatch.delenv('TREEDIST_NO_PYGLUE', raising=False)
+    with pytest.raises(ValueError):
+        _lib.TreeSet(['((a:1,b:1):1,(c:1,d:1):1);', '((a:1,c:1):1,\0(b:1,d:1):1);'])
+
+
+def test_postings_cover_exactly_the_shared_entries(lib_built):
+    """n_postings = number of (tree, split) entries whose split occurs in at least two trees (what the events kernel enumerates)."""
+    from treecl_b200 import _lib, synth
+    trees = synth.structured_trees(60, 24, n_classes=4, class_nni=3, lam=2.0, seed=11)
+    ts = _lib.TreeSet(trees)
+    inf = ts.info
+    ids = ts.get(_lib.TD_GET_IDS, np.uint32)
+    ids = ids[ids != 0xFFFFFFFF]
+    uniq, counts = np.unique(ids, return_counts=True)
+    assert inf.dict_size == uniq.size
+    assert inf.dict_shared == int((counts >= 2).sum())
+    assert inf.n_postings == int(counts[counts >= 2].sum())
