@@ -15,9 +15,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
 #include <functional>
 #include <mutex>
+#include <new>
+#include <pthread.h>
 #include <string_view>
 #include <thread>
 #include <unordered_map>
@@ -317,17 +320,97 @@ static inline uint64_t mask_hash(const uint64_t *m, int W)
     return h;
 }
 
+// Worker pool shared by all encode calls of the process: spawning 16 threads for each of the ~10 parallel sections of one encode
+// cost several milliseconds.  Workers sleep on a condition variable between sections; a section that finds the pool busy (another
+// encode running concurrently) falls back to plain threads.
+class WorkerPool {
+public:
+    explicit WorkerPool(int workers)
+    {
+        for (int t = 0; t < workers; t++) std::thread([this, t] { loop(t + 1); }).detach();
+        n_workers_ = workers;
+    }
+    int workers() const { return n_workers_; }
+    bool try_acquire() { return busy_.try_lock(); }
+    void release() { busy_.unlock(); }
+    // run job(tid) on the caller (tid 0) and on workers 1 .. n_threads-1; returns when all are done
+    void run(int n_threads, const std::function<void(int)> &job)
+    {
+        const int helpers = std::min(n_threads - 1, n_workers_);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            job_ = &job; helpers_ = helpers; pending_ = helpers; generation_++;
+        }
+        cv_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int tid)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *job = nullptr;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (tid <= helpers_) job = job_;
+            }
+            if (job) {
+                (*job)(tid);
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_, busy_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int helpers_ = 0, pending_ = 0, n_workers_ = 0;
+    uint64_t generation_ = 0;
+};
+
+static std::atomic<WorkerPool *> g_pool{nullptr};
+static std::mutex g_pool_mu;
+
+static WorkerPool *worker_pool()
+{
+    WorkerPool *p = g_pool.load(std::memory_order_acquire);
+    if (p) return p;
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    p = g_pool.load(std::memory_order_relaxed);
+    if (!p) {
+        // a forked child has none of the parent's threads: it starts over with a pool of its own (the parent's is simply abandoned)
+        static bool registered = false;
+        if (!registered) { pthread_atfork(nullptr, nullptr, [] { g_pool.store(nullptr); new (&g_pool_mu) std::mutex(); }); registered = true; }
+        p = new WorkerPool((int)std::max(1u, std::thread::hardware_concurrency()) - 1);   // never destroyed: workers are detached
+        g_pool.store(p, std::memory_order_release);
+    }
+    return p;
+}
+
 template <class F>
 static void parallel_for(int64_t n, int n_threads, F &&fn)
 {
     if (n_threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) fn(i, 0); return; }
     std::atomic<int64_t> next{0};
     const int64_t chunk = std::max<int64_t>(1, n / (n_threads * 16));
+    auto body = [&](int t) {
+        for (;;) { int64_t b = next.fetch_add(chunk); if (b >= n) break; int64_t e = std::min(n, b + chunk); for (int64_t i = b; i < e; i++) fn(i, t); }
+    };
+    WorkerPool *pool = worker_pool();
+    if (pool->workers() + 1 >= n_threads && pool->try_acquire()) {
+        const std::function<void(int)> job = body;
+        pool->run(n_threads, job);
+        pool->release();
+        return;
+    }
     std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++)
-        th.emplace_back([&, t] {
-            for (;;) { int64_t b = next.fetch_add(chunk); if (b >= n) break; int64_t e = std::min(n, b + chunk); for (int64_t i = b; i < e; i++) fn(i, t); }
-        });
+    for (int t = 0; t < n_threads; t++) th.emplace_back(body, t);
     for (auto &x : th) x.join();
 }
 

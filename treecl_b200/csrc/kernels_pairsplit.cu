@@ -40,7 +40,11 @@ constexpr int KCH = 16;               // taxa per staged chunk
 #ifndef PS_MINB
 #define PS_MINB 3
 #endif
+#ifndef PS_OB
+#define PS_OB 8
+#endif
 constexpr int NSTAGE = PS_NSTAGE;     // chunks in flight
+constexpr int OB = PS_OB;             // rows of the epilogue handled together
 constexpr int SA = 68, SB = 36;       // row strides (doubles) of the staged leaf chunks: = 4 mod 16 -> conflict-free DMMA fragments
 constexpr int ES = 40;                // row stride (doubles) of the per-cell slots: conflict-free 16-byte accesses of the C fragments
 constexpr double kRisk1 = 0.9;        // wrf: exact recompute when -E1 > kRisk1 * (Q1_i + Q1_j)
@@ -530,60 +534,63 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     const int iw = i0 + warp * 8;
     // condensed index of (iw, j); row iw + r is at idx0 + r (N - iw - 2) - r (r - 1) / 2   (rectangular: idx0 + r n_cols)
     const int64_t idx0 = (RECT ? (int64_t)iw * p.n_cols - p.col_offset : ((int64_t)iw * p.N - (int64_t)iw * (iw + 1) / 2 - iw - 1 - p.p_base)) + j;
-    uint32_t ok = 0, risky = 0;
-    double v1[8], v2[8];
-    int common[8];
+#pragma unroll 1
+    for (int r0 = 0; r0 < 8; r0 += OB) {                   // OB rows at a time (their square roots overlap)
+        uint32_t ok = 0, risky = 0;
+        double v1[OB], v2[OB];
+        int common[OB];
 #pragma unroll
-    for (int rr = 0; rr < 8; rr++) {
-        const int row = warp * 8 + rr, i = iw + rr;
-        ok |= (uint32_t)(col_ok && i >= p.row_begin && i < p.row_end && (RECT || j > i)) << rr;
-        common[rr] = cnt[row * TC + lane];
-        bool rk = false;
-        v1[rr] = 0.0; v2[rr] = 0.0;
-        if constexpr (kWRF) {
-            const double q = sQ1[row] + q1j, e = E1[row * ES + lane];
-            rk |= -e > kRisk1 * q;                         // e already holds the (non-negative) leaf sum: only makes the test milder
-            v1[rr] = q + e;
+        for (int rr = 0; rr < OB; rr++) {
+            const int row = warp * 8 + r0 + rr, i = iw + r0 + rr;
+            ok |= (uint32_t)(col_ok && i >= p.row_begin && i < p.row_end && (RECT || j > i)) << rr;
+            common[rr] = cnt[row * TC + lane];
+            bool rk = false;
+            v1[rr] = 0.0; v2[rr] = 0.0;
+            if constexpr (kWRF) {
+                const double q = sQ1[row] + q1j, e = E1[row * ES + lane];
+                rk |= -e > kRisk1 * q;                     // e already holds the (non-negative) leaf sum: only makes the test milder
+                v1[rr] = q + e;
+            }
+            if constexpr (kEUC) {
+                const double q = sQ2[row] + q2j, e = E2[row * ES + lane];
+                rk |= -e > kRisk2 * q;
+                v2[rr] = fmax(q + e, 0.0);
+            }
+            risky |= (uint32_t)rk << rr;
         }
-        if constexpr (kEUC) {
-            const double q = sQ2[row] + q2j, e = E2[row * ES + lane];
-            rk |= -e > kRisk2 * q;
-            v2[rr] = fmax(q + e, 0.0);
-        }
-        risky |= (uint32_t)rk << rr;
-    }
-    if constexpr (kWeighted) {
-        risky &= ok;
-        while (risky) {                                    // rare: normally overwritten by the fix-up kernel
-            const int rr = __ffs(risky) - 1; risky &= risky - 1;
-            double t1 = 0.0, t2 = 0.0;
+        if constexpr (kWeighted) {
+            risky &= ok;
+            while (risky) {                                // rare: normally overwritten by the fix-up kernel
+                const int rr = __ffs(risky) - 1; risky &= risky - 1;
+                double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) if (q == rr) { t1 = v1[q]; t2 = v2[q]; }
-            queue_exact(p, iw + rr, j, t1, t2);
+                for (int q = 0; q < OB; q++) if (q == rr) { t1 = v1[q]; t2 = v2[q]; }
+                queue_exact(p, iw + r0 + rr, j, t1, t2);
 #pragma unroll
-            for (int q = 0; q < 8; q++) if (q == rr) { v1[q] = t1; v2[q] = t2; }
+                for (int q = 0; q < OB; q++) if (q == rr) { v1[q] = t1; v2[q] = t2; }
+            }
         }
-    }
 #pragma unroll
-    for (int rr = 0; rr < 8; rr++) {
-        const int row = warp * 8 + rr, i = iw + rr;
-        const int64_t idx = idx0 + (RECT ? (int64_t)rr * p.n_cols : (int64_t)rr * (p.N - iw - 2) - rr * (rr - 1) / 2);
-        const bool st = ok >> rr & 1u;
-        if constexpr (kRF) {
-            const int den = sS[row] + s_j;
-            double v = (double)(den - 2 * common[rr]);
-            if constexpr (NORM) v = den ? v / (double)den : 0.0;
-            if (st) p.out[0][idx] = v;
-        }
-        if constexpr (kWRF) {
-            double v = v1[rr];
-            if constexpr (NORM) { const double den = (st ? p.sum_len[i] : 1.0) + sumj; v = den != 0.0 ? v / den : 0.0; }
-            if (st) p.out[1][idx] = v;
-        }
-        if constexpr (kEUC) {
-            double v = sqrt(v2[rr]);
-            if constexpr (NORM) { const double den = (st ? p.norm[i] : 1.0) + normj; v = den != 0.0 ? v / den : 0.0; }
-            if (st) p.out[2][idx] = v;
+        for (int rr = 0; rr < OB; rr++) {
+            const int r = r0 + rr, row = warp * 8 + r, i = iw + r;
+            const int64_t idx = idx0 + (RECT ? (int64_t)r * p.n_cols : (int64_t)r * (p.N - iw - 2) - r * (r - 1) / 2);
+            const bool st = ok >> rr & 1u;
+            if constexpr (kRF) {
+                const int den = sS[row] + s_j;
+                double v = (double)(den - 2 * common[rr]);
+                if constexpr (NORM) v = den ? v / (double)den : 0.0;
+                if (st) p.out[0][idx] = v;
+            }
+            if constexpr (kWRF) {
+                double v = v1[rr];
+                if constexpr (NORM) { const double den = (st ? p.sum_len[i] : 1.0) + sumj; v = den != 0.0 ? v / den : 0.0; }
+                if (st) p.out[1][idx] = v;
+            }
+            if constexpr (kEUC) {
+                double v = sqrt(v2[rr]);
+                if constexpr (NORM) { const double den = (st ? p.norm[i] : 1.0) + normj; v = den != 0.0 ? v / den : 0.0; }
+                if (st) p.out[2][idx] = v;
+            }
         }
     }
     TRACE(5);
