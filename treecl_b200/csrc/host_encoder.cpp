@@ -501,16 +501,35 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     if (total > 0) {
         std::vector<int64_t> off(N + 1, 0);
         for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
-        std::vector<Ent> ents(total);
-        parallel_for(N, n_threads, [&](int64_t i, int) {
-            for (int s = 0; s < hs.n_splits[i]; s++) ents[off[i] + s] = Ent{mask_hash(&enc[i].masks[(size_t)s * W], W), (uint32_t)i, (uint32_t)s};
-        });
+        // hash every split and scatter the entries into 256 hash buckets: the trees are cut into chunks, every chunk counts its
+        // entries per bucket, a prefix over (bucket, chunk) gives every chunk its own slice of every bucket, and the chunks scatter
+        // in parallel (entries of a bucket stay in tree order)
         constexpr int NB = 256;
+        std::vector<Ent> ents(total);
+        const int64_t n_chunks = std::min<int64_t>(N, (int64_t)n_threads * 4);
+        std::vector<int64_t> cpos((size_t)n_chunks * NB, 0);
+        parallel_for(n_chunks, n_threads, [&](int64_t c, int) {
+            int64_t *cnt = &cpos[(size_t)c * NB];
+            for (int64_t i = N * c / n_chunks; i < N * (c + 1) / n_chunks; i++)
+                for (int s = 0; s < hs.n_splits[i]; s++) {
+                    const Ent en{mask_hash(&enc[i].masks[(size_t)s * W], W), (uint32_t)i, (uint32_t)s};
+                    ents[off[i] + s] = en; cnt[en.h >> 56]++;
+                }
+        });
         std::vector<int64_t> bstart(NB + 1, 0);
-        for (auto &en : ents) bstart[(en.h >> 56) + 1]++;
-        for (int b = 0; b < NB; b++) bstart[b + 1] += bstart[b];
+        {
+            int64_t run = 0;
+            for (int b = 0; b < NB; b++) {
+                bstart[b] = run;
+                for (int64_t c = 0; c < n_chunks; c++) { const int64_t n = cpos[(size_t)c * NB + b]; cpos[(size_t)c * NB + b] = run; run += n; }
+            }
+            bstart[NB] = run;
+        }
         std::vector<Ent> sorted(total);
-        { std::vector<int64_t> pos(bstart.begin(), bstart.end() - 1); for (auto &en : ents) sorted[pos[en.h >> 56]++] = en; }
+        parallel_for(n_chunks, n_threads, [&](int64_t c, int) {
+            int64_t *pos = &cpos[(size_t)c * NB];
+            for (int64_t e = off[N * c / n_chunks]; e < off[N * (c + 1) / n_chunks]; e++) sorted[pos[ents[e].h >> 56]++] = ents[e];
+        });
         ents.clear(); ents.shrink_to_fit();
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
         std::vector<int64_t> uniq(NB + 1, 0), shared(NB + 1, 0), shent(NB + 1, 0);
