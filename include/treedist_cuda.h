@@ -78,6 +78,15 @@ int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, 
  * building a pointer table: the Python binding joins its strings once). */
 int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_trees, int n_threads, td_treeset **out);
 
+/* Kendall-Colijn metric (treeCl/utils/kendallcolijn.py).  Encodes every tree as its vector
+ *     v = (1 - lambda) m + lambda M        KendallColijn._get_vectors / get_vector, kendallcolijn.py:53-79
+ * (m, M: edges / path length from the root to the MRCA of every leaf pair in sorted label order, then 1 / edge length per leaf) and
+ * returns a set whose Euclidean matrix - td_pairwise(ts, TD_MASK(TD_EUC), ...) - is KendallColijn.get_distance (kendallcolijn.py:81-95)
+ * for all pairs.  All trees must have one leaf set (the reference prunes differing pairs to their intersection first: do that with
+ * td_newick_prune and encode the pruned pair); other sets are refused with TD_ERR_UNSUPPORTED.  td_info.n_taxa of the result is the
+ * vector length n(n-1)/2 + n.  Only TD_EUC (and TD_WRF = the L1 distance of the vectors) are meaningful on such a set. */
+int td_encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, td_treeset **out);
+
 void td_treeset_free(td_treeset *ts);
 int td_treeset_info(const td_treeset *ts, td_info *info);
 

@@ -2,7 +2,9 @@
 
 Parity status: PINNED against the reference's golden vectors for geo/euc/wrf/rf on 10-taxon unrooted binary
 trees and for geodesic partial overlap (tests/test_oracle_golden.py); UNPINNED for rooted trees, polytomies,
-zero/missing lengths, and rf/wrf/euc under partial overlap (no reference test covers them).
+zero/missing lengths, and rf/wrf/euc under partial overlap (no reference test covers them); UNPINNED for the
+Kendall-Colijn metric (kc_*): the reference has no test for it and dendropy is not installed here, the restatement
+is checked against hand-derived values of the published definition only (tests/test_kendall_colijn.py).
 """
 import ctypes
 import os
@@ -10,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-__all__ = ['build', 'pair', 'matrix', 'matrix_range', 'prune_newick', 'encode_summary', 'stats', 'stats_reset',
+__all__ = ['build', 'pair', 'matrix', 'matrix_range', 'prune_newick', 'encode_summary', 'stats', 'stats_reset', 'kc_pair', 'kc_vector', 'kc_matrix',
            'METRICS', 'OracleError']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -47,6 +49,9 @@ def _load():
         lib.orc_encode_summary.argtypes = [ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3 + \
                                           [ctypes.POINTER(ctypes.c_double)] * 2
         lib.orc_stats.argtypes = [ctypes.POINTER(ctypes.c_long)] * 3
+        lib.orc_kc_pair.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        lib.orc_kc_vector.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_long, ctypes.POINTER(ctypes.c_long)]
+        lib.orc_kc_matrix.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -113,3 +118,27 @@ def stats():
 
 def stats_reset():
     _load().orc_stats_reset()
+
+
+def kc_pair(nwk_a, nwk_b, lbda=0.5, min_overlap=4):
+    """KendallColijn(t1).get_distance(KendallColijn(t2), lbda, min_overlap) restated (treeCl/utils/kendallcolijn.py:81-95)."""
+    out = ctypes.c_double()
+    _check(_load().orc_kc_pair(_b(nwk_a), _b(nwk_b), float(lbda), int(min_overlap), ctypes.byref(out)))
+    return out.value
+
+
+def kc_vector(nwk, lbda=0.5):
+    """KendallColijn(tree).get_vector(lbda) restated (treeCl/utils/kendallcolijn.py:53-79)."""
+    need = ctypes.c_long()
+    _check(_load().orc_kc_vector(_b(nwk), float(lbda), None, 0, ctypes.byref(need)))
+    out = np.zeros(need.value, dtype=np.float64)
+    _check(_load().orc_kc_vector(_b(nwk), float(lbda), out.ctypes.data, need.value, None))
+    return out
+
+
+def kc_matrix(newicks, lbda=0.5, min_overlap=4):
+    n = len(newicks)
+    arr = (ctypes.c_char_p * n)(*[_b(s) for s in newicks])
+    out = np.zeros(n * (n - 1) // 2, dtype=np.float64)
+    _check(_load().orc_kc_matrix(arr, n, float(lbda), int(min_overlap), out.ctypes.data))
+    return out

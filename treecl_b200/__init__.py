@@ -4,9 +4,10 @@ Drop-in surface (same names and arguments as kgori/treeCl for this path):
     treecl_b200.Collection(...).get_inter_tree_distances('rf'|'wrf'|'euc'|'geo', ...) -> DistanceMatrix
     treecl_b200.treedist.{rf,wrf,euc,geo}dist / *_matrix
     treecl_b200.Tree, treecl_b200.DistanceMatrix, treecl_b200.parutils.*JobHandler
+    treecl_b200.kendallcolijn.KendallColijn / kendall_colijn_matrix (treeCl/utils/kendallcolijn.py)
 Everything is computed by libtreedist_cuda.so (hand-written sm_100a kernels); there is no CPU fallback.
 """
-from . import parutils, tasks, treedist  # noqa: F401
+from . import kendallcolijn, parutils, tasks, treedist  # noqa: F401
 from .collection import Collection, Record  # noqa: F401
 from .distance_matrix import DistanceMatrix  # noqa: F401
 from .errors import OptionError  # noqa: F401

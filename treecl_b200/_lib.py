@@ -60,6 +60,7 @@ def load():
     lib.td_launch_count.restype = ctypes.c_uint64
     lib.td_encode_newick.argtypes = [ctypes.POINTER(ctypes.c_char_p), i64, i32, ctypes.POINTER(vp)]
     lib.td_encode_newick_joined.argtypes = [ctypes.c_char_p, i64, i64, i32, ctypes.POINTER(vp)]
+    lib.td_encode_kendall_colijn.argtypes = [ctypes.POINTER(ctypes.c_char_p), i64, dbl, i32, ctypes.POINTER(vp)]
     lib.td_treeset_free.argtypes = [vp]
     lib.td_treeset_free.restype = None
     lib.td_treeset_info.argtypes = [vp, ctypes.POINTER(td_info)]
@@ -148,6 +149,19 @@ class TreeSet(object):
         self._h = handle
         self._lib = lib
         self.n_trees = len(newicks)
+
+    @classmethod
+    def kendall_colijn(cls, newicks, lbda=0.5, n_threads=0):
+        """Set of Kendall-Colijn vectors v = (1 - lbda) m + lbda M (treeCl/utils/kendallcolijn.py:53-79): its 'euc' matrix is the
+        Kendall-Colijn distance matrix.  All trees must have one leaf set."""
+        lib = load()
+        raw = [_b(s) for s in newicks]
+        arr = (ctypes.c_char_p * len(raw))(*raw)
+        handle = ctypes.c_void_p()
+        check(lib.td_encode_kendall_colijn(arr, len(raw), float(lbda), int(n_threads), ctypes.byref(handle)))
+        self = cls.__new__(cls)
+        self._h, self._lib, self.n_trees = handle, lib, len(raw)
+        return self
 
     def close(self):
         if getattr(self, '_h', None):

@@ -452,6 +452,21 @@ int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, 
     return TD_OK;
 }
 
+int td_encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, td_treeset **out)
+{
+    if (!out) { set_error("null output pointer"); return TD_ERR_ARG; }
+    *out = nullptr;
+    if (!(lambda >= 0.0 && lambda <= 1.0)) { set_error("lambda must lie in [0, 1]"); return TD_ERR_ARG; }
+    td_treeset *ts = new (std::nothrow) td_treeset();
+    if (!ts) { set_error("out of memory"); return TD_ERR_NOMEM; }
+    int rc;
+    try { rc = encode_kendall_colijn(newick, n_trees, lambda, n_threads, ts->host); }
+    catch (const std::bad_alloc &) { set_error("out of memory while encoding"); rc = TD_ERR_NOMEM; }
+    if (rc) { delete ts; return rc; }
+    *out = ts;
+    return TD_OK;
+}
+
 int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_trees, int n_threads, td_treeset **out)
 {
     if (!buffer || total_bytes <= 0 || n_trees < 1) { set_error("empty buffer"); return TD_ERR_ARG; }

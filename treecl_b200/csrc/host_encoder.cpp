@@ -414,6 +414,9 @@ static void parallel_for(int64_t n, int n_threads, F &&fn)
     for (auto &x : th) x.join();
 }
 
+static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::string> &labels, int n_threads, HostSet &hs,
+                         const std::function<void(const char *)> &lap);
+
 int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &hs)
 {
     if (N < 1 || !newick) { set_error("td_encode_newick: need at least one tree"); return TD_ERR_ARG; }
@@ -467,11 +470,18 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     }
     if (status != TD_OK) { set_error("%s", err_msg.c_str()); return status; }
     lap("parse+encode");
+    return finish_encode(enc, tab.labels, n_threads, hs, lap);
+}
 
+// Everything after the per-tree encoding: SoA packing, the split dictionary with its postings, the per-tree lists and aggregates.
+static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::string> &labels, int n_threads, HostSet &hs,
+                         const std::function<void(const char *)> &lap)
+{
+    const int64_t N = (int64_t)enc.size();
     // ---- pack ------------------------------------------------------------------------------------------
-    const int n_taxa = (int)tab.labels.size(), W = std::max(1, (n_taxa + 63) / 64);
+    const int n_taxa = (int)labels.size(), W = std::max(1, (n_taxa + 63) / 64);
     hs = HostSet();
-    hs.N = N; hs.n_taxa = n_taxa; hs.W = W; hs.labels = tab.labels;
+    hs.N = N; hs.n_taxa = n_taxa; hs.W = W; hs.labels = labels;
     hs.n_splits.resize(N); hs.n_leaves.resize(N); hs.tree_rooted.resize(N); hs.n_shared.assign(N, 0);
     hs.leafmask.resize((size_t)N * W); hs.sum_len.resize(N); hs.norm.resize(N);
     hs.single_l1.assign(N, 0.0); hs.single_l2.assign(N, 0.0);
@@ -624,6 +634,90 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     });
     lap("lists");
     return TD_OK;
+}
+
+// ---- Kendall-Colijn vectors (treeCl/utils/kendallcolijn.py:38-79) ------------------------------------------------------
+// v = (1 - lambda) m + lambda M: for every pair of leaves (sorted label order, itertools.combinations order) the number of edges and
+// the path length from the root to their MRCA, then per leaf the constant 1 and its edge length.  The set is packed as "trees" without
+// internal edges whose leaf-edge lengths are the vector entries, so that the Euclidean kernel (td_pairwise with TD_EUC) returns exactly
+// KendallColijn.get_distance for trees on one leaf set.
+int encode_kendall_colijn(const char *const *newick, int64_t N, double lambda, int n_threads, HostSet &hs)
+{
+    if (N < 1 || !newick) { set_error("td_encode_kendall_colijn: need at least one tree"); return TD_ERR_ARG; }
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, N / 8));
+    TaxonTable tab;
+    {
+        std::vector<std::string> l0; int r0;
+        int rc = newick_labels(newick[0], l0, r0);
+        if (rc) { std::string m = std::string("tree 0: ") + last_error(); set_error("%s", m.c_str()); return rc; }
+        tab.build(std::move(l0));
+    }
+    const int n = (int)tab.labels.size();
+    const int64_t D = (int64_t)n * (n - 1) / 2 + n;
+    if (D >= (1 << 24)) { set_error("Kendall-Colijn vectors of %lld entries are not supported", (long long)D); return TD_ERR_UNSUPPORTED; }
+    const int W = (int)((D + 63) / 64);
+    std::vector<TreeEnc> enc(N);
+    std::atomic<int> status{TD_OK};
+    std::mutex err_mu; std::string err_msg;
+    auto fail = [&](int rc, int64_t i, const std::string &what) {
+        int exp = TD_OK;
+        if (status.compare_exchange_strong(exp, rc)) { std::lock_guard<std::mutex> g(err_mu); err_msg = "tree " + std::to_string(i) + ": " + what; }
+    };
+    struct Scratch { FlatTree t; std::vector<int> edges, taxon, first, next, tail; std::vector<double> dist; std::vector<char> seen; };
+    std::vector<Scratch> scratch(n_threads);
+    parallel_for(N, n_threads, [&](int64_t i, int tid) {
+        if (status.load(std::memory_order_relaxed) != TD_OK) return;
+        Scratch &sc = scratch[tid];
+        if (int rc = parse_newick(newick[i], sc.t)) { fail(rc, i, last_error()); return; }
+        const FlatTree &t = sc.t;
+        const int nn = t.size();
+        // depths (parents precede their children), leaves -> taxon index
+        sc.edges.assign(nn, 0); sc.dist.assign(nn, 0.0); sc.taxon.assign(nn, -1);
+        int n_leaves = 0;
+        sc.seen.assign(n, 0);
+        for (int v = 1; v < nn; v++) { sc.edges[v] = sc.edges[t.parent[v]] + 1; sc.dist[v] = sc.dist[t.parent[v]] + t.len[v]; }
+        TreeEnc &e = enc[i];
+        e.rooted = 0; e.n_leaves = (int)D; e.masks.clear(); e.lens.clear();
+        e.leafmask.assign(W, 0);
+        for (int64_t k = 0; k < D; k++) e.leafmask[k >> 6] |= 1ull << (k & 63);
+        e.leaflen.assign((size_t)D, 0.0);
+        for (int v = 0; v < nn; v++)
+            if (t.nchild[v] == 0) {
+                auto it = tab.index.find(t.label[v]);
+                if (it == tab.index.end() || sc.seen[it->second]) { fail(TD_ERR_UNSUPPORTED, i, "Kendall-Colijn sets need one common leaf set (prune first)"); return; }
+                sc.taxon[v] = it->second; sc.seen[it->second] = 1; n_leaves++;
+                e.leaflen[(size_t)(D - n + it->second)] = (1.0 - lambda) + lambda * t.len[v];
+            }
+        if (n_leaves != n) { fail(TD_ERR_UNSUPPORTED, i, "Kendall-Colijn sets need one common leaf set (prune first)"); return; }
+        // leaf lists per node as linked lists; node v (children have larger indices) hands its list to its parent after pairing it
+        // with the leaves the parent has collected so far: every cross pair has the parent as MRCA
+        sc.first.assign(nn, -1); sc.tail.assign(nn, -1); sc.next.assign(nn, -1);
+        for (int v = nn - 1; v >= 1; v--) {
+            if (t.nchild[v] == 0) { sc.first[v] = sc.tail[v] = v; }
+            const int p = t.parent[v];
+            const double val = (1.0 - lambda) * (double)sc.edges[p] + lambda * sc.dist[p];
+            for (int x = sc.first[p]; x >= 0; x = sc.next[x])
+                for (int y = sc.first[v]; y >= 0; y = sc.next[y]) {
+                    int a = sc.taxon[x], b = sc.taxon[y];
+                    if (a > b) std::swap(a, b);
+                    e.leaflen[(size_t)((int64_t)a * n - (int64_t)a * (a + 1) / 2 + (b - a - 1))] = val;
+                }
+            if (sc.first[v] >= 0) {
+                if (sc.first[p] < 0) sc.first[p] = sc.first[v]; else sc.next[sc.tail[p]] = sc.first[v];
+                sc.tail[p] = sc.tail[v];
+            }
+        }
+        double sl = 0.0, sq = 0.0;
+        for (double x : e.leaflen) { sl += x; sq += x * x; }
+        e.sum_len = sl; e.sum_sq = sq;
+    });
+    if (status != TD_OK) { set_error("%s", err_msg.c_str()); return status; }
+    // pseudo-labels of the vector entries: "a|b" for the pairs, "a" for the leaves
+    std::vector<std::string> names; names.reserve((size_t)D);
+    for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) names.push_back(tab.labels[a] + "|" + tab.labels[b]);
+    for (int a = 0; a < n; a++) names.push_back(tab.labels[a]);
+    return finish_encode(enc, names, n_threads, hs, [](const char *) {});
 }
 
 }  // namespace td

@@ -64,6 +64,7 @@ const char *last_error();
 
 // host_encoder.cpp
 int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, HostSet &hs);
+int encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, HostSet &hs);
 int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted);
 int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
 
