@@ -67,10 +67,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
@@ -132,15 +128,17 @@ constexpr int RG = 16;                // trees per row group: one CTA of pair_ev
 // One CTA per ROW GROUP of RG consecutive trees: all events (i, j) with i in the group, binned by column tile j / 32.
 //   entries : the group's shared-list entries, each with its position x in the postings; entry (d, i) owns the events
 //             (i, post_tree[b]) for b in (x, post_end[x])
-//   count   : the events are numbered 0 .. T-1 over all entries (block scan of the entry sizes); thread k takes events k, k + 256, ...
-//             (entry by binary search in the scanned sizes), so all global reads are independent and coalesce along a posting list;
-//             a shared-memory histogram over the column tiles counts them
+//   count   : a warp walks EVW entries at a time, lane b takes the b-th later holder of each: no searching, coalesced reads of a
+//             posting list, EVW independent reads in flight per lane; a shared-memory histogram over the column tiles counts them
 //   place   : block scan of the histogram, ONE global atomicAdd claims the group's contiguous range of the event buffer
 //   fill    : the same walk again, slots from shared-memory atomics, one aligned record store per event
 // and the (offset, count) of every (row group, column tile) segment goes to the segment table for pair_dense_kernel.
 // Nothing but the range claim touches a global atomic, and there is no separate count / scan / fill launch.
 constexpr int EVT = 1024;             // threads of pair_events_kernel
-constexpr int EVU = 4;                // events per thread and step of the walks (independent global reads in flight)
+#ifndef PS_EVW
+#define PS_EVW 2
+#endif
+constexpr int EVW = PS_EVW;           // entries a warp walks at a time
 
 template <int WMODE, bool RECT>
 __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant__ PairParams p)
@@ -148,8 +146,8 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char ev_smem[];
     const int n_ent = RG * p.sh_stride, ct = p.col_tiles_total;
     double *ent_len = reinterpret_cast<double *>(ev_smem);                                 // [n_ent]     (weighted only, else unused)
-    uint32_t *ent_off = reinterpret_cast<uint32_t *>(ev_smem + (WMODE ? (size_t)n_ent * 8 : 0));   // [n_ent + 1]
-    int *ent_x = reinterpret_cast<int *>(ent_off + n_ent + 1);                             // [n_ent]
+    uint32_t *ent_n = reinterpret_cast<uint32_t *>(ev_smem + (WMODE ? (size_t)n_ent * 8 : 0));     // [n_ent + 1] events of the entry
+    int *ent_x = reinterpret_cast<int *>(ent_n + n_ent + 1);                               // [n_ent] position in the postings
     uint32_t *hist = reinterpret_cast<uint32_t *>(ent_x + n_ent);                          // [ct]
     __shared__ uint32_t warp_sum[EVT / 32];
     __shared__ uint32_t s_base;
@@ -176,38 +174,34 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     // ---- entries (e = position * RG + local tree) and their sizes ------------------------------------------------------------------------
     for (int c = tid; c < ct; c += EVT) hist[c] = 0u;
     const int per = (n_ent + EVT - 1) / EVT, e_lo = min(tid * per, n_ent), e_hi = min(e_lo + per, n_ent);
-    uint32_t mine = 0;
     for (int e = e_lo; e < e_hi; e++) {
         const int i = tree0 + (e & (RG - 1)), pos = e / RG;
         int x = -1;
         if (i >= p.row_begin && i < p.row_end) x = p.shared_x[(size_t)i * p.sh_stride + pos];
         uint32_t n = 0;
         if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[e] = p.post_len[x]; }
-        ent_x[e] = x; ent_off[e] = n; mine += n;
+        ent_x[e] = x; ent_n[e] = n;
     }
-    uint32_t T;
-    uint32_t run = block_scan(mine, T);
-    for (int e = e_lo; e < e_hi; e++) { const uint32_t n = ent_off[e]; ent_off[e] = run; run += n; }
-    if (tid == EVT - 1) ent_off[n_ent] = T;
     __syncthreads();
 
-    auto entry_of = [&](uint32_t k) {                      // last entry e with ent_off[e] <= k (entries of size 0 are skipped over)
-        int lo = 0, hi = n_ent;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ent_off[mid] <= k) lo = mid; else hi = mid; }
-        return lo;
-    };
-    // ---- count: EVU independent reads of the postings per thread and step ---------------------------------------------------------------------
-    for (uint32_t k0 = tid; k0 < T; k0 += EVT * EVU) {
-        int j[EVU];
+    // ---- count: a warp walks EVW entries at a time, lane b takes the b-th later holder of each (no search; EVW independent reads) ----------
+    for (int e0 = warp * EVW; e0 < n_ent; e0 += (EVT / 32) * EVW) {
+        int x[EVW]; uint32_t n[EVW], n_max = 0;
 #pragma unroll
-        for (int u = 0; u < EVU; u++) {
-            const uint32_t k = k0 + u * EVT;
-            j[u] = -1;
-            if (k < T) { const int e = entry_of(k); j[u] = p.post_tree[ent_x[e] + 1 + (int)(k - ent_off[e])]; }
+        for (int u = 0; u < EVW; u++) {
+            const int e = e0 + u;
+            x[u] = -1; n[u] = 0;
+            if (e < n_ent) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
+            n_max = max(n_max, n[u]);
         }
+        for (uint32_t b = lane; b < n_max; b += 32) {
+            int j[EVW];
 #pragma unroll
-        for (int u = 0; u < EVU; u++)
-            if (j[u] >= (RECT ? (int)p.col_offset : 0)) atomicAdd(&hist[j[u] >> 5], 1u);
+            for (int u = 0; u < EVW; u++) j[u] = b < n[u] ? p.post_tree[x[u] + 1 + (int)b] : -1;
+#pragma unroll
+            for (int u = 0; u < EVW; u++)
+                if (j[u] >= (RECT ? (int)p.col_offset : 0)) atomicAdd(&hist[j[u] >> 5], 1u);
+        }
     }
     __syncthreads();
     // ---- place: scan the histogram, claim the range, publish the segment table --------------------------------------------------------------
@@ -225,38 +219,44 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     }
     __syncthreads();
     // ---- fill ----------------------------------------------------------------------------------------------------------------------------
-    for (uint32_t k0 = tid; k0 < T; k0 += EVT * EVU) {
-        int j[EVU], ee[EVU]; double lb[EVU];
-#pragma unroll
-        for (int u = 0; u < EVU; u++) {
-            const uint32_t k = k0 + u * EVT;
-            j[u] = -1; ee[u] = 0; lb[u] = 0.0;
-            if (k < T) {
-                const int e = entry_of(k), b = ent_x[e] + 1 + (int)(k - ent_off[e]);
-                ee[u] = e; j[u] = p.post_tree[b];
-                if constexpr (WMODE) lb[u] = p.post_len[b];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < EVU; u++) {
-            uint32_t o = 0xFFFFFFFFu;
-            if (j[u] >= (RECT ? (int)p.col_offset : 0)) o = atomicAdd(&hist[j[u] >> 5], 1u);   // else: no event / the other set's own side
-            if (o < p.ev_capacity) {
-                const uint32_t cell = (uint32_t)((((tree0 + (ee[u] & (RG - 1))) & 63) << 5) | (j[u] & 31));
-                if constexpr (WMODE == 0) reinterpret_cast<uint32_t *>(p.ev)[o] = cell;
-                else {
-                    const double la = ent_len[ee[u]];
-                    const double t2 = -2.0 * la * lb[u], t1 = fabs(la - lb[u]) - fabs(la) - fabs(lb[u]);
-                    int4 *dst = reinterpret_cast<int4 *>(p.ev) + (size_t)o * (rec_bytes(WMODE) / 16);
-                    if constexpr (WMODE == 3) {
-                        dst[0] = make_int4(__double2loint(t2), __double2hiint(t2), __double2loint(t1), __double2hiint(t1));
-                        dst[1] = make_int4((int)cell, 0, 0, 0);
-                    } else {
-                        const double tv = WMODE == 2 ? t2 : t1;
-                        dst[0] = make_int4(__double2loint(tv), __double2hiint(tv), (int)cell, 0);
-                    }
+    auto emit = [&](int e, int j, double lb) {              // one event of entry e with the later holder j (length lb)
+        uint32_t o = 0xFFFFFFFFu;
+        if (j >= (RECT ? (int)p.col_offset : 0)) o = atomicAdd(&hist[j >> 5], 1u);   // else: no event / the other set's own side
+        if (o < p.ev_capacity) {
+            const uint32_t cell = (uint32_t)((((tree0 + (e & (RG - 1))) & 63) << 5) | (j & 31));
+            if constexpr (WMODE == 0) reinterpret_cast<uint32_t *>(p.ev)[o] = cell;
+            else {
+                const double la = ent_len[e];
+                const double t2 = -2.0 * la * lb, t1 = fabs(la - lb) - fabs(la) - fabs(lb);
+                int4 *dst = reinterpret_cast<int4 *>(p.ev) + (size_t)o * (rec_bytes(WMODE) / 16);
+                if constexpr (WMODE == 3) {
+                    dst[0] = make_int4(__double2loint(t2), __double2hiint(t2), __double2loint(t1), __double2hiint(t1));
+                    dst[1] = make_int4((int)cell, 0, 0, 0);
+                } else {
+                    const double tv = WMODE == 2 ? t2 : t1;
+                    dst[0] = make_int4(__double2loint(tv), __double2hiint(tv), (int)cell, 0);
                 }
             }
+        }
+    };
+    for (int e0 = warp * EVW; e0 < n_ent; e0 += (EVT / 32) * EVW) {
+        int x[EVW]; uint32_t n[EVW], n_max = 0;
+#pragma unroll
+        for (int u = 0; u < EVW; u++) {
+            const int e = e0 + u;
+            x[u] = -1; n[u] = 0;
+            if (e < n_ent) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
+            n_max = max(n_max, n[u]);
+        }
+        for (uint32_t b = lane; b < n_max; b += 32) {
+            int j[EVW]; double lb[EVW];
+#pragma unroll
+            for (int u = 0; u < EVW; u++) {
+                j[u] = -1; lb[u] = 0.0;
+                if (b < n[u]) { j[u] = p.post_tree[x[u] + 1 + (int)b]; if constexpr (WMODE) lb[u] = p.post_len[x[u] + 1 + (int)b]; }
+            }
+#pragma unroll
+            for (int u = 0; u < EVW; u++) emit(e0 + u, j[u], lb[u]);
         }
     }
 }
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     const int tile_r = u + p.tile_row0, tile_c = RECT ? x + p.col_tile0 : 2 * tile_r + x;
     const long long t = RECT ? (long long)u * p.tiles_x + x : (long long)u * L0 - (long long)u * (u - 1) + x;
     const int i0 = tile_r * TR, j0 = tile_c * TC;
+    (void)t;                                               // only the -DPS_TRACE build uses the linear tile index
 
     // Shared memory.  The ring of leaf chunks and the per-cell slots share one region: the slots are only needed once the leaf sums are
     // in registers (the ring holds NSTAGE * KCH = 64 taxa, so up to 64 taxa there is no refill and no barrier inside the k-loop).
