@@ -33,6 +33,7 @@ SEED = 0xCA55E77E + 1          # treeCl RANDOM_SEED + config index (SURVEY.md 8(
 
 
 # BASELINE.json configs (index -> trees, taxa, metrics); configs[1] is the bench line, the others are for experiments
+WORKLOAD_FMT = '{} uniform random {}-taxon trees, {} condensed matrices'      # both arms name the workload identically
 CONFIGS = {0: (200, 20, ('rf', 'wrf', 'euc')), 1: (5000, 50, ('rf', 'euc')), 2: (20000, 100, ('wrf', 'euc')),
            4: (2000, 30, ('geo',))}
 
@@ -128,7 +129,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'tree-pairs/sec (rf+euc matrices)', 'value': value, 'unit': 'pairs/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '{} uniform random {}-taxon trees, rf+euc condensed matrices'.format(nt, nx),
+        'config': {'workload': WORKLOAD_FMT.format(nt, nx, '+'.join(METRICS)),
                    'sample_pairs_per_step': sample},
         'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': desc,
                          'best_cpu_value': best,
@@ -260,7 +261,7 @@ def run_ours(args):
             'metric': 'tree-pairs/sec ({} matrices)'.format('+'.join(METRICS)), 'value': value, 'unit': 'pairs/s', 'n_gpus': n_gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '{} uniform random {}-taxon trees, {} condensed matrices, one call (3 kernels) per step'.format(nt, nx, '+'.join(METRICS)),
+            'config': {'workload': WORKLOAD_FMT.format(nt, nx, '+'.join(METRICS)), 'launches': 'one call = 3 kernels (events, tiles, exact fix-up) per step',
                        'pairs': pairs_total, 'pairs_per_gpu': my_pairs, 'parallelism': 'rows sharded x{}'.format(n_gpus),
                        'l2': '256 MiB memset + 256 MiB read between timed steps (outside the event pairs): L2 cold and clean; outputs (200 MB/step) exceed L2',
                        'dict_size': int(info.dict_size), 'dict_shared': int(info.dict_shared), 'max_shared': int(info.max_shared)},
