@@ -395,3 +395,36 @@ def test_baseline_config_3_properties(td, oracle_mod):
     assert (got['wrf'] >= got['euc']).all()
     parts = [ts.pairwise(('wrf',), row_begin=a, row_end=b)['wrf'] for a, b in engine.balanced_row_ranges(n, 8)]
     assert np.array_equal(np.concatenate(parts), got['wrf'])
+
+
+def test_concurrent_launches_on_one_set_share_the_event_buffer_safely(td, monkeypatch):
+    """The postings pipeline keeps one event buffer per resident set: launches from different streams / host threads on the same set
+    are ordered behind each other (cudaStreamWaitEvent), so they must give the same bytes as a lone launch."""
+    import threading
+    import torch
+    from treecl_b200 import _lib, synth
+    monkeypatch.setenv('TREEDIST_PAIR_KERNEL', 'split')
+    trees = synth.uniform_trees(700, 24, seed=77)
+    ts = _lib.TreeSet(trees)
+    ts.upload(0)
+    pairs = 700 * 699 // 2
+    ref = {m: torch.empty(pairs, dtype=torch.float64, device='cuda') for m in ('rf', 'wrf', 'euc')}
+    ts.pairwise_device(('rf', 'wrf', 'euc'), {m: ref[m].data_ptr() for m in ref})
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    outs = [{m: torch.full((pairs,), -1.0, dtype=torch.float64, device='cuda') for m in ('rf', 'wrf', 'euc')} for _ in streams]
+    torch.cuda.synchronize()
+
+    def work(k):
+        for _ in range(5):
+            ts.pairwise_device(('rf', 'wrf', 'euc'), {m: outs[k][m].data_ptr() for m in outs[k]}, stream=streams[k].cuda_stream)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(streams))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    for k in range(len(streams)):
+        for m in ('rf', 'wrf', 'euc'):
+            assert torch.equal(outs[k][m], ref[m]), (k, m)
