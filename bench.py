@@ -170,7 +170,7 @@ def run_ours(args):
     outs = {m: torch.empty(max(my_pairs, 1), dtype=torch.float64, device=dev) for m in METRICS}
     ptrs = {m: outs[m].data_ptr() for m in METRICS}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    flush_rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)      # 256 MiB, read after the memset
+    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)    # 256 MiB, read (reduced) after the memset
 
     def step():
         ts.pairwise_device(METRICS, ptrs, row_begin=r0, row_end=r1, stream=stream.cuda_stream)
