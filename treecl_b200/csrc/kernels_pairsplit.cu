@@ -97,12 +97,13 @@ __host__ __device__ constexpr size_t kRegionBytes(uint32_t mask)
 struct FixScale { double to_fix, from_fix; };
 __device__ __forceinline__ FixScale fix_scale(double q)
 {
-    const int e = (__double2hiint(q) >> 20) & 0x7FF;                  // biased exponent of q (q >= 0)
+    // biased exponent of to_fix = 2^(61 - (e - 1023)) is 2107 - e; capped at 2045 so that from_fix = 1 / to_fix (biased exponent
+    // 2046 - that) is a normal number too.  The cap only applies to Q < 2^-961 (zero included), where corrections times 2^1022 still fit.
+    const int e = (__double2hiint(q) >> 20) & 0x7FF;                  // biased exponent of q (q >= 0, finite)
+    const int be = min(2107 - e, 2045);
     FixScale f;
-    if (e > 61 && e < 2047 - 1) {                                      // normal range with room for both factors
-        f.to_fix = __hiloint2double((1023 + 61 + 1023 - e) << 20, 0);   // 2^(61 - (e - 1023))
-        f.from_fix = __hiloint2double((e - 61) << 20, 0);               // 2^((e - 1023) - 61)
-    } else { f.to_fix = 1.0; f.from_fix = 1.0; }                       // zero / denormal-scale sets: plain integers
+    f.to_fix = __hiloint2double(be << 20, 0);
+    f.from_fix = __hiloint2double((2046 - be) << 20, 0);
     return f;
 }
 
@@ -555,7 +556,8 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             if constexpr (kEUC) {
                 const double q = sQ2[row] + q2j, e = E2[row * ES + lane];
                 rk |= -e > kRisk2 * q;
-                v2[rr] = fmax(q + e, 0.0);
+                const double sum = q + e;
+                v2[rr] = sum < 0.0 ? 0.0 : sum;             // (cheaper than fmax: no NaN handling needed here)
             }
             risky |= (uint32_t)rk << rr;
         }
