@@ -428,3 +428,13 @@ def test_concurrent_launches_on_one_set_share_the_event_buffer_safely(td, monkey
     for k in range(len(streams)):
         for m in ('rf', 'wrf', 'euc'):
             assert torch.equal(outs[k][m], ref[m]), (k, m)
+
+
+def test_randomised_cross_check_of_the_pair_kernels(td):
+    """A few seconds of tools/fuzz_parity.py: random sizes / taxa / sharing / normalisation / row ranges / rectangular splits,
+    postings pipeline against the merge kernel (rf bit for bit, wrf / euc to 1e-9) and against the oracle for the small sets."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_parity.py'), '8', '7'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert 'fuzz ok' in out.stdout
