@@ -8,7 +8,7 @@ import pandas as pd
 import pytest
 from scipy.spatial.distance import squareform
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
