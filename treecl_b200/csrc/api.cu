@@ -70,7 +70,7 @@ static std::mutex g_props_mu;
 
 constexpr int kCounters = 64;
 constexpr int kWorklists = 8;
-constexpr unsigned kWorklistCap = 1u << 18;
+constexpr unsigned kWorklistCap = 1u << 20;       // pairs per exact fix-up list (beyond it the tile kernel recomputes in place, slowly)
 
 struct DeviceSet {
     int device = -1, sm_count = 148;

@@ -47,8 +47,11 @@ constexpr int NSTAGE = PS_NSTAGE;     // chunks in flight
 constexpr int OB = PS_OB;             // rows of the epilogue handled together
 constexpr int SA = 68, SB = 36;       // row strides (doubles) of the staged leaf chunks: = 4 mod 16 -> conflict-free DMMA fragments
 constexpr int ES = 40;                // row stride (doubles) of the per-cell slots: conflict-free 16-byte accesses of the C fragments
-constexpr double kRisk1 = 0.9;        // wrf: exact recompute when -E1 > kRisk1 * (Q1_i + Q1_j)
-constexpr double kRisk2 = 0.98;       // euc: exact recompute when the result is < 2 % of Q2_i + Q2_j (error amplification <= 50)
+// (Q + E) subtracts.  A result below 0.2 % of Q = Q_i + Q_j (error amplification 500: relative error <= 500 * (n_taxa + splits) * 2^-53,
+// i.e. <= 7e-11 even for the 1,275-entry Kendall-Colijn vectors) is recomputed exactly by the fix-up kernel.  For euc that is a pair
+// closer than 4.5 % of the root of the summed squared norms: near-duplicates, not the bulk of a real data set.
+constexpr double kRisk1 = 0.998;      // wrf: exact recompute when -E1 > kRisk1 * (Q1_i + Q1_j)
+constexpr double kRisk2 = 0.998;      // euc: exact recompute when -E2 > kRisk2 * (Q2_i + Q2_j)
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
