@@ -541,6 +541,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             for (int64_t e = off[N * c / n_chunks]; e < off[N * (c + 1) / n_chunks]; e++) sorted[pos[ents[e].h >> 56]++] = ents[e];
         });
         ents.clear(); ents.shrink_to_fit();
+        lap("  dict: hash+scatter");
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
         std::vector<int64_t> uniq(NB + 1, 0), shared(NB + 1, 0), shent(NB + 1, 0);
         std::vector<double> copairs(NB, 0.0);
@@ -562,6 +563,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             }
             uniq[b + 1] = u; shared[b + 1] = sh; shent[b + 1] = she; copairs[b] = cp;
         });
+        lap("  dict: sort+count");
         double cp_total = 0;
         for (int b = 0; b < NB; b++) { uniq[b + 1] += uniq[b]; shared[b + 1] += shared[b]; shent[b + 1] += shent[b]; cp_total += copairs[b]; }
         hs.dict_shared = shared[NB];
