@@ -127,7 +127,8 @@ int64_t td_condensed_offset(int64_t n_trees, int64_t row);
  * in scipy-condensed order (itertools.combinations order, treeCl/tasks.py:651-653).  d_out[m] are DEVICE pointers
  * (double; entries for metrics not requested are ignored).  Asynchronous on `stream`.  Multi-GPU: every rank
  * uploads the same set and calls this with its own row range; no collective is involved.
- * Pairs whose leaf sets differ follow treeCl/treedist.py:63-68: fewer than min_overlap common leaves ->
+ * Kernel choice is internal (postings pipeline / merge kernel / int8 incidence contraction for RF alone on densely sharing sets /
+ * restrict-then-join for differing leaf sets); all give the same values.  Pairs whose leaf sets differ follow treeCl/treedist.py:63-68: fewer than min_overlap common leaves ->
  * overlap_fail_value, else both trees are restricted to the intersection first. */
 int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap,
                        double overlap_fail_value, int64_t row_begin, int64_t row_end, void *const d_out[4],

@@ -1,0 +1,22 @@
+import os, sys
+sys.path.insert(0, '/root/repo')
+import torch
+from treecl_b200 import _lib, synth
+n, taxa = 5000, 50
+trees = synth.structured_trees(n, taxa, n_classes=64, class_nni=10, lam=3.0, seed=7)
+ts = _lib.TreeSet(trees); ts.upload(0)
+pairs = n * (n - 1) // 2
+out = torch.empty(pairs, dtype=torch.float64, device='cuda')
+res = {}
+for k in ('merge', 'auto'):
+    if k == 'auto': os.environ.pop('TREEDIST_PAIR_KERNEL', None)
+    else: os.environ['TREEDIST_PAIR_KERNEL'] = k
+    for _ in range(3): ts.pairwise_device(('rf',), {'rf': out.data_ptr()})
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ts.pairwise_device(('rf',), {'rf': out.data_ptr()})
+    e1.record(); torch.cuda.synchronize()
+    res[k] = out.clone()
+    print(k, '%.3f ms' % (e0.elapsed_time(e1) / 10), 'dict_shared', ts.info.dict_shared)
+print('identical:', torch.equal(res['merge'], res['auto']))

@@ -332,6 +332,43 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     return TD_OK;
 }
 
+// Exact RF through the int8 tcgen05 split-incidence contraction (kernels_incidence.cu); builds the incidence matrix on first use.
+static bool rf_incidence_fits(const HostSet &h)
+{
+    const int bk = incidence_bk(), tile = incidence_tile();
+    const int64_t d_pad = std::max<int64_t>((h.dict_shared + bk - 1) / bk * bk, bk), rows = (h.N + tile - 1) / tile * tile;
+    return h.uniform && h.max_splits <= 32767 && (double)d_pad * (double)rows <= 64e9;
+}
+
+static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16,
+                            cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    int rc;
+    CUDA_TRY(cudaSetDevice(d->device));
+    {
+        std::lock_guard<std::mutex> guard(d->x_mu);
+        if (!d->X) {
+            const int bk = incidence_bk(), tile = incidence_tile();
+            const int64_t d_pad = std::max<int64_t>((h.dict_shared + bk - 1) / bk * bk, bk);
+            const int64_t rows = (h.N + tile - 1) / tile * tile;
+            if ((double)d_pad * (double)rows > 64e9) { set_error("incidence matrix of %lld x %lld bytes is too large: the set shares too few splits for this path (use td_pairwise_device)", (long long)rows, (long long)d_pad); return TD_ERR_UNSUPPORTED; }
+            int8_t *X = nullptr;
+            if ((rc = dev_alloc(d, &X, (size_t)rows * d_pad))) return rc;
+            CUDA_TRY(cudaMemsetAsync(X, 0, (size_t)rows * d_pad, st));
+            CUDA_TRY(launch_build_incidence(d->shared, d->sh_stride, h.N, d_pad, X, st));
+            launch_counter_add(1);
+            cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap);
+            if (e != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+            d->X = X; d->d_pad = d_pad; d->rows_x = rows;
+        }
+    }
+    CUDA_TRY(launch_rf_incidence(d->tmap, d->nsplits, h.N, d->d_pad, row_begin, row_end, condensed_offset(h.N, row_begin), normalise,
+                                 out_is_u16, d_out, st));
+    launch_counter_add(1);
+    return TD_OK;
+}
+
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
@@ -376,6 +413,14 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
                                 && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         const bool use_split = use_join && split_fits && !(force && (!strcmp(force, "join") || !strcmp(force, "join_tile")));
+        // RF alone on a densely sharing set: the int8 tcgen05 incidence contraction instead of the merge kernel (same integers)
+        const bool want_inc = force ? !strcmp(force, "incidence") : true;
+        if (m3 == 1u && !rect && !use_join && want_inc && rf_incidence_fits(h) && h.dict_shared > 0) {
+            if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
+            int rc = run_rf_incidence(ts, d, normalise, row_begin, row_end, d_out[TD_RF], 0, st);
+            if (rc) return rc;
+            goto geodesic;
+        }
         const int tile = use_join ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
@@ -410,6 +455,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
             }
         }
     }
+geodesic:
     if (mask & TD_MASK(TD_GEO)) {
         if (!d_out[TD_GEO]) { set_error("output pointer for the geodesic metric is null"); return TD_ERR_ARG; }
         if (h.max_splits > 128 || h.W > 3) { set_error("geodesic kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
@@ -636,29 +682,7 @@ int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int
     if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { set_error("output pointer is not device memory"); return TD_ERR_ARG; }
     DeviceSet *d; int rc;
     if ((rc = check_ready(ts, attr.device, &d))) return rc;
-    CUDA_TRY(cudaSetDevice(d->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    {
-        std::lock_guard<std::mutex> guard(d->x_mu);
-        if (!d->X) {
-            const int bk = incidence_bk(), tile = incidence_tile();
-            const int64_t d_pad = std::max<int64_t>((h.dict_shared + bk - 1) / bk * bk, bk);
-            const int64_t rows = (h.N + tile - 1) / tile * tile;
-            if ((double)d_pad * (double)rows > 64e9) { set_error("incidence matrix of %lld x %lld bytes is too large: the set shares too few splits for this path (use td_pairwise_device)", (long long)rows, (long long)d_pad); return TD_ERR_UNSUPPORTED; }
-            int8_t *X = nullptr;
-            if ((rc = dev_alloc(d, &X, (size_t)rows * d_pad))) return rc;
-            CUDA_TRY(cudaMemsetAsync(X, 0, (size_t)rows * d_pad, st));
-            CUDA_TRY(launch_build_incidence(d->shared, d->sh_stride, h.N, d_pad, X, st));
-            launch_counter_add(1);
-            cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap);
-            if (e != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(e)); return TD_ERR_CUDA; }
-            d->X = X; d->d_pad = d_pad; d->rows_x = rows;
-        }
-    }
-    CUDA_TRY(launch_rf_incidence(d->tmap, d->nsplits, h.N, d->d_pad, row_begin, row_end, condensed_offset(h.N, row_begin), normalise,
-                                 out_is_u16, d_out, st));
-    launch_counter_add(1);
-    return TD_OK;
+    return run_rf_incidence(ts, d, normalise, row_begin, row_end, d_out, out_is_u16, (cudaStream_t)stream);
 }
 
 int td_geo_get_stats(td_treeset *ts, td_geo_stats *out)
