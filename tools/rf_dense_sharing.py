@@ -20,3 +20,21 @@ for k in ('merge', 'auto'):
     res[k] = out.clone()
     print(k, '%.3f ms' % (e0.elapsed_time(e1) / 10), 'dict_shared', ts.info.dict_shared)
 print('identical:', torch.equal(res['merge'], res['auto']))
+# euc and rf+euc: merge kernel vs the split-extended tile kernel (+ incidence contraction for rf)
+outs = {m: torch.empty(pairs, dtype=torch.float64, device='cuda') for m in ('rf', 'euc')}
+for metrics in (('euc',), ('rf', 'euc')):
+    keep = {}
+    for k in ('merge', 'auto'):
+        if k == 'auto': os.environ.pop('TREEDIST_PAIR_KERNEL', None)
+        else: os.environ['TREEDIST_PAIR_KERNEL'] = k
+        ptrs = {m: outs[m].data_ptr() for m in metrics}
+        for _ in range(3): ts.pairwise_device(metrics, ptrs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): ts.pairwise_device(metrics, ptrs)
+        e1.record(); torch.cuda.synchronize()
+        keep[k] = {m: outs[m].clone() for m in metrics}
+        print('+'.join(metrics), k, '%.3f ms' % (e0.elapsed_time(e1) / 10))
+    d = (keep['merge']['euc'] - keep['auto']['euc']).abs() / keep['merge']['euc'].clamp_min(1e-300)
+    print('   euc max rel diff %.2e, exact zeros agree: %s' % (float(d[keep['merge']['euc'] > 0].max()), bool(((keep['merge']['euc'] == 0) == (keep['auto']['euc'] == 0)).all())))

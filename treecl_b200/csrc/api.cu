@@ -97,6 +97,11 @@ struct DeviceSet {
     alignas(64) unsigned char tmap[128];
     alignas(64) unsigned char tmap_leaf_a[128], tmap_leaf_b[128];   // TMA descriptors over leafT (postings pipeline)
     bool leaf_maps = false;
+    // split-extended matrix [n_k + dict_shared][Npad] for the Euclidean metric of densely sharing sets (built on demand)
+    double *leafX = nullptr;
+    int x_rows = 0;
+    alignas(64) unsigned char tmap_x_a[128], tmap_x_b[128];
+    std::mutex lx_mu;
     std::mutex x_mu;
     // event buffers of the two-kernel join (one launch at a time per set: later launches wait on ev_done)
     std::mutex ev_mu;
@@ -369,6 +374,51 @@ static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t
     return TD_OK;
 }
 
+// Euclidean metric (and RF through the incidence contraction) of a DENSELY sharing set: the shared splits become extra rows of the
+// matrix behind the tile kernel's tensor maps, so the common-split products are part of its fp64 tensor-core dot product and no events
+// are needed.  wrf has no product form and stays with the merge kernel.
+constexpr double kSplitRowsBytesMax = 8e9;
+
+static bool split_rows_fit(const HostSet &h, const DeviceSet *d)
+{
+    return h.uniform && d->leaf_maps && h.dict_shared > 0 && ((double)d->n_k + (double)h.dict_shared) * (double)d->Npad * 8.0 <= kSplitRowsBytesMax
+           && rf_incidence_fits(h);
+}
+
+static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams &p, void *const d_out[4], cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    int rc;
+    {
+        std::lock_guard<std::mutex> guard(d->lx_mu);
+        if (!d->leafX) {
+            const int rows = d->n_k + (int)h.dict_shared;
+            double *X = nullptr;
+            if ((rc = dev_alloc(d, &X, (size_t)rows * d->Npad))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(X, d->leafT, (size_t)d->n_k * d->Npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(X + (size_t)d->n_k * d->Npad, 0, (size_t)h.dict_shared * d->Npad * sizeof(double), st));
+            CUDA_TRY(launch_build_split_rows(d->shared, d->sh_stride, h.N, d->Npad, X + (size_t)d->n_k * d->Npad, st));
+            launch_counter_add(1);
+            if (make_leaf_tensor_maps(X, (int64_t)d->Npad, rows, d->tmap_x_a, d->tmap_x_b) != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed"); return TD_ERR_CUDA; }
+            CUDA_TRY(cudaStreamSynchronize(st));              // other streams may use the matrix from now on
+            d->leafX = X; d->x_rows = rows;
+        }
+    }
+    if (pairsplit_tiles(false, p) > 0) {
+        p.seg = nullptr; p.ev = nullptr; p.ev_capacity = 0; p.trace = nullptr;
+        p.tmap_a = d->tmap_x_a; p.tmap_b = d->tmap_x_b; p.k_rows = d->x_rows; p.q2t = d->q2t;
+        p.col_tiles_total = (int)((d->N + 31) / 32);
+        CUDA_TRY(launch_pairsplit_tiles(4u, false, p, st));
+        CUDA_TRY(launch_exact_fixup(4u, false, p, d->sm_count, st));
+        launch_counter_add(2);
+    }
+    if (m3 & 1u) {
+        if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
+        if ((rc = run_rf_incidence(ts, d, p.normalise, p.row_begin, p.row_end, d_out[TD_RF], 0, st))) return rc;
+    }
+    return TD_OK;
+}
+
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
@@ -421,13 +471,16 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
             if (rc) return rc;
             goto geodesic;
         }
-        const int tile = use_join ? 64 : pick_tile(d, weighted);
+        // euc (+ rf) on a densely sharing set: split-extended tile kernel (+ incidence contraction) instead of the merge kernel
+        const bool want_ext = force ? !strcmp(force, "extended") : true;
+        const bool use_ext = (m3 & 4u) && !(m3 & 2u) && !rect && !use_join && want_ext && split_rows_fit(h, d);
+        const int tile = (use_join || use_ext) ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
         p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits; p.nshared = d->nshared;
         p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
         p.q1 = d->q1; p.q2 = d->q2; p.table_slots = slots; p.row_table_slots = row_slots;
-        p.N = d->N; p.n_k = d->n_k; p.n_taxa = d->n_taxa; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
+        p.N = d->N; p.n_k = d->n_k; p.n_taxa = d->n_taxa; p.k_rows = d->n_taxa; p.row_begin = row_begin; p.row_end = row_end; p.normalise = normalise;
         p.out[0] = (double *)d_out[TD_RF]; p.out[1] = (double *)d_out[TD_WRF]; p.out[2] = (double *)d_out[TD_EUC];
         for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !p.out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
         int64_t tile_cols;
@@ -442,12 +495,13 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         p.tile_row0 = (int)(row_begin / tile);
         const int64_t tile_rows = (row_end + tile - 1) / tile - p.tile_row0;
         if (tile_rows > 0 && tile_cols > 0) {
-            if (use_join) {
+            if (use_join || use_ext) {
                 const uint32_t w = d->next_worklist.fetch_add(1) % kWorklists;
                 p.wl_pairs = d->wl_pairs + (size_t)w * kWorklistCap; p.wl_count = d->wl_count + w; p.wl_capacity = kWorklistCap;
                 CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
             }
-            if (use_split) { int rc = run_pairsplit(d, m3, rect, p, ev_capacity, st); if (rc) return rc; }
+            if (use_ext) { int rc = run_split_rows(ts, d, m3, p, d_out, st); if (rc) return rc; }
+            else if (use_split) { int rc = run_pairsplit(d, m3, rect, p, ev_capacity, st); if (rc) return rc; }
             else {
                 if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
                 else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));

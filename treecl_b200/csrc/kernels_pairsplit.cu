@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     TRACE(0);
 
     // ---- leaf-length chunks: two TMA requests per chunk (rows of A, rows of B), issued by one thread ------------------------------------
-    const int k_used = kWeighted ? (p.n_taxa + 3) & ~3 : 0;                  // <= n_k; rows >= n_taxa of leafT are zero
+    const int k_used = kWeighted ? (p.k_rows + 3) & ~3 : 0;                   // rows of the matrix behind the tensor maps (beyond: zeros)
     const int n_chunks = (k_used + KCH - 1) / KCH;
     auto issue_chunk = [&](int chunk, int stage) {                            // one thread
         mbar_expect_tx(&full[stage], (uint32_t)(KCH * (SA + SB) * sizeof(double)));
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
     {
         const uint2 *segp = p.seg + (size_t)(tile_r * (TR / RG)) * p.col_tiles_total + tile_c;
 #pragma unroll
-        for (int q = 0; q < TR / RG; q++) sg[q] = segp[(size_t)q * p.col_tiles_total];
+        for (int q = 0; q < TR / RG; q++) sg[q] = p.seg ? segp[(size_t)q * p.col_tiles_total] : make_uint2(0u, 0u);   // no table: no events
     }
     // ---- per-tree scalars: requested now (threads 0..95), parked in registers, put into shared memory just before the epilogue -------
     int sc_s = 0; double sc_q1 = 0.0, sc_q2 = 0.0;
@@ -675,6 +675,25 @@ cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, voi
     return cudaSuccess;
 }
 
+// Split-extended matrix for densely sharing sets: rows [0, n_k) are leafT, row n_k + sid holds the lengths of shared split sid (0 where a
+// tree does not have it).  With it the common-split products of the Euclidean metric are part of the tile kernel's dot product and no
+// events are needed:  euc^2 = Q2t_i + Q2t_j - 2 <row_i, row_j>.
+__global__ void build_split_rows_kernel(const SplitRec *__restrict__ shared, int sh_stride, int64_t N, int64_t ld, double *__restrict__ rows)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N * sh_stride) return;
+    const SplitRec r = shared[e];
+    if (r.id != kSentinelId) rows[(size_t)r.pad * ld + e / sh_stride] = r.len;
+}
+
+cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, cudaStream_t st)
+{
+    const int64_t n = N * sh_stride;
+    if (n <= 0) return cudaSuccess;
+    build_split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shared, sh_stride, N, ld, rows);
+    return cudaGetLastError();
+}
+
 size_t pairsplit_dense_smem_bytes(uint32_t mask)
 {
     size_t s = 128 + kRegionBytes(mask) + NSTAGE * 8 + (TR + TC) * sizeof(int);
@@ -719,6 +738,17 @@ size_t pairsplit_events_smem_bytes(uint32_t mask, int sh_stride, int col_tiles_t
 }
 int pairsplit_row_group() { return RG; }
 
+// the tile kernel alone (p carries the tile geometry; p.seg == nullptr: no events)
+cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st)
+{
+    if (p.n_tiles <= 0) return cudaSuccess;
+    const size_t smem_d = pairsplit_dense_smem_bytes(mask);
+    // rectangular: (column tiles, tile rows); triangular: tile rows u and R-1-u folded into one grid row
+    const dim3 grid = rect ? dim3((unsigned)p.tiles_x, (unsigned)p.tri_rows)
+                           : dim3((unsigned)(2 * (p.tiles_x - 2 * p.tile_row0) - 2 * (p.tri_rows - 1)), (unsigned)((p.tri_rows + 1) / 2));
+    return rect ? launch_dense_mask<true>(mask, p, grid, smem_d, st) : launch_dense_mask<false>(mask, p, grid, smem_d, st);
+}
+
 // p must carry the tile geometry (pairsplit_tiles), the postings, the segment table and the event buffer; *ev_cursor must be zero
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches)
 {
@@ -735,11 +765,7 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         ++*launches;
         if (e != cudaSuccess) return e;
     }
-    const size_t smem_d = pairsplit_dense_smem_bytes(mask);
-    // rectangular: (column tiles, tile rows); triangular: tile rows u and R-1-u folded into one grid row
-    const dim3 grid = rect ? dim3((unsigned)p.tiles_x, (unsigned)p.tri_rows)
-                           : dim3((unsigned)(2 * (p.tiles_x - 2 * p.tile_row0) - 2 * (p.tri_rows - 1)), (unsigned)((p.tri_rows + 1) / 2));
-    e = rect ? launch_dense_mask<true>(mask, p, grid, smem_d, st) : launch_dense_mask<false>(mask, p, grid, smem_d, st);
+    e = launch_pairsplit_tiles(mask, rect, p, st);
     ++*launches;
     if (e != cudaSuccess || !weighted) return e;
     ++*launches;
