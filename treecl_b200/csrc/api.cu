@@ -381,8 +381,11 @@ constexpr double kSplitRowsBytesMax = 8e9;
 
 static bool split_rows_fit(const HostSet &h, const DeviceSet *d)
 {
-    return h.uniform && d->leaf_maps && h.dict_shared > 0 && ((double)d->n_k + (double)h.dict_shared) * (double)d->Npad * 8.0 <= kSplitRowsBytesMax
-           && rf_incidence_fits(h);
+    // cost model (measured, tools/rf_dense_sharing.py): the tile kernel spends ~0.064 ps per pair and row of the extended matrix, the
+    // merge kernel ~19 ps per pair and list step (S_i + S_j steps): the extension pays while rows <= ~25 x 2 S
+    const double rows = (double)d->n_k + (double)h.dict_shared;
+    return h.uniform && d->leaf_maps && h.dict_shared > 0 && rows * (double)d->Npad * 8.0 <= kSplitRowsBytesMax
+           && rows <= 50.0 * std::max(h.max_splits, 1) && rf_incidence_fits(h);
 }
 
 static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams &p, void *const d_out[4], cudaStream_t st)
