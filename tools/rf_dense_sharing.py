@@ -21,8 +21,8 @@ for k in ('merge', 'auto'):
     print(k, '%.3f ms' % (e0.elapsed_time(e1) / 10), 'dict_shared', ts.info.dict_shared)
 print('identical:', torch.equal(res['merge'], res['auto']))
 # euc and rf+euc: merge kernel vs the split-extended tile kernel (+ incidence contraction for rf)
-outs = {m: torch.empty(pairs, dtype=torch.float64, device='cuda') for m in ('rf', 'euc')}
-for metrics in (('euc',), ('rf', 'euc')):
+outs = {m: torch.empty(pairs, dtype=torch.float64, device='cuda') for m in ('rf', 'wrf', 'euc')}
+for metrics in (('euc',), ('rf', 'euc'), ('wrf',), ('rf', 'wrf', 'euc')):
     keep = {}
     for k in ('merge', 'auto'):
         if k == 'auto': os.environ.pop('TREEDIST_PAIR_KERNEL', None)
@@ -36,5 +36,9 @@ for metrics in (('euc',), ('rf', 'euc')):
         e1.record(); torch.cuda.synchronize()
         keep[k] = {m: outs[m].clone() for m in metrics}
         print('+'.join(metrics), k, '%.3f ms' % (e0.elapsed_time(e1) / 10))
-    d = (keep['merge']['euc'] - keep['auto']['euc']).abs() / keep['merge']['euc'].clamp_min(1e-300)
-    print('   euc max rel diff %.2e, exact zeros agree: %s' % (float(d[keep['merge']['euc'] > 0].max()), bool(((keep['merge']['euc'] == 0) == (keep['auto']['euc'] == 0)).all())))
+    for m in metrics:
+        if m == 'rf':
+            print('   rf identical: %s' % torch.equal(keep['merge'][m], keep['auto'][m]))
+        else:
+            d = (keep['merge'][m] - keep['auto'][m]).abs() / keep['merge'][m].clamp_min(1e-300)
+            print('   %s max rel diff %.2e, exact zeros agree: %s' % (m, float(d[keep['merge'][m] > 0].max()), bool(((keep['merge'][m] == 0) == (keep['auto'][m] == 0)).all())))

@@ -376,7 +376,7 @@ static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t
 
 // Euclidean metric (and RF through the incidence contraction) of a DENSELY sharing set: the shared splits become extra rows of the
 // matrix behind the tile kernel's tensor maps, so the common-split products are part of its fp64 tensor-core dot product and no events
-// are needed.  wrf has no product form and stays with the merge kernel.
+// are needed; wrf is the L1 distance of the same rows.
 constexpr double kSplitRowsBytesMax = 8e9;
 
 static bool split_rows_fit(const HostSet &h, const DeviceSet *d)
@@ -411,8 +411,12 @@ static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams 
         p.seg = nullptr; p.ev = nullptr; p.ev_capacity = 0; p.trace = nullptr;
         p.tmap_a = d->tmap_x_a; p.tmap_b = d->tmap_x_b; p.k_rows = d->x_rows; p.q2t = d->q2t;
         p.col_tiles_total = (int)((d->N + 31) / 32);
-        CUDA_TRY(launch_pairsplit_tiles(4u, false, p, st));
-        CUDA_TRY(launch_exact_fixup(4u, false, p, d->sm_count, st));
+        // wrf: the L1 distance of the extended rows is the whole weighted-RF sum over shared splits and leaves (purely additive);
+        // the splits a tree shares with nobody enter through q1 := single_l1
+        p.q1 = d->single_l1;
+        const uint32_t mw = m3 & 6u;
+        CUDA_TRY(launch_pairsplit_tiles(mw, false, p, st));
+        CUDA_TRY(launch_exact_fixup(mw, false, p, d->sm_count, st));
         launch_counter_add(2);
     }
     if (m3 & 1u) {
@@ -476,7 +480,8 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         }
         // euc (+ rf) on a densely sharing set: split-extended tile kernel (+ incidence contraction) instead of the merge kernel
         const bool want_ext = force ? !strcmp(force, "extended") : true;
-        const bool use_ext = (m3 & 4u) && !(m3 & 2u) && !rect && !use_join && want_ext && split_rows_fit(h, d);
+        // (wrf and euc together: the merge kernel does both in one pass in the same time, so it keeps that case)
+        const bool use_ext = (m3 & 6u) && ((m3 & 6u) != 6u || (force && !strcmp(force, "extended"))) && !rect && !use_join && want_ext && split_rows_fit(h, d);
         const int tile = (use_join || use_ext) ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
