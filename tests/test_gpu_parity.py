@@ -142,7 +142,7 @@ def pair_kernel(request, monkeypatch):
 
 @pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
 @pytest.mark.parametrize('norm', [False, True])
-@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile', 'split'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile', 'split', 'extended'], indirect=True)
 def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_kernel):
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)
@@ -158,7 +158,7 @@ def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_
     # another kernel (rf alone -> incidence contraction, euc alone -> split-extended tile kernel on densely sharing sets)
     for metric in ('rf', 'wrf', 'euc'):
         alone = ts.pairwise((metric,), normalise=norm)[metric]
-        if metric == 'rf' or pair_kernel != 'auto':
+        if metric == 'rf' or pair_kernel not in ('auto', 'extended'):
             assert np.array_equal(alone, got[metric]), metric
         else:
             assert_close(alone, got[metric])
