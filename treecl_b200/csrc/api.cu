@@ -381,11 +381,9 @@ constexpr double kSplitRowsBytesMax = 8e9;
 
 static bool split_rows_fit(const HostSet &h, const DeviceSet *d)
 {
-    // cost model (measured, tools/rf_dense_sharing.py): the tile kernel spends ~0.064 ps per pair and row of the extended matrix, the
-    // merge kernel ~19 ps per pair and list step (S_i + S_j steps): the extension pays while rows <= ~25 x 2 S
     const double rows = (double)d->n_k + (double)h.dict_shared;
     return h.uniform && d->leaf_maps && h.dict_shared > 0 && rows * (double)d->Npad * 8.0 <= kSplitRowsBytesMax
-           && rows <= 50.0 * std::max(h.max_splits, 1) && rf_incidence_fits(h);
+           && rf_incidence_fits(h);
 }
 
 static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams &p, void *const d_out[4], cudaStream_t st)
@@ -460,28 +458,44 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         // kernel choice: sparse sharing -> tile hash join (work ~ entries + matches); dense sharing -> merge-join
         const int slots = pairjoin_table_slots(h.max_shared);
         const char *force = getenv("TREEDIST_PAIR_KERNEL");
+        if (force && (!*force || !strcmp(force, "auto"))) force = nullptr;
         const int row_slots = pairjoin_row_table_slots(h.max_tile_entries);
         const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, row_slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024)
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
-        bool use_join = join_fits && h.mean_common <= 9.0;        // measured crossover with the merge kernel: ~10 (tools/kernel_choice.py)
-        if (force && !strcmp(force, "merge")) use_join = false;
-        if (force && (!strcmp(force, "join") || !strcmp(force, "join_tile") || !strcmp(force, "split")) && join_fits) use_join = true;
         const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
         const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
                                 && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
-        const bool use_split = use_join && split_fits && !(force && (!strcmp(force, "join") || !strcmp(force, "join_tile")));
-        // RF alone on a densely sharing set: the int8 tcgen05 incidence contraction instead of the merge kernel (same integers)
-        const bool want_inc = force ? !strcmp(force, "incidence") : true;
-        if (m3 == 1u && !rect && !use_join && want_inc && rf_incidence_fits(h) && h.dict_shared > 0) {
+        // Kernel choice by a cost model in picoseconds per pair, calibrated on one B200 (tools/kernel_choice.py, tools/rf_dense_sharing.py):
+        //   postings pipeline      11 + 13.4 x (expected common splits per pair): work follows the events
+        //   merge kernel           1.83 x (S_i + S_j): every pair walks both shared lists
+        //   split-extended tiles   0.064 x rows of the extended matrix (x 2.4 when it has to do the L1 sums of wrf), wrf + euc
+        //                          together excluded (the merge kernel does both in one pass in that time); rf rides on the
+        //                          incidence contraction, which alone costs next to nothing
+        const double c_split = 11.0 + 13.4 * h.mean_common;
+        const double c_merge = 1.83 * 2.0 * (double)h.total_splits / (double)std::max<int64_t>(h.N, 1);
+        const bool ext_ok = !rect && split_rows_fit(h, d) && ((m3 & 6u) != 6u);
+        const double c_ext = ext_ok ? 0.064 * ((double)d->n_k + (double)h.dict_shared) * ((m3 & 2u) ? 2.4 : 1.0) : 1e30;
+        const bool inc_ok = m3 == 1u && !rect && rf_incidence_fits(h) && h.dict_shared > 0;
+        enum { K_SPLIT, K_JOIN, K_MERGE, K_EXT, K_INC } kernel;
+        if (inc_ok && c_split > 20.0) kernel = K_INC;                               // rf alone unless the set shares almost nothing
+        else if (join_fits && c_split <= std::min(c_merge, c_ext)) kernel = split_fits ? K_SPLIT : K_JOIN;
+        else kernel = (m3 & 6u) && c_ext < c_merge ? K_EXT : K_MERGE;
+        if (force) {                                                                // a forced kernel that cannot run falls back to the merge kernel
+            kernel = K_MERGE;
+            if (!strcmp(force, "merge")) kernel = K_MERGE;
+            else if (!strcmp(force, "split") && join_fits) kernel = split_fits ? K_SPLIT : K_JOIN;
+            else if ((!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) kernel = K_JOIN;
+            else if (!strcmp(force, "incidence")) kernel = inc_ok ? K_INC : K_MERGE;
+            else if (!strcmp(force, "extended")) kernel = (!rect && split_rows_fit(h, d) && (m3 & 6u)) ? K_EXT : (inc_ok ? K_INC : K_MERGE);
+        }
+        if (getenv("TREEDIST_DEBUG")) fprintf(stderr, "[treedist] mask %u: kernel %d (0 split, 1 join, 2 merge, 3 extended, 4 incidence); cost model split %.1f merge %.1f ext %.1f ps/pair; join_fits %d split_fits %d\n", m3, (int)kernel, c_split, c_merge, c_ext, (int)join_fits, (int)split_fits);
+        const bool use_split = kernel == K_SPLIT, use_join = kernel == K_SPLIT || kernel == K_JOIN, use_ext = kernel == K_EXT;
+        if (kernel == K_INC) {
             if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
             int rc = run_rf_incidence(ts, d, normalise, row_begin, row_end, d_out[TD_RF], 0, st);
             if (rc) return rc;
             goto geodesic;
         }
-        // euc (+ rf) on a densely sharing set: split-extended tile kernel (+ incidence contraction) instead of the merge kernel
-        const bool want_ext = force ? !strcmp(force, "extended") : true;
-        // (wrf and euc together: the merge kernel does both in one pass in the same time, so it keeps that case)
-        const bool use_ext = (m3 & 6u) && ((m3 & 6u) != 6u || (force && !strcmp(force, "extended"))) && !rect && !use_join && want_ext && split_rows_fit(h, d);
         const int tile = (use_join || use_ext) ? 64 : pick_tile(d, weighted);
         if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
         PairParams p{};
