@@ -392,7 +392,6 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
     SplitRec *stageB = reinterpret_cast<SplitRec *>(cur); cur += (size_t)TC * p.sh_stride * sizeof(SplitRec);   // column trees' lists
     uint32_t *events = reinterpret_cast<uint32_t *>(cur); cur += kEventCap * sizeof(uint32_t);          // row | col<<8 | pos<<16
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cur); cur += 8;
-    uint32_t *ev_count = reinterpret_cast<uint32_t *>(cur);
 
     const int tid = threadIdx.x;
     const long long t_begin = p.n_tiles * (long long)blockIdx.x / gridDim.x;
