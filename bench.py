@@ -212,7 +212,7 @@ def run_ours(args):
     def e2e_step():
         t = _lib.TreeSet(trees)                                   # parse + encode on the host
         t.pairwise(METRICS, row_begin=r0, row_end=r1, device=local, out=host_np)   # H2D, kernels, D2H
-        h2d = upload_bytes(t.info, nt)
+        h2d = upload_bytes(t.info, nt, METRICS)
         t.close()
         return h2d
 
@@ -282,11 +282,14 @@ def run_ours(args):
     return 0
 
 
-def upload_bytes(info, nt):
+def upload_bytes(info, nt, metrics=('rf', 'euc')):
     sh = ((info.max_shared + 1) + 1) & ~1
     s = max(info.max_splits, 1)
-    # leaf lengths, shared lists (+ posting index), per-tree scalars, full lists (ids, lengths, masks), postings (tree, end, length)
-    return nt * (info.n_taxa * 8 + sh * (16 + 4) + 4 + 7 * 8 + s * (4 + 8 + 8 * info.words)) + info.n_postings * 16
+    # leaf lengths, shared lists (+ posting index), per-tree scalars, postings (tree, end, length) ...
+    b = nt * (info.n_taxa * 8 + sh * (16 + 4) + 4 + 7 * 8) + info.n_postings * 16
+    if 'geo' in metrics or not info.uniform:
+        b += nt * (s * (4 + 8 + 8 * info.words) + 8 * info.words + 4)      # ... and, for the kernels that need them, the full lists
+    return b
 
 
 def main():

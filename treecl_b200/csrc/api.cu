@@ -98,6 +98,8 @@ struct DeviceSet {
     alignas(64) unsigned char tmap_leaf_a[128], tmap_leaf_b[128];   // TMA descriptors over leafT (postings pipeline)
     bool leaf_maps = false;
     // split-extended matrix [n_k + dict_shared][Npad] for the Euclidean metric of densely sharing sets (built on demand)
+    bool full_lists = false;            // ids / lens / masks / leafmask / rooted uploaded (geodesic and restrict-then-join kernels)
+    std::mutex full_mu;
     double *leafX = nullptr;
     int x_rows = 0;
     alignas(64) unsigned char tmap_x_a[128], tmap_x_b[128];
@@ -227,11 +229,8 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         CUDA_TRY(cudaMemcpyAsync(d->post_end, h.post_end.data(), d->n_post * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d->post_len, h.post_len.data(), d->n_post * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d->leafmask, h.leafmask.data(), N * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d->rooted, h.tree_rooted.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // the full split lists (ids, lengths, masks), leaf masks and rootedness are only read by the geodesic and the restrict-then-join
+    // kernels: they follow on first use (upload_full_lists), a matrix of rf / wrf / euc on one leaf set never pays for them
     if (h.n_taxa > 0) {
         CUDA_TRY(launch_transpose_leaf(d->leaflen, d->leafT, h.N, h.n_taxa, d->Npad, st));
         launch_counter_add(1);
@@ -241,6 +240,23 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     CUDA_TRY(cudaStreamSynchronize(st));
     own.keep = true;
     ts->devs[device] = d;
+    return TD_OK;
+}
+
+// second part of the upload, on first use by the geodesic / restrict-then-join kernels (space is already part of the set's arena)
+static int upload_full_lists(td_treeset *ts, DeviceSet *d, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> guard(d->full_mu);
+    if (d->full_lists) return TD_OK;
+    const HostSet &h = ts->host;
+    const size_t N = (size_t)h.N;
+    CUDA_TRY(cudaMemcpyAsync(d->ids, h.ids.data(), N * d->stride * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->lens, h.lens.data(), N * d->stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->masks, h.masks.data(), N * d->stride * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->leafmask, h.leafmask.data(), N * d->W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->rooted, h.tree_rooted.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                  // launches on other streams may read the arrays from now on
+    d->full_lists = true;
     return TD_OK;
 }
 
@@ -432,6 +448,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
         if (h.max_splits > 128 || h.W > 3) { set_error("the restrict-then-join kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         CUDA_TRY(cudaSetDevice(d->device));
+        { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
         GeoParams g{};
         g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
         g.leafmask = d->leafmask; g.rooted = d->rooted;
@@ -535,6 +552,7 @@ geodesic:
     if (mask & TD_MASK(TD_GEO)) {
         if (!d_out[TD_GEO]) { set_error("output pointer for the geodesic metric is null"); return TD_ERR_ARG; }
         if (h.max_splits > 128 || h.W > 3) { set_error("geodesic kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
+        { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
         GeoParams g{};
         g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
         g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);

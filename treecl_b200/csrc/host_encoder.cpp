@@ -18,6 +18,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <pthread.h>
@@ -507,7 +508,10 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     lap("pack");
     // ---- global split dictionary (exact: ties on the 64-bit hash are resolved by comparing the masks) --------
     struct Ent { uint64_t h; uint32_t tree, slot; };
-    std::vector<uint32_t> id_of((size_t)N * stride, kSentinelId), mult_of((size_t)N * stride, 0), sid_of((size_t)N * stride, 0), x_of((size_t)N * stride, 0);
+    // per (tree, slot): dictionary id, multiplicity, compact shared index, position in the postings.  Only slots < n_splits are ever
+    // written or read, so the arrays are left uninitialised (a serial fill of four of them and of the two entry tables cost ~1.5 ms)
+    const size_t n_slots = (size_t)N * stride;
+    std::unique_ptr<uint32_t[]> id_of(new uint32_t[n_slots]), mult_of(new uint32_t[n_slots]), sid_of(new uint32_t[n_slots]), x_of(new uint32_t[n_slots]);
     if (total > 0) {
         std::vector<int64_t> off(N + 1, 0);
         for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
@@ -515,7 +519,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         // entries per bucket, a prefix over (bucket, chunk) gives every chunk its own slice of every bucket, and the chunks scatter
         // in parallel (entries of a bucket stay in tree order)
         constexpr int NB = 256;
-        std::vector<Ent> ents(total);
+        std::unique_ptr<Ent[]> ents(new Ent[total]);
         const int64_t n_chunks = std::min<int64_t>(N, (int64_t)n_threads * 4);
         std::vector<int64_t> cpos((size_t)n_chunks * NB, 0);
         parallel_for(n_chunks, n_threads, [&](int64_t c, int) {
@@ -535,18 +539,18 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             }
             bstart[NB] = run;
         }
-        std::vector<Ent> sorted(total);
+        std::unique_ptr<Ent[]> sorted(new Ent[total]);
         parallel_for(n_chunks, n_threads, [&](int64_t c, int) {
             int64_t *pos = &cpos[(size_t)c * NB];
             for (int64_t e = off[N * c / n_chunks]; e < off[N * (c + 1) / n_chunks]; e++) sorted[pos[ents[e].h >> 56]++] = ents[e];
         });
-        ents.clear(); ents.shrink_to_fit();
+        ents.reset();
         lap("  dict: hash+scatter");
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
         std::vector<int64_t> uniq(NB + 1, 0), shared(NB + 1, 0), shent(NB + 1, 0);
         std::vector<double> copairs(NB, 0.0);
         parallel_for(NB, n_threads, [&](int64_t b, int) {
-            auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
+            Ent *lo = sorted.get() + bstart[b], *hi = sorted.get() + bstart[b + 1];
             std::sort(lo, hi, [&](const Ent &x, const Ent &y) {
                 if (x.h != y.h) return x.h < y.h;
                 int c = mask_cmp(mask_of(x), mask_of(y), W);
@@ -576,7 +580,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         // equal splits in the sorted bucket IS the posting list of that split (trees ascending)
         hs.post_tree.resize(n_post); hs.post_end.resize(n_post); hs.post_len.resize(n_post);
         parallel_for(NB, n_threads, [&](int64_t b, int) {
-            auto lo = sorted.begin() + bstart[b], hi = sorted.begin() + bstart[b + 1];
+            Ent *lo = sorted.get() + bstart[b], *hi = sorted.get() + bstart[b + 1];
             int64_t id = uniq[b], sid = shared[b], x = shent[b];
             for (auto it = lo; it != hi;) {
                 auto run = it + 1;
