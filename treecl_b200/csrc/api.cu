@@ -102,6 +102,10 @@ struct DeviceSet {
     std::mutex full_mu;
     double *leafX = nullptr;
     int x_rows = 0;
+    // hybrid postings pipeline: leafT plus the heavy_rows most widely held shared splits as rows (built on demand), q1 without them
+    double *leafH = nullptr, *q1_light = nullptr;
+    alignas(64) unsigned char tmap_h_a[128], tmap_h_b[128];
+    std::mutex lh_mu;
     alignas(64) unsigned char tmap_x_a[128], tmap_x_b[128];
     std::mutex lx_mu;
     std::mutex x_mu;
@@ -186,7 +190,7 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         const size_t o_leafT = take((size_t)d->n_k * Npad * 8), o_leaflen = take(N * std::max(h.n_taxa, 1) * 8);
         const size_t o_shared = take(Npad * d->sh_stride * sizeof(SplitRec));
         const size_t o_nsplits = take(Npad * 4), o_nshared = take(Npad * 4);
-        const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8), o_q2t = take(Npad * 8);
+        const size_t o_sum = take(Npad * 8), o_norm = take(Npad * 8), o_s1 = take(Npad * 8), o_s2 = take(Npad * 8), o_q1 = take(Npad * 8), o_q2 = take(Npad * 8), o_q2t = take(Npad * 8), o_q1l = take(Npad * 8);
         const size_t n_post = h.post_tree.size();
         const size_t o_ptree = take(n_post * 4), o_pend = take(n_post * 4), o_plen = take(n_post * 8), o_shx = take(Npad * d->sh_stride * 4);
         const size_t o_ids = take(N * d->stride * 4), o_lens = take(N * d->stride * 8), o_masks = take(N * d->stride * d->W * 8);
@@ -200,7 +204,7 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
         d->leafT = (double *)(base + o_leafT); d->leaflen = (double *)(base + o_leaflen); d->shared = (SplitRec *)(base + o_shared);
         d->nsplits = (int32_t *)(base + o_nsplits); d->nshared = (int32_t *)(base + o_nshared);
         d->sum_len = (double *)(base + o_sum); d->norm = (double *)(base + o_norm); d->single_l1 = (double *)(base + o_s1);
-        d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2); d->q2t = (double *)(base + o_q2t);
+        d->single_l2 = (double *)(base + o_s2); d->q1 = (double *)(base + o_q1); d->q2 = (double *)(base + o_q2); d->q2t = (double *)(base + o_q2t); d->q1_light = (double *)(base + o_q1l);
         d->post_tree = (int32_t *)(base + o_ptree); d->post_end = (int32_t *)(base + o_pend); d->post_len = (double *)(base + o_plen);
         d->n_post = (int64_t)n_post; d->shared_x = (int32_t *)(base + o_shx);
         d->ids = (uint32_t *)(base + o_ids); d->lens = (double *)(base + o_lens); d->masks = (uint64_t *)(base + o_masks);
@@ -224,6 +228,7 @@ static int upload(td_treeset *ts, int device, cudaStream_t st)
     CUDA_TRY(cudaMemcpyAsync(d->q1, h.q1.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->q2, h.q2.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d->q2t, h.q2t.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d->q1_light, h.q1_light.data(), N * sizeof(double), cudaMemcpyHostToDevice, st));
     if (d->n_post) {
         CUDA_TRY(cudaMemcpyAsync(d->post_tree, h.post_tree.data(), d->n_post * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d->post_end, h.post_end.data(), d->n_post * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -308,8 +313,18 @@ static size_t split_event_bytes(const DeviceSet *d, int64_t capacity, int rec)
     return 256 + up(groups * col_tiles * sizeof(uint2)) + up((size_t)capacity * rec);
 }
 
+static bool rf_incidence_fits(const HostSet &h);
+static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16,
+                            cudaStream_t st);
+
+// the hybrid form of the postings pipeline applies: heavy shared splits as matrix rows, the rest as events, rf from the incidence kernel
+static bool hybrid_applies(const HostSet &h, const DeviceSet *d, uint32_t m3, bool rect)
+{
+    return !rect && (m3 & 6u) && h.heavy_rows > 0 && d->leaf_maps && rf_incidence_fits(h) && !getenv("TREEDIST_NO_HYBRID");
+}
+
 // postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
-static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, cudaStream_t st)
+static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, void *const d_out[4], cudaStream_t st)
 {
     const long long tiles = pairsplit_tiles(rect, p);
     if (tiles <= 0) return TD_OK;
@@ -334,13 +349,36 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     p.col_tiles_total = (int)col_tiles; p.rg0 = p.tile_row0 * (64 / pairsplit_row_group());
     p.tmap_a = d->leaf_maps ? d->tmap_leaf_a : nullptr; p.tmap_b = d->leaf_maps ? d->tmap_leaf_b : nullptr;
     p.post_tree = d->post_tree; p.post_end = d->post_end; p.post_len = d->post_len; p.n_post = d->n_post; p.q2t = d->q2t; p.shared_x = d->shared_x;
+    const HostSet &h = ts->host;
+    const bool hybrid = hybrid_applies(h, d, m3, rect);
+    uint32_t mk = m3;
+    if (hybrid) {
+        {
+            std::lock_guard<std::mutex> guard(d->lh_mu);
+            if (!d->leafH) {
+                const int rows = d->n_k + h.heavy_rows;
+                double *X = nullptr; int rc;
+                if ((rc = dev_alloc(d, &X, (size_t)rows * d->Npad))) return rc;
+                CUDA_TRY(cudaMemcpyAsync(X, d->leafT, (size_t)d->n_k * d->Npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                CUDA_TRY(cudaMemsetAsync(X + (size_t)d->n_k * d->Npad, 0, (size_t)h.heavy_rows * d->Npad * sizeof(double), st));
+                CUDA_TRY(launch_build_split_rows(d->shared, d->sh_stride, h.N, d->Npad, X + (size_t)d->n_k * d->Npad, h.heavy_rows, st));
+                launch_counter_add(1);
+                if (make_leaf_tensor_maps(X, (int64_t)d->Npad, rows, d->tmap_h_a, d->tmap_h_b) != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed"); return TD_ERR_CUDA; }
+                CUDA_TRY(cudaStreamSynchronize(st));          // other streams may use the matrix from now on
+                d->leafH = X;
+            }
+        }
+        p.heavy_rows = h.heavy_rows; p.k_rows = d->n_k + h.heavy_rows; p.tmap_a = d->tmap_h_a; p.tmap_b = d->tmap_h_b;
+        p.q1 = d->q1_light;                                   // wrf: the heavy splits are part of the L1 sum over the rows
+        mk = m3 & 6u;                                         // rf comes from the incidence contraction (the events only count light splits)
+    }
     CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
     CUDA_TRY(cudaMemsetAsync(p.ev_cursor, 0, sizeof(uint32_t), st));
     int launches = 0;
     unsigned long long *trace = nullptr;
     const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
     if (trace_path) { CUDA_TRY(cudaMalloc(&trace, (size_t)tiles * 64)); CUDA_TRY(cudaMemsetAsync(trace, 0, (size_t)tiles * 64, st)); p.trace = trace; }
-    CUDA_TRY(launch_pairsplit(m3, rect, p, d->sm_count, st, &launches));
+    CUDA_TRY(launch_pairsplit(mk, rect, p, d->sm_count, st, &launches));
     if (trace) {
         std::vector<unsigned long long> host((size_t)tiles * 8);
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -350,6 +388,11 @@ static int run_pairsplit(DeviceSet *d, uint32_t m3, bool rect, PairParams &p, in
     }
     CUDA_TRY(cudaEventRecord(d->ev_done, st));
     launch_counter_add(launches);
+    if (hybrid && (m3 & 1u)) {
+        if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
+        int rc = run_rf_incidence(ts, d, p.normalise, p.row_begin, p.row_end, d_out[TD_RF], 0, st);
+        if (rc) return rc;
+    }
     return TD_OK;
 }
 
@@ -414,7 +457,7 @@ static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams 
             if ((rc = dev_alloc(d, &X, (size_t)rows * d->Npad))) return rc;
             CUDA_TRY(cudaMemcpyAsync(X, d->leafT, (size_t)d->n_k * d->Npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
             CUDA_TRY(cudaMemsetAsync(X + (size_t)d->n_k * d->Npad, 0, (size_t)h.dict_shared * d->Npad * sizeof(double), st));
-            CUDA_TRY(launch_build_split_rows(d->shared, d->sh_stride, h.N, d->Npad, X + (size_t)d->n_k * d->Npad, st));
+            CUDA_TRY(launch_build_split_rows(d->shared, d->sh_stride, h.N, d->Npad, X + (size_t)d->n_k * d->Npad, (int)h.dict_shared, st));
             launch_counter_add(1);
             if (make_leaf_tensor_maps(X, (int64_t)d->Npad, rows, d->tmap_x_a, d->tmap_x_b) != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed"); return TD_ERR_CUDA; }
             CUDA_TRY(cudaStreamSynchronize(st));              // other streams may use the matrix from now on
@@ -479,23 +522,28 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         const int row_slots = pairjoin_row_table_slots(h.max_tile_entries);
         const bool join_fits = h.max_shared <= 255 && pairjoin_persistent_smem_bytes(m3, row_slots, d->sh_stride) <= std::min<size_t>(d->max_smem_optin, 200 * 1024)
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
-        const int64_t ev_capacity = std::max<int64_t>(h.total_common, 1);
+        // events the postings pipeline can generate at most: all (pair, common split) incidences, minus those of the heavy rows in its hybrid form
+        const int64_t ev_capacity = std::max<int64_t>(h.total_common - (hybrid_applies(h, d, m3, rect) ? h.heavy_events : 0), 1);
         const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
                                 && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         // Kernel choice by a cost model in picoseconds per pair, calibrated on one B200 (tools/kernel_choice.py, tools/rf_dense_sharing.py):
-        //   postings pipeline      11 + 13.4 x (expected common splits per pair): work follows the events
+        //   postings pipeline      11 + 13.4 x (expected common splits per pair): work follows the events; in its hybrid form the
+        //                          splits held by the most trees are rows of the matrix (0.064 each) and leave the events
         //   merge kernel           1.83 x (S_i + S_j): every pair walks both shared lists
         //   split-extended tiles   0.064 x rows of the extended matrix (x 2.4 when it has to do the L1 sums of wrf), wrf + euc
         //                          together excluded (the merge kernel does both in one pass in that time); rf rides on the
         //                          incidence contraction, which alone costs next to nothing
-        const double c_split = 11.0 + 13.4 * h.mean_common;
+        const double c_split = hybrid_applies(h, d, m3, rect)
+                                   ? 11.0 + 13.4 * (h.mean_common - h.heavy_common) + 0.064 * h.heavy_rows * ((m3 & 2u) ? 2.4 : 1.0)
+                                   : 11.0 + 13.4 * h.mean_common;
         const double c_merge = 1.83 * 2.0 * (double)h.total_splits / (double)std::max<int64_t>(h.N, 1);
         const bool ext_ok = !rect && split_rows_fit(h, d) && ((m3 & 6u) != 6u);
         const double c_ext = ext_ok ? 0.064 * ((double)d->n_k + (double)h.dict_shared) * ((m3 & 2u) ? 2.4 : 1.0) : 1e30;
         const bool inc_ok = m3 == 1u && !rect && rf_incidence_fits(h) && h.dict_shared > 0;
         enum { K_SPLIT, K_JOIN, K_MERGE, K_EXT, K_INC } kernel;
         if (inc_ok && c_split > 20.0) kernel = K_INC;                               // rf alone unless the set shares almost nothing
-        else if (join_fits && c_split <= std::min(c_merge, c_ext)) kernel = split_fits ? K_SPLIT : K_JOIN;
+        else if (split_fits && c_split <= std::min(c_merge, c_ext)) kernel = K_SPLIT;
+        else if (!split_fits && join_fits && 29.0 + 62.0 * h.mean_common <= std::min(c_merge, c_ext)) kernel = K_JOIN;   // fused hash join (event buffer too large)
         else kernel = (m3 & 6u) && c_ext < c_merge ? K_EXT : K_MERGE;
         if (force) {                                                                // a forced kernel that cannot run falls back to the merge kernel
             kernel = K_MERGE;
@@ -505,7 +553,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
             else if (!strcmp(force, "incidence")) kernel = inc_ok ? K_INC : K_MERGE;
             else if (!strcmp(force, "extended")) kernel = (!rect && split_rows_fit(h, d) && (m3 & 6u)) ? K_EXT : (inc_ok ? K_INC : K_MERGE);
         }
-        if (getenv("TREEDIST_DEBUG")) fprintf(stderr, "[treedist] mask %u: kernel %d (0 split, 1 join, 2 merge, 3 extended, 4 incidence); cost model split %.1f merge %.1f ext %.1f ps/pair; join_fits %d split_fits %d\n", m3, (int)kernel, c_split, c_merge, c_ext, (int)join_fits, (int)split_fits);
+        if (getenv("TREEDIST_DEBUG")) fprintf(stderr, "[treedist] mask %u: kernel %d (0 split, 1 join, 2 merge, 3 extended, 4 incidence); cost model split %.1f merge %.1f ext %.1f ps/pair; join_fits %d split_fits %d; heavy rows %d covering %.2f of %.2f common splits per pair, hybrid %d\n", m3, (int)kernel, c_split, c_merge, c_ext, (int)join_fits, (int)split_fits, h.heavy_rows, h.heavy_common, h.mean_common, (int)hybrid_applies(h, d, m3, rect));
         const bool use_split = kernel == K_SPLIT, use_join = kernel == K_SPLIT || kernel == K_JOIN, use_ext = kernel == K_EXT;
         if (kernel == K_INC) {
             if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
@@ -540,7 +588,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                 CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
             }
             if (use_ext) { int rc = run_split_rows(ts, d, m3, p, d_out, st); if (rc) return rc; }
-            else if (use_split) { int rc = run_pairsplit(d, m3, rect, p, ev_capacity, st); if (rc) return rc; }
+            else if (use_split) { int rc = run_pairsplit(ts, d, m3, rect, p, ev_capacity, d_out, st); if (rc) return rc; }
             else {
                 if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
                 else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));

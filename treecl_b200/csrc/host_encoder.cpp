@@ -549,6 +549,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         auto mask_of = [&](const Ent &en) { return &enc[en.tree].masks[(size_t)en.slot * W]; };
         std::vector<int64_t> uniq(NB + 1, 0), shared(NB + 1, 0), shent(NB + 1, 0);
         std::vector<double> copairs(NB, 0.0);
+        std::vector<std::vector<uint32_t>> bmult(NB);          // multiplicities of the shared runs of every bucket, in run order
         parallel_for(NB, n_threads, [&](int64_t b, int) {
             Ent *lo = sorted.get() + bstart[b], *hi = sorted.get() + bstart[b + 1];
             std::sort(lo, hi, [&](const Ent &x, const Ent &y) {
@@ -561,7 +562,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             for (auto it = lo; it != hi;) {
                 auto run = it + 1;
                 while (run != hi && run->h == it->h && mask_cmp(mask_of(*run), mask_of(*it), W) == 0) run++;
-                u++; if (run - it >= 2) { sh++; she += run - it; }
+                u++; if (run - it >= 2) { sh++; she += run - it; bmult[b].push_back((uint32_t)(run - it)); }
                 cp += 0.5 * (double)(run - it) * (double)(run - it - 1);
                 it = run;
             }
@@ -574,6 +575,31 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         hs.total_common = (int64_t)(cp_total + 0.5);
         hs.mean_common = N > 1 ? cp_total / (0.5 * (double)N * (double)(N - 1)) : 0.0;
         hs.dict_size = uniq[NB];
+        // Compact index of the shared splits = rank by DESCENDING multiplicity: the splits held by many trees (most of the events) come
+        // first, so "the heavy rows" of the hybrid tile kernel are simply the indices below hs.heavy_rows.
+        std::vector<uint32_t> sid_rank((size_t)hs.dict_shared), mult_sorted((size_t)hs.dict_shared);
+        {
+            std::vector<uint32_t> mult_old((size_t)hs.dict_shared);
+            for (int b = 0; b < NB; b++) std::copy(bmult[b].begin(), bmult[b].end(), mult_old.begin() + shared[b]);
+            std::vector<uint32_t> order((size_t)hs.dict_shared);
+            for (size_t k = 0; k < order.size(); k++) order[k] = (uint32_t)k;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return mult_old[a] > mult_old[c]; });
+            for (size_t r = 0; r < order.size(); r++) { sid_rank[order[r]] = (uint32_t)r; mult_sorted[r] = mult_old[order[r]]; }
+        }
+        // Heavy rows by the cost model of the postings pipeline (ps per pair): a row of the extended matrix costs 0.064, an expected
+        // common split per pair left to the events costs 13.4.  Rows are taken (in steps of 4, at most 4096) while they pay.
+        {
+            const double P = 0.5 * (double)N * (double)(N - 1);
+            double best = 0.0, gain = 0.0; int best_r = 0;
+            for (size_t r = 0; r < mult_sorted.size() && r < 4096; r++) {
+                gain += 13.4 * 0.5 * (double)mult_sorted[r] * (double)(mult_sorted[r] - 1) / std::max(P, 1.0) - 0.064;
+                if (((r + 1) % 4 == 0 || r + 1 == mult_sorted.size()) && gain > best) { best = gain; best_r = (int)(r + 1); }
+            }
+            hs.heavy_rows = best > 2.0 ? best_r : 0;           // not for a gain below 2 ps per pair (15 % of an almost event-free step)
+            double he = 0.0;
+            for (int r = 0; r < hs.heavy_rows; r++) he += 0.5 * (double)mult_sorted[r] * (double)(mult_sorted[r] - 1);
+            hs.heavy_common = he / std::max(P, 1.0); hs.heavy_events = (int64_t)(he + 0.5);
+        }
         const int64_t n_post = shent[NB];
         if (n_post >= (1ll << 31)) { set_error("too many shared-split entries (%lld)", (long long)n_post); return TD_ERR_UNSUPPORTED; }
         // ids, multiplicities, the compact index of the shared splits (column of the incidence matrix) and their postings: a run of
@@ -591,7 +617,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
                     const size_t at = (size_t)k->tree * stride + k->slot;
                     id_of[at] = (uint32_t)id; mult_of[at] = (uint32_t)(run - it);
                     if (is_shared) {
-                        sid_of[at] = (uint32_t)sid; x_of[at] = (uint32_t)x;
+                        sid_of[at] = sid_rank[(size_t)sid]; x_of[at] = (uint32_t)x;
                         hs.post_tree[x] = (int32_t)k->tree; hs.post_end[x] = (int32_t)x_end; hs.post_len[x] = enc[k->tree].lens[k->slot];
                         x++;
                     }
@@ -615,13 +641,13 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
     hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
     hs.shared_x.assign((size_t)N * hs.sh_stride, -1);
-    hs.q2t.assign(N, 0.0);
+    hs.q2t.assign(N, 0.0); hs.q1_light.assign(N, 0.0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
         const int S = hs.n_splits[i];
         std::vector<int> perm(S);
         for (int s = 0; s < S; s++) perm[s] = s;
         std::sort(perm.begin(), perm.end(), [&](int a, int b) { return id_of[(size_t)i * stride + a] < id_of[(size_t)i * stride + b]; });
-        int sh = 0; double s1 = 0, s2 = 0, t1 = 0, t2 = 0;
+        int sh = 0; double s1 = 0, s2 = 0, t1 = 0, t2 = 0, h1 = 0;
         for (int k = 0; k < S; k++) {
             const int s = perm[k];
             const size_t at = (size_t)i * stride + s;
@@ -630,10 +656,11 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             hs.lens[(size_t)i * stride + k] = len;
             hs.ids[(size_t)i * stride + k] = id_of[at];
             t1 += std::fabs(len); t2 += len * len;
+            if (!(mult_of[at] >= 2 && (int)sid_of[at] < hs.heavy_rows)) h1 += std::fabs(len);      // everything but the heavy splits
             if (mult_of[at] >= 2) { hs.shared_x[(size_t)i * hs.sh_stride + sh] = (int32_t)x_of[at]; hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len}; }
             else { s1 += std::fabs(len); s2 += len * len; }
         }
-        hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2;
+        hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2; hs.q1_light[i] = h1;
         double sl = 0.0;
         for (int k = 0; k < n_taxa; k++) { const double l = hs.leaflen[(size_t)i * n_taxa + k]; sl += l * l; }
         hs.q2t[i] = t2 + sl;

@@ -39,6 +39,7 @@ struct PairParams {
     int64_t N;                // trees
     int n_k;                  // taxa padded to the k-chunk
     int n_taxa;               // rows of leafT beyond n_taxa are zero: the k-loops may stop there
+    int heavy_rows;           // postings pipeline: shared splits with compact index < heavy_rows are rows of the matrix, not events
     int k_rows;               // tile kernel of the postings pipeline: rows of the matrix behind the tensor maps (n_taxa, or n_k + shared splits)
     int64_t row_begin, row_end, p_base;
     int64_t col_offset, n_cols, col_end;   // rectangular variant: columns are trees [col_offset, col_offset + n_cols)
@@ -63,7 +64,7 @@ int pairsplit_record_bytes(uint32_t mask);
 size_t pairsplit_events_smem_bytes(uint32_t mask, int sh_stride, int col_tiles_total);
 int pairsplit_row_group();
 cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, void *tmap_a, void *tmap_b);
-cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, cudaStream_t st);
+cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, int max_rows, cudaStream_t st);
 long long pairsplit_tiles(bool rect, PairParams &p);
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);
 cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st);

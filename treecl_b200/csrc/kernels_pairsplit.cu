@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
         const int i = tree0 + (e & (RG - 1)), pos = e / RG;
         int x = -1;
         if (i >= p.row_begin && i < p.row_end) x = p.shared_x[(size_t)i * p.sh_stride + pos];
+        if (x >= 0 && p.heavy_rows > 0 && p.shared[(size_t)i * p.sh_stride + pos].pad < (uint32_t)p.heavy_rows) x = -1;    // a row of the matrix, no events
         uint32_t n = 0;
         if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[e] = p.post_len[x]; }
         ent_x[e] = x; ent_n[e] = n;
@@ -678,19 +679,19 @@ cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, voi
 // Split-extended matrix for densely sharing sets: rows [0, n_k) are leafT, row n_k + sid holds the lengths of shared split sid (0 where a
 // tree does not have it).  With it the common-split products of the Euclidean metric are part of the tile kernel's dot product and no
 // events are needed:  euc^2 = Q2t_i + Q2t_j - 2 <row_i, row_j>.
-__global__ void build_split_rows_kernel(const SplitRec *__restrict__ shared, int sh_stride, int64_t N, int64_t ld, double *__restrict__ rows)
+__global__ void build_split_rows_kernel(const SplitRec *__restrict__ shared, int sh_stride, int64_t N, int64_t ld, double *__restrict__ rows, int max_rows)
 {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N * sh_stride) return;
     const SplitRec r = shared[e];
-    if (r.id != kSentinelId) rows[(size_t)r.pad * ld + e / sh_stride] = r.len;
+    if (r.id != kSentinelId && r.pad < (uint32_t)max_rows) rows[(size_t)r.pad * ld + e / sh_stride] = r.len;
 }
 
-cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, cudaStream_t st)
+cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, int max_rows, cudaStream_t st)
 {
     const int64_t n = N * sh_stride;
     if (n <= 0) return cudaSuccess;
-    build_split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shared, sh_stride, N, ld, rows);
+    build_split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(shared, sh_stride, N, ld, rows, max_rows);
     return cudaGetLastError();
 }
 

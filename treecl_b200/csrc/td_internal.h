@@ -36,6 +36,10 @@ struct HostSet {
     std::vector<double> sum_len, norm;         // all edges incl. leaves: sum l, sqrt(sum l^2)
     std::vector<double> single_l1, single_l2;  // sums over splits held by this tree only: sum |l|, sum l^2
     std::vector<double> q1, q2;                // sums over ALL internal splits: sum |l|, sum l^2
+    std::vector<double> q1_light;              // q1 minus the lengths of the tree's HEAVY shared splits (compact index < heavy_rows)
+    int32_t heavy_rows = 0;                    // shared splits (by descending multiplicity) that the hybrid tile kernel takes as matrix rows
+    int64_t heavy_events = 0;                  // sum over the heavy splits of m (m - 1) / 2: events the hybrid form does not generate
+    double heavy_common = 0.0;                 // expected common splits per pair covered by the heavy rows
     std::vector<double> q2t;                   // q2 + sum of squared leaf-edge lengths (dot-product form of the Euclidean kernel)
     int64_t total_common = 0;                  // sum over all pairs of their number of common splits (exact)
     double mean_common = 0.0;                  // expected number of common splits of a random pair of the set
