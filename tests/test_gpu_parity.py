@@ -133,7 +133,11 @@ def make(kind, n_trees, n_taxa, seed):
 def pair_kernel(request, monkeypatch):
     """Force one of the rf/wrf/euc kernels (split = postings pipeline + fp64 tensor-core tile kernel, join / join_tile = fused hash
     join, merge = shared-memory merge-join) or let the library choose."""
-    if request.param != 'auto':
+    monkeypatch.delenv('TREEDIST_NO_HYBRID', raising=False)
+    if request.param == 'split_events_only':          # postings pipeline without heavy rows: every common split is an event
+        monkeypatch.setenv('TREEDIST_PAIR_KERNEL', 'split')
+        monkeypatch.setenv('TREEDIST_NO_HYBRID', '1')
+    elif request.param != 'auto':
         monkeypatch.setenv('TREEDIST_PAIR_KERNEL', request.param)
     else:
         monkeypatch.delenv('TREEDIST_PAIR_KERNEL', raising=False)
@@ -142,7 +146,7 @@ def pair_kernel(request, monkeypatch):
 
 @pytest.mark.parametrize('n_trees,n_taxa,kind', CASES)
 @pytest.mark.parametrize('norm', [False, True])
-@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile', 'split', 'extended'], indirect=True)
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'join_tile', 'split', 'split_events_only', 'extended'], indirect=True)
 def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_kernel):
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=100 + n_taxa)
@@ -158,7 +162,7 @@ def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_
     # another kernel (rf alone -> incidence contraction, euc alone -> split-extended tile kernel on densely sharing sets)
     for metric in ('rf', 'wrf', 'euc'):
         alone = ts.pairwise((metric,), normalise=norm)[metric]
-        if metric == 'rf' or pair_kernel not in ('auto', 'extended'):
+        if metric == 'rf' or pair_kernel not in ('auto', 'extended', 'split'):     # (hybrid: rf from another kernel, wrf / euc identical masks differ in chunking only)
             assert np.array_equal(alone, got[metric]), metric
         else:
             assert_close(alone, got[metric])
