@@ -1,23 +1,26 @@
-// kernels_pairsplit.cu -- rf / wrf / euc for sparsely sharing sets: postings pipeline + fp64 tensor-core tile kernel (sm_100a).
+// kernels_pairsplit.cu -- rf / wrf / euc on one leaf set: postings pipeline + fp64 tensor-core tile kernel (sm_100a).
 //
 // Same contract as kernels_pairwise.cu (getRobinsonFoulds / getWeightedRobinsonFoulds / getEuclideanDistance of
 // treeCl/treedist.py:111-114 for all pairs of a row range), split into a sparse and a dense part:
 //
-//   1. events.  A pair (i, j) has a common split d  <=>  i and j both appear in the POSTINGS of d (the encoder groups the
-//      shared-list entries by split, trees ascending).  pair_postings_kernel walks the postings with one warp per entry x = (d, i):
-//      every later entry (d, j) of the same group is one EVENT of pair (i, j) carrying the corrections
-//          cnt += 1,   E2 += -2 la lb,   E1 += |la - lb| - |la| - |lb|.
-//      Work is proportional to the number of events (sum over pairs of their common splits), no searching at all.  Events are
-//      binned by 64 x 32 tile with a counting sort: count pass (atomicAdd per tile), exclusive scan, fill pass.
-//   2. tiles.  pair_dense_kernel, one CTA per tile: the tile's events are applied to per-cell slots in shared memory, the leaf
-//      edges go through the fp64 tensor cores in the dot-product form
+//   1. events (pair_events_kernel).  A pair (i, j) has a common split d  <=>  i and j both appear in the POSTINGS of d (the encoder
+//      groups the shared-list entries by split, trees ascending).  Every later holder j of a split of tree i is one EVENT of pair
+//      (i, j) carrying the corrections   cnt += 1,   E2 += -2 la lb,   E1 += |la - lb| - |la| - |lb|.
+//      Work is proportional to the number of events, no searching at all.  One CTA per group of 16 row trees bins its events by
+//      64 x 32 tile with a shared-memory counting sort and claims one contiguous range of the event buffer.
+//   2. tiles (pair_dense_kernel), one CTA per tile: the tile's events are accumulated into per-cell slots in shared memory (64-bit
+//      fixed point relative to the cell's magnitude: integer adds commute, so the result does not depend on the event order), the
+//      leaf edges go through the fp64 tensor cores in the dot-product form
 //          euc^2 = (Q2_i + Q2_j) - 2 sum_k a_k b_k + E2           (Q2 = sum of squares of ALL edge lengths of a tree)
 //      (DMMA m8n8k4: the same 37 TFLOP/s as DFMA but 1/8 of the issue slots, and one FMA per term instead of DADD + DFMA),
 //      wrf keeps the direct form sum_k |a_k - b_k| on the fp64 pipe, and the epilogue leaves through shared memory so that every
 //      warp writes whole 256-byte row segments of the condensed matrix.
-// (Q + E) subtracts; cells whose correction nearly cancels Q, or that received >= 3 events (the order of >= 3 shared-memory
-// atomic adds is not fixed), are queued for exact_fixup_kernel, which recomputes them additively in a fixed order: results are
-// bit-reproducible, independent of the row sharding, and identical trees give exactly 0.
+//   Hybrid form: the matrix behind the tile kernel's TMA descriptors may carry, below the taxon rows, one row per HEAVY shared split
+//   (the splits held by the most trees, PairParams::heavy_rows of them, chosen by the encoder's cost model; build_split_rows_kernel).
+//   Their products are then part of the dot product (their |la - lb| of the L1 sum), the events kernel skips them, and rf comes from
+//   the incidence contraction.  With ALL shared splits as rows no events are needed at all (the split-extended form of api.cu).
+// (Q + E) subtracts; cells whose correction nearly cancels Q are queued for exact_fixup_kernel, which recomputes them additively in a
+// fixed order: results are bit-reproducible, independent of the row sharding, and identical trees give exactly 0.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
