@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, '/root/repo')
 import torch
 from treecl_b200 import _lib, synth
-n, taxa = 5000, 50
+n, taxa = (int(sys.argv[1]) if len(sys.argv) > 1 else 5000), (int(sys.argv[2]) if len(sys.argv) > 2 else 50)
 trees = synth.structured_trees(n, taxa, n_classes=64, class_nni=10, lam=3.0, seed=7)
 ts = _lib.TreeSet(trees); ts.upload(0)
 pairs = n * (n - 1) // 2

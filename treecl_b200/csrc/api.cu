@@ -524,7 +524,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         // events the postings pipeline can generate at most: all (pair, common split) incidences, minus those of the heavy rows in its hybrid form
         const int64_t ev_capacity = std::max<int64_t>(h.total_common - (hybrid_applies(h, d, m3, rect) ? h.heavy_events : 0), 1);
-        const bool split_fits = join_fits && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
+        const bool split_fits = h.max_shared <= 255 && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
                                 && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         // Kernel choice by a cost model in picoseconds per pair, calibrated on one B200 (tools/kernel_choice.py, tools/rf_dense_sharing.py):
         //   postings pipeline      11 + 13.4 x (expected common splits per pair): work follows the events; in its hybrid form the
@@ -548,7 +548,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (force) {                                                                // a forced kernel that cannot run falls back to the merge kernel
             kernel = K_MERGE;
             if (!strcmp(force, "merge")) kernel = K_MERGE;
-            else if (!strcmp(force, "split") && join_fits) kernel = split_fits ? K_SPLIT : K_JOIN;
+            else if (!strcmp(force, "split") && (split_fits || join_fits)) kernel = split_fits ? K_SPLIT : K_JOIN;
             else if ((!strcmp(force, "join") || !strcmp(force, "join_tile")) && join_fits) kernel = K_JOIN;
             else if (!strcmp(force, "incidence")) kernel = inc_ok ? K_INC : K_MERGE;
             else if (!strcmp(force, "extended")) kernel = (!rect && split_rows_fit(h, d) && (m3 & 6u)) ? K_EXT : (inc_ok ? K_INC : K_MERGE);
