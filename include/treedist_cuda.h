@@ -65,6 +65,10 @@ typedef struct {
     int64_t total_splits;
     int32_t device;          /* device the set is resident on, -1 if not uploaded                            */
     int32_t n_postings;      /* entries of the shared-split postings (= sum over trees of their shared-list lengths)      */
+    int32_t heavy_rows;      /* shared splits (by descending multiplicity) the hybrid tile kernel takes as matrix rows     */
+    int32_t reserved;
+    double mean_common;      /* expected number of common splits of a random pair of the set                              */
+    double heavy_common;     /* ... of which the heavy rows cover                                                          */
 } td_info;
 
 /* ---- host side: split encoder ------------------------------------------------------------------------ */

@@ -230,3 +230,15 @@ def test_postings_cover_exactly_the_shared_entries(lib_built):
     assert inf.dict_size == uniq.size
     assert inf.dict_shared == int((counts >= 2).sum())
     assert inf.n_postings == int(counts[counts >= 2].sum())
+
+
+def test_heavy_rows_follow_the_sharing_level(lib_built):
+    """The encoder's choice for the hybrid tile kernel: no heavy rows for independent random trees (nothing is shared by many trees),
+    a few rows that cover almost all common splits for a clustered set."""
+    from treecl_b200 import _lib, synth
+    sparse = _lib.TreeSet(synth.uniform_trees(1500, 40, seed=3)).info
+    assert sparse.heavy_rows == 0 and sparse.heavy_common == 0.0 and 0.0 < sparse.mean_common < 1.0
+    dense = _lib.TreeSet(synth.structured_trees(1500, 40, n_classes=8, class_nni=6, lam=2.0, seed=4)).info
+    assert dense.mean_common > 10.0
+    assert 0 < dense.heavy_rows <= dense.dict_shared
+    assert 0.9 * dense.mean_common <= dense.heavy_common <= dense.mean_common + 1e-9

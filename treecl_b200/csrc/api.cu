@@ -681,6 +681,7 @@ int td_treeset_info(const td_treeset *ts, td_info *info)
     info->n_trees = h.N; info->n_taxa = h.n_taxa; info->words = h.W; info->max_splits = h.max_splits; info->max_shared = h.max_shared;
     info->uniform = h.uniform; info->rooted = h.rooted; info->dict_size = h.dict_size; info->dict_shared = h.dict_shared;
     info->total_splits = h.total_splits; info->device = -1; info->n_postings = (int32_t)h.post_tree.size();
+    info->heavy_rows = h.heavy_rows; info->mean_common = h.mean_common; info->heavy_common = h.heavy_common;
     for (DeviceSet *d : ts->devs) if (d) { info->device = d->device; break; }
     return TD_OK;
 }
