@@ -138,6 +138,17 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
                        double overlap_fail_value, int64_t row_begin, int64_t row_end, void *const d_out[4],
                        void *stream);
 
+/* The kernels cannot return a status: a pair that compares a rooted with an unrooted tree (undefined in the reference) or a
+ * geodesic pair that hits the iteration cap leaves NaN in the output and raises a sticky flag on the resident set.  td_pairwise
+ * reads it itself; after the asynchronous entry points (td_pairwise_device, td_pairwise_rect_device) call td_check_errors once the
+ * stream has been synchronised: it returns TD_ERR_MIXED_ROOTING / TD_ERR_CUDA and clears the flag (one flag per set and GPU, shared by
+ * all launches in flight on it). */
+int td_check_errors(td_treeset *ts, int device);
+
+/* The library caches freed device blocks per GPU (cudaMalloc / cudaFree cost milliseconds): at most TREEDIST_CACHE_BYTES
+ * (environment, default 4 GiB) per device.  td_trim_cache gives the cache of `device` (-1: all) back to the driver. */
+int td_trim_cache(int device);
+
 /* Same, end to end with HOST output buffers: uploads the set if needed, runs the kernels, and streams the
  * condensed result(s) into out[metric] (host pointers, pinned or pageable).  Synchronous. */
 int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,

@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-__all__ = ['build', 'pair', 'matrix', 'matrix_range', 'prune_newick', 'encode_summary', 'stats', 'stats_reset', 'kc_pair', 'kc_vector', 'kc_matrix',
+__all__ = ['build', 'pair', 'matrix', 'matrix_range', 'matrix_rows', 'prune_newick', 'encode_summary', 'stats', 'stats_reset', 'kc_pair', 'kc_vector', 'kc_matrix',
            'METRICS', 'OracleError']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +44,8 @@ def _load():
         lib.orc_matrix_range.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
+        lib.orc_matrix_rows.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.orc_prune_newick.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
                                          ctypes.c_char_p, ctypes.c_size_t]
         lib.orc_encode_summary.argtypes = [ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3 + \
@@ -90,6 +92,17 @@ def matrix(newicks, metric, normalise=False, min_overlap=4, overlap_fail_value=0
     n = len(newicks)
     return matrix_range(newicks, metric, 0, n * (n - 1) // 2, normalise, min_overlap, overlap_fail_value,
                         nthreads, reparse_per_pair)
+
+
+def matrix_rows(newicks, metric, rows, normalise=False, min_overlap=4, overlap_fail_value=0.0, nthreads=1):
+    """Rows `rows` of the SQUARE matrix, shape (len(rows), n): spot checks of matrices too large for matrix()."""
+    n = len(newicks)
+    arr = (ctypes.c_char_p * n)(*[_b(s) for s in newicks])
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    out = np.zeros((rows.size, n), dtype=np.float64)
+    _check(_load().orc_matrix_rows(arr, n, METRICS[metric], int(bool(normalise)), int(min_overlap), float(overlap_fail_value),
+                                   int(nthreads), rows.ctypes.data, int(rows.size), out.ctypes.data))
+    return out
 
 
 def prune_newick(nwk, keep):

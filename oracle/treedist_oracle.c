@@ -808,6 +808,86 @@ int orc_matrix_range(const char *const *nwk, int n, int metric, int normalise, i
     return rc;
 }
 
+/* Selected rows of the SQUARE matrix: out[k * n + j] = d(tree rows[k], tree j) for every j (0 on the diagonal), trees parsed once
+ * and in parallel.  For spot checks of matrices too large for orc_matrix (random rows across the whole triangle). */
+typedef struct { job_t *J; const long *rows; int n_rows; long next; int phase; } rows_job_t;
+
+static void *rows_worker(void *arg)
+{
+    rows_job_t *R = (rows_job_t *)arg; job_t *J = R->J;
+    for (;;) {
+        long w = __sync_fetch_and_add(&R->next, 1);
+        if (J->rc) break;
+        if (R->phase == 0) {                               /* parse tree w */
+            if (w >= J->n) break;
+            int rc = parse_full(J->nwk[w], &J->trees[w]);
+            if (rc) { if (!__sync_lock_test_and_set(&J->rc, rc)) memcpy(J->err, g_err, sizeof J->err); break; }
+        } else if (R->phase == 1) {                        /* encode tree w over the shared taxon table (kept in J->out as a pointer) */
+            if (w >= J->n) break;
+            char **l0; int n0 = sorted_labels(&J->trees[0], &l0);
+            int rc = tree_encode(&J->trees[w], l0, n0, &J->encs[w]);
+            free(l0);
+            if (rc) { if (!__sync_lock_test_and_set(&J->rc, rc)) memcpy(J->err, g_err, sizeof J->err); break; }
+        } else {                                           /* 64 columns of one requested row */
+            const long chunks = ((long)J->n + 63) / 64;
+            if (w >= chunks * R->n_rows) break;
+            const long k = w / chunks, j0 = (w % chunks) * 64, i = R->rows[k];
+            for (long j = j0; j < j0 + 64 && j < J->n; j++) {
+                double d = 0; int rc = ORC_OK;
+                if (j != i) {
+                    const long a = i < j ? i : j, b = i < j ? j : i;
+                    if (J->all_same) rc = enc_distance(&J->encs[a], &J->encs[b], J->metric, J->normalise, &d);
+                    else rc = pair_trees(&J->trees[a], &J->trees[b], J->metric, J->normalise, J->min_overlap, J->fail, &d);
+                }
+                if (rc) { if (!__sync_lock_test_and_set(&J->rc, rc)) memcpy(J->err, g_err, sizeof J->err); break; }
+                J->out[k * (long)J->n + j] = d;
+            }
+        }
+    }
+    return NULL;
+}
+
+static void rows_run(rows_job_t *R, int phase, int nthreads)
+{
+    R->phase = phase; R->next = 0;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, rows_worker, R);
+    rows_worker(R);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
+}
+
+int orc_matrix_rows(const char *const *nwk, int n, int metric, int normalise, int min_overlap, double fail, int nthreads,
+                    const long *rows, int n_rows, double *out)
+{
+    if (metric < 0 || metric > 3) FAIL(ORC_EARG, "unknown metric %d", metric);
+    for (int k = 0; k < n_rows; k++) if (rows[k] < 0 || rows[k] >= n) FAIL(ORC_EARG, "row %ld outside [0,%d)", rows[k], n);
+    if (nthreads < 1) nthreads = 1;
+    job_t J; memset(&J, 0, sizeof J);
+    J.nwk = nwk; J.n = n; J.metric = metric; J.normalise = normalise; J.min_overlap = min_overlap; J.fail = fail; J.out = out;
+    J.trees = (tree_t *)calloc(n, sizeof(tree_t));
+    rows_job_t R; memset(&R, 0, sizeof R); R.J = &J; R.rows = rows; R.n_rows = n_rows;
+    rows_run(&R, 0, nthreads);
+    if (!J.rc) {
+        char **l0; int n0 = sorted_labels(&J.trees[0], &l0); J.all_same = 1;
+        for (int i = 1; i < n && J.all_same; i++) {
+            char **li; int ni = sorted_labels(&J.trees[i], &li);
+            if (ni != n0) J.all_same = 0;
+            for (int k = 0; J.all_same && k < n0; k++) if (strcmp(l0[k], li[k])) J.all_same = 0;
+            free(li);
+        }
+        free(l0);
+        if (J.all_same) { J.encs = (enc_t *)calloc(n, sizeof(enc_t)); rows_run(&R, 1, nthreads); }
+    }
+    if (!J.rc) rows_run(&R, 2, nthreads);
+    int rc = J.rc;
+    if (rc) memcpy(g_err, J.err, sizeof g_err);
+    if (J.encs) { for (int i = 0; i < n; i++) enc_free(&J.encs[i]); free(J.encs); }
+    for (int i = 0; i < n; i++) tree_free(&J.trees[i]);
+    free(J.trees);
+    return rc;
+}
+
 int orc_matrix(const char *const *nwk, int n, int metric, int normalise, int min_overlap, double fail,
                int nthreads, int reparse_per_pair, double *condensed)
 {

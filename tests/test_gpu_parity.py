@@ -21,6 +21,26 @@ def assert_close(got, want, rtol=RTOL, atol=1e-12):
     assert not bad.any(), 'max rel err {:.3e} at {}'.format((err / np.maximum(np.abs(want), 1e-300)).max(), np.argmax(err))
 
 
+def condensed_index(n, i, j):
+    """scipy-condensed position of the pair (i, j), i != j (vectorised)."""
+    i, j = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64)
+    a, b = np.minimum(i, j), np.maximum(i, j)
+    return a * n - a * (a + 1) // 2 + (b - a - 1)
+
+
+def square_rows(cond, n, rows):
+    """Rows `rows` of the square matrix behind the condensed vector `cond` (0 on the diagonal), shape (len(rows), n)."""
+    out = np.zeros((len(rows), n), dtype=np.float64)
+    cols = np.arange(n)
+    for k, r in enumerate(rows):
+        other = cols[cols != r]
+        out[k, other] = cond[condensed_index(n, r, other)]
+    return out
+
+
+NTHREADS = os.cpu_count() or 4
+
+
 @pytest.fixture(scope='module')
 def td():
     import treecl_b200
@@ -53,6 +73,15 @@ class TestTreeDistanceGoldens:
         dm = self.c.get_inter_tree_distances('rf', show_progress=False)
         assert dm.values[0, 1] == self.td.treedist.rfdist(self.tree1, self.tree2, False)
         assert dm.get_names() == self.c.names and dm.values.shape == (15, 15)
+        # the matrix path agrees with the scalar path for EVERY entry and every metric, not only [0, 1]
+        trees = [self.td.Tree(r.tree) for r in self.c]
+        for metric in ('rf', 'wrf', 'euc', 'geo'):
+            vals = self.c.get_inter_tree_distances(metric, show_progress=False).values
+            fn = getattr(self.td.treedist, metric + 'dist')
+            for i in range(15):
+                for j in range(i + 1, 15):
+                    want = fn(trees[i], trees[j], False)
+                    assert vals[i, j] == want if metric == 'rf' else vals[i, j] == pytest.approx(want, rel=1e-12), (metric, i, j)
         assert (dm.values == dm.values.T).all() and (np.diag(dm.values) == 0).all()
 
 
@@ -228,6 +257,56 @@ def test_mixed_rooting_is_refused(td):
         ts.pairwise(('rf',))
 
 
+def test_async_entry_points_surface_the_error_flag(td):
+    """td_pairwise_device cannot return what a kernel finds: the mixed-rooting flag is read with td_check_errors (and cleared)."""
+    import torch
+    from treecl_b200 import _lib
+    ts = _lib.TreeSet(['((A:1,B:1):1,(C:1,D:1):1);', '((A:1,B:1):1,C:1,D:1);', '((A:1,C:1):1,B:1,D:1);']).upload(0)
+    out = torch.zeros(3, dtype=torch.float64, device='cuda:0')
+    before = torch.cuda.current_device()
+    ts.pairwise_device(('rf',), {'rf': out.data_ptr()}, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.cuda.current_device() == before
+    with pytest.raises(ValueError):
+        ts.check_errors(0)
+    ts.check_errors(0)                                       # the flag was cleared by the read
+    ok = _lib.TreeSet(['((A:1,B:1):1,C:1,D:1);', '((A:1,C:1):1,B:1,D:1);']).upload(0)
+    ok.pairwise_device(('rf',), {'rf': out.data_ptr()}, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ok.check_errors(0)
+    assert out[0].item() == 2.0
+
+
+def test_first_rf_only_calls_race_on_two_streams(td, oracle_mod):
+    """The incidence matrix of the int8 tcgen05 path is built lazily by the first rf-only call: a second call on another stream must
+    not see it half built."""
+    import threading
+    import torch
+    from treecl_b200 import _lib
+    trees = make('structured', 600, 60, seed=11)
+    want = oracle_mod.matrix(trees, 'rf', nthreads=NTHREADS)
+    for _ in range(3):
+        ts = _lib.TreeSet(trees).upload(0)
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        outs = [torch.full((want.size,), -1.0, dtype=torch.float64, device='cuda:0') for _ in streams]
+        torch.cuda.synchronize()
+        go = threading.Barrier(2)
+
+        def work(k):
+            go.wait()
+            ts.pairwise_device(('rf',), {'rf': outs[k].data_ptr()}, stream=streams[k].cuda_stream)
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        for o in outs:
+            assert np.array_equal(o.cpu().numpy(), want)
+        ts.close()
+
+
 def test_polytomies_and_rooted_trees(td, oracle_mod):
     """UNPINNED by the reference (no golden): extended common-edge rule and clade (rooted) mode, oracle vs CUDA."""
     from treecl_b200 import _lib
@@ -279,25 +358,33 @@ def test_row_sharding_is_byte_identical(td, pair_kernel):
     assert np.array_equal(out['rf'], full['rf']) and np.array_equal(out['geo'], full['geo'])
 
 
-@pytest.mark.parametrize('pair_kernel', ['merge', 'join', 'split'], indirect=True)
-def test_rectangular_variant(td, pair_kernel):
-    """query x reference distances (treeCl/bootstrap.py:174-218) = a block of the square matrix."""
+@pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'split'], indirect=True)
+@pytest.mark.parametrize('kind', ['uniform', 'structured'])
+def test_rectangular_variant(td, oracle_mod, pair_kernel, kind):
+    """query x reference distances (treeCl/bootstrap.py:174-218) against the ORACLE's block of the square matrix,
+    geodesic included."""
     import torch
-    from treecl_b200 import _lib, synth
-    trees = synth.uniform_trees(150, 30, seed=33)
+    from treecl_b200 import _lib
+    trees = make(kind, 150, 30, seed=33)
     split = 70
     ts = _lib.TreeSet(trees).upload(0)
-    sq = {m: squareform(v) for m, v in ts.pairwise(('rf', 'wrf', 'euc', 'geo')).items()}
-    outs = {m: torch.zeros(split * (150 - split), dtype=torch.float64, device='cuda:0') for m in sq}
-    ts.pairwise_rect_device(split, tuple(sq), {m: outs[m].data_ptr() for m in sq},
+    metrics = ('rf', 'wrf', 'euc', 'geo')
+    outs = {m: torch.zeros(split * (150 - split), dtype=torch.float64, device='cuda:0') for m in metrics}
+    ts.pairwise_rect_device(split, metrics, {m: outs[m].data_ptr() for m in metrics},
                             stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    for m in sq:
-        assert np.array_equal(outs[m].cpu().numpy().reshape(split, 150 - split), sq[m][:split, split:]), m
+    for m in metrics:
+        want = squareform(oracle_mod.matrix(trees, m, nthreads=NTHREADS))[:split, split:]
+        got = outs[m].cpu().numpy().reshape(split, 150 - split)
+        if m == 'rf':
+            assert np.array_equal(got, want), m
+        else:
+            assert_close(got, want)
 
 
-def test_properties_at_bench_size(td):
-    """BASELINE config 2 (5,000 x 50): too big for the oracle, so check size-independent properties."""
+def test_baseline_config_2_full_vs_oracle(td, oracle_mod):
+    """BASELINE configs[1] = the bench workload (5,000 x 50, seed of bench.py): EVERY entry of the rf, euc and wrf matrices against
+    the oracle (12.5 M pairs per metric), plus the size-independent properties."""
     from treecl_b200 import _lib, synth
     n, taxa = 5000, 50
     trees = synth.uniform_trees(n, taxa, seed=0xCA55E77E + 1)
@@ -305,6 +392,12 @@ def test_properties_at_bench_size(td):
     got = ts.pairwise(('rf', 'euc', 'wrf'))
     rf, euc, wrf = got['rf'], got['euc'], got['wrf']
     assert rf.size == n * (n - 1) // 2
+    assert np.array_equal(rf, oracle_mod.matrix(trees, 'rf', nthreads=NTHREADS))
+    assert_close(euc, oracle_mod.matrix(trees, 'euc', nthreads=NTHREADS))
+    assert_close(wrf, oracle_mod.matrix(trees, 'wrf', nthreads=NTHREADS))
+    # the bench launch itself (rf + euc in one call) gives the same bytes
+    both = ts.pairwise(('rf', 'euc'))
+    assert np.array_equal(both['rf'], rf) and np.array_equal(both['euc'], euc)
     assert (rf == np.round(rf)).all() and (rf % 2 == 0).all() and rf.min() >= 0 and rf.max() <= 2 * (taxa - 3)
     assert (euc > 0).all() and (wrf >= euc).all()                   # L1 >= L2
     # order reversal: d(i,j) computed with the trees listed backwards is the same matrix transposed
@@ -312,27 +405,22 @@ def test_properties_at_bench_size(td):
     rev = ts_rev.pairwise(('rf', 'euc'))
     idx = np.random.default_rng(0).integers(0, n, size=(2000, 2))
     idx = idx[idx[:, 0] < idx[:, 1]]
-    p = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
-    fwd = p(idx[:, 0], idx[:, 1]); bwd = p(n - 1 - idx[:, 1], n - 1 - idx[:, 0])
+    fwd = condensed_index(n, idx[:, 0], idx[:, 1]); bwd = condensed_index(n, n - 1 - idx[:, 1], n - 1 - idx[:, 0])
     assert np.array_equal(rf[fwd], rev['rf'][bwd])
     assert_close(euc[fwd], rev['euc'][bwd], rtol=1e-12)
-    # a 300-tree sub-block agrees with the matrix of the sub-collection (dictionary ids differ between the two runs)
-    sub = _lib.TreeSet(trees[:300]).pairwise(('rf', 'euc'))
-    blk = np.concatenate([np.arange(p(i, i + 1), p(i, 299) + 1) for i in range(299)])
-    assert np.array_equal(sub['rf'], rf[blk])
-    assert_close(sub['euc'], euc[blk], rtol=1e-12)
 
 
 @pytest.mark.parametrize('kind,n_trees,n_taxa', [('structured', 300, 40), ('structured', 257, 100), ('structured', 130, 200),
                                                  ('uniform', 200, 20), ('uniform', 129, 64)])
-def test_rf_incidence_tcgen05(td, kind, n_trees, n_taxa):
-    """int8 tcgen05 contraction X * X^T over the shared-split dictionary: bit-identical to the join / merge RF."""
+def test_rf_incidence_tcgen05(td, oracle_mod, kind, n_trees, n_taxa):
+    """int8 tcgen05 contraction X * X^T over the shared-split dictionary (f64, u16 and row-shard forms): bit-identical to the ORACLE."""
     import torch
     from treecl_b200 import _lib
     trees = make(kind, n_trees, n_taxa, seed=900 + n_taxa)
     ts = _lib.TreeSet(trees)
-    want = ts.pairwise(('rf',))['rf']
-    want_n = ts.pairwise(('rf',), normalise=True)['rf']
+    want = oracle_mod.matrix(trees, 'rf', nthreads=NTHREADS)                 # never the library's own answer
+    want_n = oracle_mod.matrix(trees, 'rf', normalise=True, nthreads=NTHREADS)
+    assert np.array_equal(ts.pairwise(('rf',))['rf'], want) and np.array_equal(ts.pairwise(('rf',), normalise=True)['rf'], want_n)
     pairs = want.size
     st = torch.cuda.current_stream().cuda_stream
     out = torch.full((pairs,), -1.0, dtype=torch.float64, device='cuda:0')
@@ -373,40 +461,84 @@ def test_baseline_config_1_full(td, oracle_mod):
 
 
 def test_baseline_config_5_full_size(td, oracle_mod):
-    """BASELINE configs[4]: 2,000 random 30-taxon trees, geodesic.  Full matrix on the GPU; the oracle checks a slice
-    (first 30,000 pairs) and size-independent properties cover the rest."""
+    """BASELINE configs[4]: 2,000 random 30-taxon trees, geodesic: all 1,999,000 pairs against the oracle."""
     from treecl_b200 import _lib, synth
     n = 2000
     trees = synth.uniform_trees(n, 30, seed=0xCA55E77E + 4)
     ts = _lib.TreeSet(trees)
     got = ts.pairwise(('geo', 'euc'))
     geo, euc = got['geo'], got['euc']
-    want = oracle_mod.matrix_range(trees, 'geo', 0, 30000, nthreads=8)
-    assert_close(geo[:30000], want)
+    assert_close(geo, oracle_mod.matrix(trees, 'geo', nthreads=NTHREADS))
     assert np.isfinite(geo).all() and (geo >= euc * (1 - 1e-12)).all()          # the geodesic is never shorter than the chord
     st = ts.geo_stats()
     assert st['pairs'] == n * (n - 1) // 2 and 2.0 < st['ratios'] / st['pairs'] < 4.0
     # order reversal gives the transposed matrix
     rev = _lib.TreeSet(trees[::-1]).pairwise(('geo',))['geo']
     idx = np.random.default_rng(1).integers(0, n, size=(3000, 2)); idx = idx[idx[:, 0] < idx[:, 1]]
-    p = lambda i, j: i * n - i * (i + 1) // 2 + (j - i - 1)
-    assert_close(geo[p(idx[:, 0], idx[:, 1])], rev[p(n - 1 - idx[:, 1], n - 1 - idx[:, 0])], rtol=1e-10)
+    assert_close(geo[condensed_index(n, idx[:, 0], idx[:, 1])], rev[condensed_index(n, n - 1 - idx[:, 1], n - 1 - idx[:, 0])], rtol=1e-10)
 
 
-def test_baseline_config_3_properties(td, oracle_mod):
-    """BASELINE configs[2] shape (100 taxa, wrf + euc) at a size the test suite can generate quickly (3,000 trees);
-    the oracle checks a slice, sharding and order reversal cover the rest.  The full 20,000-tree set is run by
-    `bench.py --config 2`."""
+def test_baseline_config_3_full_size(td, oracle_mod):
+    """BASELINE configs[2] at its own size: 20,000 random 100-taxon trees, wrf + euc (200 M pairs per metric).  The oracle checks
+    128 random rows of the SQUARE matrix (2.56 M pairs per metric, spread over the whole triangle); 8-way row sharding must give
+    the same bytes."""
     from treecl_b200 import _lib, engine, synth
-    n = 3000
-    trees = synth.uniform_trees(n, 100, seed=0xCA55E77E + 2)
-    ts = _lib.TreeSet(trees)
+    n = 20000
+    g = synth.baseline_config(2)
+    trees = g.strings()
+    ts = g.treeset()
     got = ts.pairwise(('wrf', 'euc'))
+    rows = np.sort(np.random.default_rng(3).choice(n, size=128, replace=False))
     for m in ('wrf', 'euc'):
-        assert_close(got[m][:20000], oracle_mod.matrix_range(trees, m, 0, 20000, nthreads=8))
+        assert_close(square_rows(got[m], n, rows), oracle_mod.matrix_rows(trees, m, rows, nthreads=NTHREADS))
     assert (got['wrf'] >= got['euc']).all()
     parts = [ts.pairwise(('wrf',), row_begin=a, row_end=b)['wrf'] for a, b in engine.balanced_row_ranges(n, 8)]
     assert np.array_equal(np.concatenate(parts), got['wrf'])
+
+
+def test_baseline_config_4_shape(td, oracle_mod):
+    """BASELINE configs[3] at its own size: 100,000 clustered 200-taxon trees, RF through the int8 tcgen05 split-incidence
+    contraction.  u16: the FULL condensed matrix (5 G pairs, 10 GB) on the device; f64: a band of rows through td_pairwise (whose
+    choice for rf alone is the same kernel) and through td_rf_incidence_device.  The oracle checks 24 random rows of the square
+    matrix (2.4 M pairs) of the u16 matrix, and the band in f64."""
+    import torch
+    from treecl_b200 import _lib, synth
+    n = 100000
+    g = synth.baseline_config(3)
+    ts = g.treeset().upload(0)
+    assert ts.info.uniform == 1 and ts.info.max_splits == 197
+    st = torch.cuda.current_stream().cuda_stream
+    pairs = n * (n - 1) // 2
+    out16 = torch.zeros(pairs, dtype=torch.int16, device='cuda:0')
+    ts.rf_incidence_device(out16.data_ptr(), out_is_u16=True, stream=st)
+    torch.cuda.synchronize()
+    rows = np.sort(np.random.default_rng(4).choice(n, size=24, replace=False))
+    r0 = int(rows[11])
+    rows = np.concatenate([rows, np.arange(r0, r0 + 8)])                       # + the band [r0, r0 + 8) for the f64 forms
+    trees = g.strings()
+    want = oracle_mod.matrix_rows(trees, 'rf', rows, nthreads=NTHREADS)
+    del trees
+    cols = torch.arange(n, device='cuda:0')
+    for k, r in enumerate(rows[:24]):
+        other = cols[cols != int(r)]
+        a, b = torch.clamp(other, max=int(r)), torch.clamp(other, min=int(r))
+        idx = a * n - a * (a + 1) // 2 + (b - a - 1)
+        got = out16[idx].cpu().numpy().astype(np.float64)
+        assert np.array_equal(got, np.delete(want[k], int(r))), int(r)
+    # f64 band, both entry points
+    p0, p1 = _lib.condensed_offset(n, r0), _lib.condensed_offset(n, r0 + 8)
+    band = torch.zeros(p1 - p0, dtype=torch.float64, device='cuda:0')
+    ts.rf_incidence_device(band.data_ptr(), row_begin=r0, row_end=r0 + 8, stream=st)
+    torch.cuda.synchronize()
+    host = ts.pairwise(('rf',), row_begin=r0, row_end=r0 + 8)['rf']
+    at = 0
+    for k in range(8):
+        i = r0 + k
+        w = want[24 + k, i + 1:]
+        assert np.array_equal(band[at:at + w.size].cpu().numpy(), w) and np.array_equal(host[at:at + w.size], w), i
+        assert np.array_equal(out16[p0 + at:p0 + at + w.size].cpu().numpy().astype(np.float64), w)
+        at += w.size
+    assert at == p1 - p0
 
 
 def test_concurrent_launches_on_one_set_share_the_event_buffer_safely(td, monkeypatch):

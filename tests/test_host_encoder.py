@@ -11,9 +11,13 @@ from conftest import GOLDEN, ROOT
 
 
 def test_every_declared_symbol_is_exported(lib_built):
-    header = open(os.path.join(ROOT, 'include', 'treedist_cuda.h')).read()
-    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
-    declared = set(re.findall(r'\b(td_[a-z0-9_]+)\s*\(', header))
+    declared = set()
+    inc = os.path.join(ROOT, 'include')
+    for name in sorted(os.listdir(inc)):
+        if name.endswith('.h'):
+            header = re.sub(r'/\*.*?\*/', '', open(os.path.join(inc, name)).read(), flags=re.S)
+            declared |= set(re.findall(r'\b(td_[a-z0-9_]+)\s*\(', header))
+    assert {'td_synth_trees', 'td_check_errors', 'td_trim_cache'} <= declared
     assert {'td_encode_newick', 'td_upload', 'td_pairwise', 'td_pairwise_device', 'td_last_error'} <= declared
     lib = ctypes.CDLL(lib_built)
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
@@ -107,7 +111,8 @@ def test_non_uniform_sets_are_flagged(lib_built):
     assert [bin(int(x)).count('1') for x in lm] == [5, 5]
 
 
-@pytest.mark.parametrize('bad', ['', 'A;', '((A,B),C', '(A,B))', '(A,,B);', "('A,B);", '(A:x,B:1);', '(A,A,B);'])
+@pytest.mark.parametrize('bad', ['', 'A;', '((A,B),C', '(A,B))', '(A,,B);', "('A,B);", '(A:x,B:1);', '(A,A,B);',
+                                 '(A:nan,B:1,C:1);', '(A:inf,B:1,C:1);', '(A:-inf,B:1,C:1);', '((C:1,D:1):1:2,A:1,B:1);', '(A:1:2,B:1,C:1);'])
 def test_parse_errors_are_value_errors(lib_built, bad):
     from treecl_b200 import _lib
     with pytest.raises(ValueError):
@@ -173,6 +178,35 @@ def test_synthetic_sets_are_deterministic(lib_built):
     assert list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [17] * 6      # binary, trifurcating root: n-3
     s = _lib.TreeSet(synth.structured_trees(64, 30, n_classes=4, lam=0.5, seed=1))
     assert s.info.dict_size < 64 * 27 // 4            # shared structure -> small dictionary
+
+
+def test_native_generator(lib_built, oracle_mod):
+    """csrc/synth.cpp: deterministic, independent of the set size and of the thread count, binary trees of the requested shape."""
+    from treecl_b200 import _lib, synth
+    a = synth.native_trees(200, 30, 'uniform', seed=7, n_threads=1)
+    b = synth.native_trees(300, 30, 'uniform', seed=7, n_threads=4)
+    assert a == b[:200] and a != synth.native_trees(200, 30, 'uniform', seed=8)
+    ts = _lib.TreeSet(a)
+    assert ts.info.uniform == 1 and list(ts.get(_lib.TD_GET_NSPLITS, np.int32)) == [27] * 200 and ts.info.n_taxa == 30
+    assert ts.get(_lib.TD_GET_LABELS, None) == synth.taxon_labels(30)
+    g = synth.NativeTrees(256, 40, 'structured', seed=2, n_classes=4, class_nni=6, lam=1.0)
+    s = g.treeset()
+    assert s.n_trees == 256 and s.info.uniform == 1 and s.info.dict_size < 256 * 37 // 4      # shared structure -> small dictionary
+    assert g.strings() == synth.native_trees(256, 40, 'structured', seed=2, n_classes=4, class_nni=6, lam=1.0)
+    # mean RF of independent uniform trees is close to its maximum; the oracle reads the generator's Newick
+    rf = oracle_mod.matrix(a[:40], 'rf')
+    assert rf.mean() > 2 * 27 * 0.9
+    g.close()
+
+
+def test_oracle_matrix_rows_agree_with_the_condensed_matrix(oracle_mod):
+    from scipy.spatial.distance import squareform
+    from treecl_b200 import synth
+    trees = synth.structured_trees(60, 16, n_classes=3, class_nni=3, lam=1.0, seed=4)
+    rows = [0, 7, 59, 31]
+    for m in ('rf', 'wrf', 'euc', 'geo'):
+        sq = squareform(oracle_mod.matrix(trees, m, nthreads=2))
+        assert np.array_equal(oracle_mod.matrix_rows(trees, m, rows, nthreads=3), sq[rows]), m
 
 
 def test_marshalling_paths_build_the_same_set(lib_built, monkeypatch):

@@ -79,6 +79,11 @@ def load():
     lib.td_pairwise_rect_device.argtypes = [vp, i64, u32, i32, _c_void_p4, vp]
     lib.td_rf_incidence_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     lib.td_geo_get_stats.argtypes = [vp, ctypes.POINTER(td_geo_stats)]
+    lib.td_check_errors.argtypes = [vp, i32]
+    lib.td_trim_cache.argtypes = [i32]
+    lib.td_synth_trees.argtypes = [i32, i64, i32, ctypes.c_uint64, i32, i32, dbl, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.td_synth_free.argtypes = [vp]
+    lib.td_synth_free.restype = None
     _lib = lib
     return lib
 
@@ -151,6 +156,17 @@ class TreeSet(object):
         self._h = handle
         self._lib = lib
         self.n_trees = len(newicks)
+
+    @classmethod
+    def from_joined(cls, buffer, total_bytes, n_trees, n_threads=0):
+        """Encode n_trees NUL-terminated Newick strings stored back to back (bytes object or an address + size)."""
+        lib = load()
+        handle = ctypes.c_void_p()
+        src = buffer if isinstance(buffer, (bytes, bytearray)) else ctypes.cast(ctypes.c_void_p(buffer), ctypes.c_char_p)
+        check(lib.td_encode_newick_joined(src, int(total_bytes), int(n_trees), int(n_threads), ctypes.byref(handle)))
+        self = cls.__new__(cls)
+        self._h, self._lib, self.n_trees = handle, lib, int(n_trees)
+        return self
 
     @classmethod
     def kendall_colijn(cls, newicks, lbda=0.5, n_threads=0):
@@ -240,6 +256,11 @@ class TreeSet(object):
                                     int(row_begin), int(row_end), _c_void_p4(*table), int(device)))
         return res
 
+    def check_errors(self, device=0):
+        """After pairwise_device / pairwise_rect_device and a stream synchronise: raises if a launch flagged an error (mixed rooting,
+        geodesic iteration cap); clears the flag."""
+        check(self._lib.td_check_errors(self._h, int(device)))
+
     def geo_stats(self):
         st = td_geo_stats()
         check(self._lib.td_geo_get_stats(self._h, ctypes.byref(st)))
@@ -271,6 +292,10 @@ def device_count():
     c = ctypes.c_int()
     load().td_device_count(ctypes.byref(c))
     return c.value
+
+
+def trim_cache(device=-1):
+    check(load().td_trim_cache(int(device)))
 
 
 def launch_count():

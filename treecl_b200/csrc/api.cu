@@ -24,7 +24,16 @@ struct BlockPool {
     size_t cached = 0;
 };
 static BlockPool g_pools[64];
-constexpr size_t kPoolLimit = 24ull << 30;        // bytes kept per device before blocks really go back to the driver
+// bytes kept per device before blocks really go back to the driver: TREEDIST_CACHE_BYTES, default 4 GiB (td_trim_cache() empties it)
+static size_t pool_limit()
+{
+    static const size_t v = [] {
+        const char *e = getenv("TREEDIST_CACHE_BYTES");
+        if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 10); if (end != e) return (size_t)x; }
+        return (size_t)(4ull << 30);
+    }();
+    return v;
+}
 
 static cudaError_t pool_alloc(int device, size_t bytes, void **out, size_t *got)
 {
@@ -55,12 +64,20 @@ static cudaError_t pool_alloc(int device, size_t bytes, void **out, size_t *got)
     return e;
 }
 
+static void pool_trim(int device)
+{
+    BlockPool &P = g_pools[device & 63];
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto &b : P.free_blocks) cudaFree(b.second);
+    P.free_blocks.clear(); P.cached = 0;
+}
+
 static void pool_free(int device, void *p, size_t bytes)
 {
     if (!p) return;
     BlockPool &P = g_pools[device & 63];
     std::lock_guard<std::mutex> g(P.mu);
-    if (P.cached + bytes > kPoolLimit) { cudaFree(p); return; }
+    if (P.cached + bytes > pool_limit()) { cudaFree(p); return; }
     P.free_blocks.emplace_back(bytes, p); P.cached += bytes;
 }
 
@@ -143,8 +160,11 @@ static void free_device(DeviceSet *d)
     if (!d) return;
     int cur = -1; cudaGetDevice(&cur);
     if (d->device >= 0) cudaSetDevice(d->device);
+    // launches on any stream may still read or write the set's memory: nothing goes back to the pool (where another thread could be
+    // handed it) before the device has drained
+    if (d->device >= 0) cudaDeviceSynchronize();
     for (auto &b : d->allocs) pool_free(d->device, b.second, b.first);
-    if (d->ev_done) { cudaEventSynchronize(d->ev_done); cudaEventDestroy(d->ev_done); }
+    if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev_block) pool_free(d->device, d->ev_block, d->ev_block_got);
     if (cur >= 0) cudaSetDevice(cur);
     delete d;
@@ -424,6 +444,7 @@ static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t
             launch_counter_add(1);
             cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap);
             if (e != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+            CUDA_TRY(cudaStreamSynchronize(st));              // other streams may use the matrix from now on (as for leafH / leafX)
             d->X = X; d->d_pad = d_pad; d->rows_x = rows;
         }
     }
@@ -620,6 +641,27 @@ geodesic:
 
 using namespace td;
 
+namespace {
+// the entry points select the set's GPU; the caller's current device is put back on the way out
+struct DeviceScope {
+    int saved = -1;
+    DeviceScope() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; cudaGetLastError(); } }
+    ~DeviceScope() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
+// reads and clears the sticky error flag of a resident set (the caller has synchronised the launches it asks about)
+int take_error_flag(DeviceSet *d)
+{
+    int flag = 0;
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaMemcpy(&flag, d->error_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) CUDA_TRY(cudaMemset(d->error_flag, 0, sizeof flag));
+    if (flag & 2) { set_error("cannot compare a rooted with an unrooted tree (undefined in the reference as well)"); return TD_ERR_MIXED_ROOTING; }
+    if (flag & 1) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
+    return TD_OK;
+}
+}  // namespace
+
 extern "C" {
 
 const char *td_last_error(void) { return last_error(); }
@@ -669,6 +711,7 @@ int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_t
 void td_treeset_free(td_treeset *ts)
 {
     if (!ts) return;
+    DeviceScope scope;
     for (DeviceSet *d : ts->devs) free_device(d);
     delete ts;
 }
@@ -742,6 +785,7 @@ int td_device_count(int *count)
 int td_upload(td_treeset *ts, int device, void *stream)
 {
     if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    DeviceScope scope;
     return upload(ts, device, (cudaStream_t)stream);
 }
 
@@ -751,6 +795,7 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
                        int64_t row_begin, int64_t row_end, void *const d_out[4], void *stream)
 {
     if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    DeviceScope scope;
     const int64_t N = ts->host.N;
     if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
     if (row_begin < 0 || row_end > N || row_begin > row_end) { set_error("row range [%lld,%lld) outside [0,%lld]", (long long)row_begin, (long long)row_end, (long long)N); return TD_ERR_ARG; }
@@ -764,6 +809,7 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
 int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4], void *stream)
 {
     if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    DeviceScope scope;
     const int64_t N = ts->host.N;
     if (split <= 0 || split >= N) { set_error("split %lld must be inside (0,%lld)", (long long)split, (long long)N); return TD_ERR_ARG; }
     if (!(metric_mask & 15u) || (metric_mask & ~15u) || !d_out) { set_error("bad metric_mask / output table"); return TD_ERR_ARG; }
@@ -777,6 +823,7 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
                 int64_t row_begin, int64_t row_end, double *const out[4], int device)
 {
     if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    DeviceScope scope;
     int rc;
     if ((rc = upload(ts, device, 0))) return rc;        // no-op when already resident
     DeviceSet *dset = resident(ts, device);
@@ -803,11 +850,27 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
-    {
-        int flag = 0; cudaMemcpy(&flag, dset->error_flag, sizeof flag, cudaMemcpyDeviceToHost);
-        if (flag) cudaMemset(dset->error_flag, 0, sizeof flag);
-        if (flag & 2) { set_error("cannot compare a rooted with an unrooted tree (undefined in the reference as well)"); return TD_ERR_MIXED_ROOTING; }
-        if (flag & 1) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
+    return take_error_flag(dset);
+}
+
+int td_check_errors(td_treeset *ts, int device)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    DeviceScope scope;
+    DeviceSet *d; int rc;
+    if ((rc = check_ready(ts, device, &d))) return rc;
+    return take_error_flag(d);
+}
+
+int td_trim_cache(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return TD_OK; }      // no GPU: nothing is cached
+    DeviceScope scope;
+    for (int dev = 0; dev < count && dev < 64; dev++) {
+        if (device >= 0 && dev != device) continue;
+        if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        pool_trim(dev);
     }
     return TD_OK;
 }
@@ -815,6 +878,7 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
 int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16, void *stream)
 {
     if (!ts || !d_out) { set_error("null argument"); return TD_ERR_ARG; }
+    DeviceScope scope;
     const HostSet &h = ts->host;
     if (!h.uniform) { set_error("the incidence path needs one shared leaf set"); return TD_ERR_UNSUPPORTED; }
     if (row_begin < 0 || row_end > h.N || row_begin > row_end) { set_error("row range outside [0,N]"); return TD_ERR_ARG; }

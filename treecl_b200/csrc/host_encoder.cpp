@@ -95,7 +95,7 @@ static int parse_newick(const char *text, FlatTree &t)
 {
     t.clear();
     const char *s = text, *e = text + strlen(text);
-    int cur = t.add(-1), depth = 0; bool want_subtree = true;
+    int cur = t.add(-1), depth = 0; bool want_subtree = true, have_len = false;
     s = skip_blank(s, e);
     if (s >= e || *s != '(') { set_error("newick: expected '(' at start"); return TD_ERR_PARSE; }
     while (s < e) {
@@ -103,7 +103,7 @@ static int parse_newick(const char *text, FlatTree &t)
         if (s >= e) break;
         char c = *s;
         if (want_subtree) {
-            if (c == '(') { depth++; cur = t.add(cur); s++; continue; }
+            if (c == '(') { depth++; cur = t.add(cur); have_len = false; s++; continue; }
             std::string_view lab; const char *n = scan_label(s, e, &t, lab);
             if (!n) { set_error("newick: unterminated quoted label"); return TD_ERR_PARSE; }
             if (lab.empty()) { set_error("newick: empty leaf label near '%.16s'", s); return TD_ERR_PARSE; }
@@ -114,15 +114,17 @@ static int parse_newick(const char *text, FlatTree &t)
             const char *b = s; if (b < e && *b == '+') b++;
             double v = 0; auto r = std::from_chars(b, e, v);
             if (r.ec != std::errc() || r.ptr == b) { set_error("newick: bad branch length near '%.16s'", s); return TD_ERR_PARSE; }
-            t.len[cur] = v; s = r.ptr; continue;
+            if (!std::isfinite(v)) { set_error("newick: non-finite branch length near '%.16s'", s); return TD_ERR_PARSE; }
+            if (have_len) { set_error("newick: second branch length on one node near '%.16s'", s); return TD_ERR_PARSE; }
+            t.len[cur] = v; have_len = true; s = r.ptr; continue;
         }
         if (c == ',') {
             if (depth == 0) { set_error("newick: ',' outside parentheses"); return TD_ERR_PARSE; }
-            cur = t.add(t.parent[cur]); s++; want_subtree = true; continue;
+            cur = t.add(t.parent[cur]); have_len = false; s++; want_subtree = true; continue;
         }
         if (c == ')') {
             if (depth == 0) { set_error("newick: unbalanced ')'"); return TD_ERR_PARSE; }
-            depth--; cur = t.parent[cur]; s++; continue;
+            depth--; cur = t.parent[cur]; have_len = false; s++; continue;
         }
         if (c == ';') break;
         // internal node label / support value: dropped (treeCl/tree.py:823-825)
@@ -400,19 +402,24 @@ static void parallel_for(int64_t n, int n_threads, F &&fn)
     if (n_threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) fn(i, 0); return; }
     std::atomic<int64_t> next{0};
     const int64_t chunk = std::max<int64_t>(1, n / (n_threads * 16));
+    // an exception inside a worker (bad_alloc) must not escape its thread (std::terminate): it is parked and rethrown on the caller
+    std::atomic<bool> failed{false};
     auto body = [&](int t) {
-        for (;;) { int64_t b = next.fetch_add(chunk); if (b >= n) break; int64_t e = std::min(n, b + chunk); for (int64_t i = b; i < e; i++) fn(i, t); }
+        try {
+            for (;;) { int64_t b = next.fetch_add(chunk); if (b >= n || failed.load(std::memory_order_relaxed)) break; int64_t e = std::min(n, b + chunk); for (int64_t i = b; i < e; i++) fn(i, t); }
+        } catch (...) { failed.store(true); }
     };
     WorkerPool *pool = worker_pool();
     if (pool->workers() + 1 >= n_threads && pool->try_acquire()) {
         const std::function<void(int)> job = body;
         pool->run(n_threads, job);
         pool->release();
-        return;
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(body, t);
+        for (auto &x : th) x.join();
     }
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++) th.emplace_back(body, t);
-    for (auto &x : th) x.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::string> &labels, int n_threads, HostSet &hs,

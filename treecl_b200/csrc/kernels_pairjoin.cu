@@ -22,6 +22,7 @@
 #include <cstdint>
 
 #include "kernels.h"
+#include "exact_pair.cuh"
 
 namespace td {
 
@@ -43,29 +44,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t hash_id(uint32_t id, uint32_t mask) { return (id * 2654435761u >> 7) & mask; }
-
-// exact, purely additive recomputation for one pair: internal edges by a merge of the two shared-split lists, leaf
-// edges by a strided walk over the taxon-major leaf matrix (global memory / L2; only nearly identical trees come here)
-__device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2)
-{
-    s1 = 0.0; s2 = 0.0;
-    const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
-    SplitRec a = *A, b = *B;
-    while ((a.id & b.id) != kSentinelId) {
-        const bool adv_a = a.id <= b.id, adv_b = b.id <= a.id;
-        const double la = adv_a ? a.len : 0.0, lb = adv_b ? b.len : 0.0;
-        const double d = la - lb;
-        s1 += fabs(d); s2 = fma(d, d, s2);
-        if (adv_a) a = *++A;
-        if (adv_b) b = *++B;
-    }
-    s1 += p.single_l1[i] + p.single_l1[j];
-    s2 += p.single_l2[i] + p.single_l2[j];
-    for (int k = 0; k < p.n_k; k++) {
-        const double d = p.leafT[(size_t)k * p.ldT + i] - p.leafT[(size_t)k * p.ldT + j];
-        s1 += fabs(d); s2 = fma(d, d, s2);
-    }
-}
 
 template <uint32_t MASK, bool RECT>
 __global__ void __launch_bounds__(NT, 3) pairjoin_kernel(const PairParams p)
@@ -702,34 +680,9 @@ __global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, co
     for (unsigned w = warp; w < n; w += n_warps) {
         const int2 ij = p.wl_pairs[w];
         const int64_t i = ij.x, j = ij.y;
-        double s1 = 0.0, s2 = 0.0;
-        for (int k = lane; k < p.n_k; k += 32) {
-            const double d = p.leafT[(size_t)k * p.ldT + i] - p.leafT[(size_t)k * p.ldT + j];
-            s1 += fabs(d); s2 = fma(d, d, s2);
-        }
-        const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
-        const int hi0 = p.sh_stride - 1;
-        for (int e = lane; e < p.sh_stride; e += 32) {
-            const SplitRec a = A[e];
-            if (a.id != kSentinelId) {
-                int lo = 0, hi = hi0;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (B[mid].id < a.id) lo = mid + 1; else hi = mid; }
-                const SplitRec b = B[lo];
-                const double d = (b.id == a.id) ? a.len - b.len : a.len;       // common, or held by i only
-                s1 += fabs(d); s2 = fma(d, d, s2);
-            }
-            const SplitRec b = B[e];
-            if (b.id != kSentinelId) {
-                int lo = 0, hi = hi0;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid].id < b.id) lo = mid + 1; else hi = mid; }
-                if (A[lo].id != b.id) { s1 += fabs(b.len); s2 = fma(b.len, b.len, s2); }          // held by j only
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+        double s1, s2;
+        exact_pair_warp(p, i, j, lane, s1, s2);
         if (lane == 0) {
-            s1 += p.single_l1[i] + p.single_l1[j];
-            s2 += p.single_l2[i] + p.single_l2[j];
             const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
             if (mask & 2u) {
                 double v = s1;

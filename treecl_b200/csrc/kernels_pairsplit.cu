@@ -29,6 +29,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "exact_pair.cuh"
 
 namespace td {
 
@@ -272,28 +273,6 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------------------------
 // tiles
 // ------------------------------------------------------------------------------------------------------------------------------
-// exact, purely additive recomputation of one pair (merge of the two shared-split lists + strided walk over the leaf matrix)
-__device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2)
-{
-    s1 = 0.0; s2 = 0.0;
-    const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
-    SplitRec a = *A, b = *B;
-    while ((a.id & b.id) != kSentinelId) {
-        const bool adv_a = a.id <= b.id, adv_b = b.id <= a.id;
-        const double la = adv_a ? a.len : 0.0, lb = adv_b ? b.len : 0.0;
-        const double d = la - lb;
-        s1 += fabs(d); s2 = fma(d, d, s2);
-        if (adv_a) a = *++A;
-        if (adv_b) b = *++B;
-    }
-    s1 += p.single_l1[i] + p.single_l1[j];
-    s2 += p.single_l2[i] + p.single_l2[j];
-    for (int k = 0; k < p.n_k; k++) {
-        const double d = p.leafT[(size_t)k * p.ldT + i] - p.leafT[(size_t)k * p.ldT + j];
-        s1 += fabs(d); s2 = fma(d, d, s2);
-    }
-}
-
 // rare path, kept out of line: queue the pair for the exact fix-up kernel (same stream, right after this one); when the work
 // list is full the exact sums are computed here instead
 __device__ __noinline__ void queue_exact(const PairParams &p, int64_t i, int64_t j, double &t1, double &t2)
