@@ -91,6 +91,13 @@ int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_t
  * vector length n(n-1)/2 + n.  Only TD_EUC (and TD_WRF = the L1 distance of the vectors) are meaningful on such a set. */
 int td_encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, td_treeset **out);
 
+/* Encode once, run everywhere (SURVEY 8(b) td_treeset_from_soa, 8(e)): the encoded set as one flat byte string.  Rank 0 encodes and
+ * serialises, the bytes travel by one broadcast (torch.distributed / NCCL / MPI - the library does not care), every other rank
+ * deserialises instead of parsing and encoding the same Newick strings again.  td_treeset_serialize(ts, NULL, 0, &need) sizes the
+ * buffer.  The format is this build's memory layout behind a version word: not a storage format. */
+int td_treeset_serialize(const td_treeset *ts, void *dst, int64_t cap_bytes, int64_t *need_bytes);
+int td_treeset_deserialize(const void *data, int64_t bytes, td_treeset **out);
+
 void td_treeset_free(td_treeset *ts);
 int td_treeset_info(const td_treeset *ts, td_info *info);
 
@@ -153,6 +160,18 @@ int td_trim_cache(int device);
  * condensed result(s) into out[metric] (host pointers, pinned or pageable).  Synchronous. */
 int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
                 int64_t row_begin, int64_t row_end, double *const out[4], int device);
+
+/* Same for ONE metric, but the result is the N x N SQUARE symmetric matrix with a zero diagonal, row-major in out[N * N]: what
+ * scipy.spatial.distance.squareform makes of the condensed vector at treeCl/collection.py:456, produced on the device so that
+ * get_inter_tree_distances can wrap the caller's buffer in a DistanceMatrix without another pass over it. */
+int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overlap, double overlap_fail_value, double *out, int device);
+
+/* Output buffers in page-locked host memory are filled by direct device-to-host copies at PCIe rate, in row bands that overlap the
+ * kernels; pageable buffers work too but go through a pinned staging block and a host copy.  td_alloc_pinned / td_free_pinned hand
+ * out page-locked blocks from a cache (page-locking costs tens of milliseconds per 100 MB; at most TREEDIST_PINNED_CACHE_BYTES, default
+ * 4 GiB, stay cached).  Band size: TREEDIST_BAND_BYTES per metric (default 32 MiB). */
+int td_alloc_pinned(int64_t bytes, void **out);
+int td_free_pinned(void *p);
 
 /* Rectangular variant (treeCl/bootstrap.py:174-218): all |A| x |B| distances, row-major
  * out[a * nB + b].  Both sets must have been encoded TOGETHER (one td_encode_newick call) - `split` is the index

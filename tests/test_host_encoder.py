@@ -170,6 +170,42 @@ def test_balanced_row_ranges_cover_the_triangle():
                 assert max(counts) - min(counts) <= 2 * n
 
 
+def test_folded_row_ranges_tile_the_triangle_and_balance():
+    from treecl_b200 import _lib, engine
+    for n in (2, 17, 333, 2000, 5000, 20000, 100000):
+        for parts in (1, 2, 3, 4, 8):
+            fr = engine.folded_row_ranges(n, parts)
+            assert len(fr) == parts and all(len(r) <= 2 for r in fr)
+            rows = sorted(x for r in fr for x in r)
+            assert rows[0][0] == 0 and rows[-1][1] == n and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+            counts = [sum(_lib.condensed_offset(n, b) - _lib.condensed_offset(n, a) for a, b in r) for r in fr]
+            assert sum(counts) == n * (n - 1) // 2
+            if n >= 2000:
+                assert all(a % 64 == 0 for r in fr for a, _ in r)                 # whole tile rows
+                assert max(counts) <= (1.03 if n >= 2500 * parts else 1.12) * (sum(counts) / parts), (n, parts, counts)
+                if parts > 1:
+                    assert all(len(r) == 2 for r in fr[:-1])                      # a long-row block and a short-row block each
+
+
+def test_serialised_set_round_trip(lib_built):
+    from treecl_b200 import _lib, synth
+    for trees in (synth.structured_trees(120, 30, n_classes=3, seed=2), synth.uniform_trees(50, 70, seed=3),
+                  ['((A:1,B:1):1,C:1,(D:1,E:1):1);', '((A:1,B:1):1,C:1,(D:1,F:1):1);']):
+        ts = _lib.TreeSet(trees)
+        blob = ts.serialize()
+        back = _lib.TreeSet.deserialize(blob)
+        assert back.n_trees == len(trees) and np.array_equal(back.serialize(), blob)
+        for what, dt in ((_lib.TD_GET_MASKS, np.uint64), (_lib.TD_GET_LENGTHS, np.float64), (_lib.TD_GET_IDS, np.uint32),
+                         (_lib.TD_GET_LEAFLEN, np.float64), (_lib.TD_GET_LEAFMASK, np.uint64), (_lib.TD_GET_ROOTED, np.int32)):
+            assert np.array_equal(ts.get(what, dt), back.get(what, dt))
+        assert ts.get(_lib.TD_GET_LABELS, None) == back.get(_lib.TD_GET_LABELS, None)
+        a, b = ts.info, back.info
+        assert (a.uniform, a.dict_size, a.dict_shared, a.max_shared, a.heavy_rows, a.n_postings) == (b.uniform, b.dict_size, b.dict_shared, b.max_shared, b.heavy_rows, b.n_postings)
+        for bad in (blob[:-8], blob[:64], np.concatenate([blob, blob[:8]]), np.zeros(256, dtype=np.uint8)):
+            with pytest.raises(ValueError):
+                _lib.TreeSet.deserialize(bad)
+
+
 def test_synthetic_sets_are_deterministic(lib_built):
     from treecl_b200 import _lib, synth
     a = synth.uniform_trees(6, 20, seed=3); b = synth.uniform_trees(6, 20, seed=3)

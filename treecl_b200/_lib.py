@@ -5,11 +5,12 @@ points raise.  The CPU oracle under oracle/ is test infrastructure and is never 
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtreedist_cuda.so')
+LIB_PATH = os.environ.get('TREEDIST_LIB') or os.path.join(_HERE, 'libtreedist_cuda.so')     # (override: A/B of builds)
 
 TD_RF, TD_WRF, TD_EUC, TD_GEO = 0, 1, 2, 3
 METRIC_INDEX = {'rf': TD_RF, 'wrf': TD_WRF, 'euc': TD_EUC, 'geo': TD_GEO}
@@ -79,11 +80,19 @@ def load():
     lib.td_pairwise_rect_device.argtypes = [vp, i64, u32, i32, _c_void_p4, vp]
     lib.td_rf_incidence_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     lib.td_geo_get_stats.argtypes = [vp, ctypes.POINTER(td_geo_stats)]
-    lib.td_check_errors.argtypes = [vp, i32]
-    lib.td_trim_cache.argtypes = [i32]
-    lib.td_synth_trees.argtypes = [i32, i64, i32, ctypes.c_uint64, i32, i32, dbl, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]
-    lib.td_synth_free.argtypes = [vp]
-    lib.td_synth_free.restype = None
+    if hasattr(lib, 'td_treeset_serialize'):
+        lib.td_treeset_serialize.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
+        lib.td_treeset_deserialize.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    if hasattr(lib, 'td_pairwise_square'):
+        lib.td_pairwise_square.argtypes = [vp, i32, i32, i32, dbl, vp, i32]
+        lib.td_alloc_pinned.argtypes = [i64, ctypes.POINTER(vp)]
+        lib.td_free_pinned.argtypes = [vp]
+    if hasattr(lib, 'td_check_errors'):         # (absent from older builds loaded through TREEDIST_LIB for A/B timing)
+        lib.td_check_errors.argtypes = [vp, i32]
+        lib.td_trim_cache.argtypes = [i32]
+        lib.td_synth_trees.argtypes = [i32, i64, i32, ctypes.c_uint64, i32, i32, dbl, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        lib.td_synth_free.argtypes = [vp]
+        lib.td_synth_free.restype = None
     _lib = lib
     return lib
 
@@ -122,6 +131,33 @@ def check(rc):
 
 def _b(s):
     return s.encode() if isinstance(s, str) else s
+
+
+PINNED_RESULT_MAX = int(os.environ.get('TREEDIST_PINNED_RESULT_MAX', 4 << 30))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Uninitialised ndarray in page-locked host memory from the library's cache (td_alloc_pinned): the device-to-host copies of
+    td_pairwise / td_pairwise_square go straight into it at PCIe rate.  The block returns to the cache when the array (and every view
+    of it) is gone."""
+    lib = load()
+    count = int(np.prod(shape))
+    nbytes = max(count * np.dtype(dtype).itemsize, 1)
+    ptr = ctypes.c_void_p()
+    check(lib.td_alloc_pinned(nbytes, ctypes.byref(ptr)))
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    weakref.finalize(buf, lib.td_free_pinned, ctypes.c_void_p(ptr.value))
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def result_empty(shape):
+    """Result buffer of a host call: page-locked when a GPU is there and the result is not huge, plain numpy otherwise."""
+    if int(np.prod(shape)) * 8 <= PINNED_RESULT_MAX:
+        try:
+            return pinned_empty(shape)
+        except (NoDeviceError, MemoryError):
+            pass
+    return np.empty(shape, dtype=np.float64)
 
 
 def condensed_offset(n, row):
@@ -166,6 +202,25 @@ class TreeSet(object):
         check(lib.td_encode_newick_joined(src, int(total_bytes), int(n_trees), int(n_threads), ctypes.byref(handle)))
         self = cls.__new__(cls)
         self._h, self._lib, self.n_trees = handle, lib, int(n_trees)
+        return self
+
+    def serialize(self):
+        """The encoded set as a numpy uint8 array (td_treeset_serialize): broadcast it and TreeSet.deserialize() on the other ranks."""
+        need = ctypes.c_int64()
+        check(self._lib.td_treeset_serialize(self._h, None, 0, ctypes.byref(need)))
+        buf = np.empty(need.value, dtype=np.uint8)
+        check(self._lib.td_treeset_serialize(self._h, buf.ctypes.data, need.value, None))
+        return buf
+
+    @classmethod
+    def deserialize(cls, buf):
+        lib = load()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        handle = ctypes.c_void_p()
+        check(lib.td_treeset_deserialize(buf.ctypes.data, buf.size, ctypes.byref(handle)))
+        self = cls.__new__(cls)
+        self._h, self._lib = handle, lib
+        self.n_trees = int(self.info.n_trees)
         return self
 
     @classmethod
@@ -248,13 +303,22 @@ class TreeSet(object):
         mask, table, res = 0, [None] * 4, {}
         for m in metrics:
             mask |= 1 << METRIC_INDEX[m]
-            arr = out[m] if out is not None else np.empty(pairs, dtype=np.float64)
+            arr = out[m] if out is not None else result_empty(pairs)
             assert arr.dtype == np.float64 and arr.size >= pairs and arr.flags.c_contiguous
             res[m] = arr
             table[METRIC_INDEX[m]] = arr.ctypes.data
         check(self._lib.td_pairwise(self._h, mask, int(bool(normalise)), int(min_overlap), float(overlap_fail_value),
                                     int(row_begin), int(row_end), _c_void_p4(*table), int(device)))
         return res
+
+    def pairwise_square(self, metric, normalise=False, min_overlap=4, overlap_fail_value=0.0, device=0, out=None):
+        """One metric as the N x N symmetric matrix with a zero diagonal (td_pairwise_square): squareform() done on the device."""
+        n = self.n_trees
+        arr = out if out is not None else result_empty((n, n))
+        assert arr.dtype == np.float64 and arr.shape == (n, n) and arr.flags.c_contiguous
+        check(self._lib.td_pairwise_square(self._h, METRIC_INDEX[metric], int(bool(normalise)), int(min_overlap), float(overlap_fail_value),
+                                           arr.ctypes.data, int(device)))
+        return arr
 
     def check_errors(self, device=0):
         """After pairwise_device / pairwise_rect_device and a stream synchronise: raises if a launch flagged an error (mixed rooting,

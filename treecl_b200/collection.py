@@ -183,8 +183,13 @@ class Collection(object):
         trees = self.trees
         ts = _lib.TreeSet(trees)
         try:
-            array = engine.pairwise_condensed(ts, (task_interface.metric,), normalise, min_overlap,
-                                              float(overlap_fail_value), devices)[task_interface.metric]
+            if devices is None or len(devices) == 1:
+                # one GPU: squareform() (collection.py:456) is done on the device, the N x N matrix lands in page-locked memory
+                square = ts.pairwise_square(task_interface.metric, normalise, min_overlap, float(overlap_fail_value),
+                                            engine.default_device() if devices is None else devices[0])
+            else:
+                square = squareform(engine.pairwise_condensed(ts, (task_interface.metric,), normalise, min_overlap,
+                                                              float(overlap_fail_value), devices)[task_interface.metric])
         finally:
             ts.close()
-        return DistanceMatrix.from_array(squareform(array), self.names)
+        return DistanceMatrix.from_array(square, self.names)

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -79,6 +80,114 @@ static void pool_free(int device, void *p, size_t bytes)
     std::lock_guard<std::mutex> g(P.mu);
     if (P.cached + bytes > pool_limit()) { cudaFree(p); return; }
     P.free_blocks.emplace_back(bytes, p); P.cached += bytes;
+}
+
+// ---- pinned host memory: cudaHostAlloc costs tens of milliseconds per 100 MB (the pages are faulted in and locked), so blocks are
+// cached for the life of the process, up to TREEDIST_PINNED_CACHE_BYTES (default 4 GiB)
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<size_t, void *>> free_blocks;
+    std::vector<std::pair<void *, size_t>> live;
+    size_t cached = 0;
+};
+static PinnedPool g_pinned;
+static size_t pinned_limit()
+{
+    static const size_t v = [] {
+        const char *e = getenv("TREEDIST_PINNED_CACHE_BYTES");
+        if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 10); if (end != e) return (size_t)x; }
+        return (size_t)(4ull << 30);
+    }();
+    return v;
+}
+
+static cudaError_t pinned_alloc(size_t bytes, void **out)
+{
+    bytes = (std::max<size_t>(bytes, 1) + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1);
+    PinnedPool &P = g_pinned;
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        size_t best = (size_t)-1, best_i = 0;
+        for (size_t i = 0; i < P.free_blocks.size(); i++) {
+            const size_t sz = P.free_blocks[i].first;
+            if (sz >= bytes && sz <= 2 * bytes + (16u << 20) && sz < best) { best = sz; best_i = i; }
+        }
+        if (best != (size_t)-1) {
+            *out = P.free_blocks[best_i].second; P.cached -= best;
+            P.free_blocks.erase(P.free_blocks.begin() + best_i);
+            P.live.emplace_back(*out, best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {                          // give the cache back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> g(P.mu);
+        for (auto &b : P.free_blocks) cudaFreeHost(b.second);
+        P.free_blocks.clear(); P.cached = 0;
+        e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    }
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> g(P.mu); P.live.emplace_back(*out, bytes); }
+    return e;
+}
+
+static bool pinned_free(void *p)
+{
+    if (!p) return true;
+    PinnedPool &P = g_pinned;
+    std::lock_guard<std::mutex> g(P.mu);
+    for (size_t i = 0; i < P.live.size(); i++) {
+        if (P.live[i].first != p) continue;
+        const size_t bytes = P.live[i].second;
+        P.live.erase(P.live.begin() + i);
+        if (P.cached + bytes > pinned_limit()) cudaFreeHost(p);
+        else { P.free_blocks.emplace_back(bytes, p); P.cached += bytes; }
+        return true;
+    }
+    return false;
+}
+
+static void pinned_trim()
+{
+    PinnedPool &P = g_pinned;
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto &b : P.free_blocks) cudaFreeHost(b.second);
+    P.free_blocks.clear(); P.cached = 0;
+}
+
+// ---- streams and events of one host-buffer call (td_pairwise, td_pairwise_square): kernels of band k on `compute`, the device-to-host
+// copy of band k on `copy`, two bands in flight.  Cached per device; a call takes a bundle for its duration, so concurrent calls on one
+// set (one host thread per GPU, or several per GPU) never share a stream.
+struct BandStreams {
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+};
+struct StreamPool { std::mutex mu; std::vector<BandStreams> idle; };
+static StreamPool g_streams[64];
+
+static cudaError_t acquire_streams(int device, BandStreams *bs)
+{
+    StreamPool &P = g_streams[device & 63];
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        if (!P.idle.empty()) { *bs = P.idle.back(); P.idle.pop_back(); return cudaSuccess; }
+    }
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&bs->compute, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&bs->copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int b = 0; b < 2; b++) {
+        if ((e = cudaEventCreateWithFlags(&bs->done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&bs->copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static void release_streams(int device, const BandStreams &bs)
+{
+    if (!bs.compute) return;
+    StreamPool &P = g_streams[device & 63];
+    std::lock_guard<std::mutex> g(P.mu);
+    P.idle.push_back(bs);
 }
 
 struct DevProps { int sm_count = 0; size_t smem_optin = 0; bool valid = false; };
@@ -708,6 +817,36 @@ int td_encode_newick_joined(const char *buffer, int64_t total_bytes, int64_t n_t
     return td_encode_newick(ptrs.data(), n_trees, n_threads, out);
 }
 
+int td_treeset_serialize(const td_treeset *ts, void *dst, int64_t cap_bytes, int64_t *need_bytes)
+{
+    if (!ts) { set_error("null treeset"); return TD_ERR_ARG; }
+    try {
+        const size_t need = serialize_set(ts->host, nullptr);
+        if (need_bytes) *need_bytes = (int64_t)need;
+        if (!dst) return TD_OK;
+        if (cap_bytes < (int64_t)need) { set_error("buffer of %lld bytes is too small for the serialised set (%lld bytes)", (long long)cap_bytes, (long long)need); return TD_ERR_ARG; }
+        std::vector<unsigned char> buf; buf.reserve(need);
+        serialize_set(ts->host, &buf);
+        memcpy(dst, buf.data(), buf.size());
+    } catch (const std::bad_alloc &) { set_error("out of memory"); return TD_ERR_NOMEM; }
+    return TD_OK;
+}
+
+int td_treeset_deserialize(const void *data, int64_t bytes, td_treeset **out)
+{
+    if (!out) { set_error("null output pointer"); return TD_ERR_ARG; }
+    *out = nullptr;
+    if (!data || bytes <= 0) { set_error("empty buffer"); return TD_ERR_ARG; }
+    td_treeset *ts = new (std::nothrow) td_treeset();
+    if (!ts) { set_error("out of memory"); return TD_ERR_NOMEM; }
+    int rc;
+    try { rc = deserialize_set(data, (size_t)bytes, ts->host); }
+    catch (const std::bad_alloc &) { set_error("out of memory"); rc = TD_ERR_NOMEM; }
+    if (rc) { delete ts; return rc; }
+    *out = ts;
+    return TD_OK;
+}
+
 void td_treeset_free(td_treeset *ts)
 {
     if (!ts) return;
@@ -819,38 +958,216 @@ int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask,
     return run_pairwise(ts, d, metric_mask, normalise, 4, 0.0, true, split, 0, split, d_out, (cudaStream_t)stream);
 }
 
+// ---- host-buffer calls: row bands, two in flight, kernels of band k under the device-to-host copy of band k - 1 -------------------------
+namespace {
+
+// bytes of one band per metric (TREEDIST_BAND_BYTES, default 32 MiB): small enough that the copy of the first band starts early and
+// two bands stay L2 / HBM friendly, large enough that a band is thousands of tiles
+size_t band_bytes_target()
+{
+    static const size_t v = [] {
+        const char *e = getenv("TREEDIST_BAND_BYTES");
+        if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 10); if (end != e && x >= (1u << 20)) return (size_t)x; }
+        return (size_t)(32u << 20);
+    }();
+    return v;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// pageable destination: the band went to a pinned staging block first, the host moves it on (a few threads: one core does ~10 GB/s)
+void host_copy(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kChunk = 8u << 20;
+    const int parts = (int)std::min<size_t>(4, bytes / kChunk);
+    if (parts <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / parts + 63) & ~(size_t)63;
+    for (int t = 1; t < parts; t++) {
+        const size_t o = (size_t)t * per, n = t == parts - 1 ? bytes - o : per;
+        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, n); });
+    }
+    memcpy(dst, src, per);
+    for (auto &x : th) x.join();
+}
+
+// rows [row_begin, row_end) cut into bands of about `target` pairs at multiples of 64 rows (whole tile rows: no tile is computed twice)
+std::vector<int64_t> plan_bands(int64_t N, int64_t row_begin, int64_t row_end, int64_t target)
+{
+    std::vector<int64_t> cuts{row_begin};
+    const int64_t total = condensed_offset(N, row_end) - condensed_offset(N, row_begin);
+    if (total > target + target / 2) {
+        int64_t r = row_begin;
+        while (r < row_end) {
+            const int64_t base = condensed_offset(N, r);
+            int64_t e = (r / 64 + 1) * 64;
+            while (e < row_end && condensed_offset(N, std::min(e, row_end)) - base < target) e += 64;
+            e = std::min(e, row_end);
+            if (condensed_offset(N, row_end) - condensed_offset(N, e) < target / 4) e = row_end;      // no tiny last band
+            cuts.push_back(e); r = e;
+        }
+    } else cuts.push_back(row_end);
+    return cuts;
+}
+
+struct HostCall {                       // everything a host-buffer call owns; released on every exit path
+    int device = -1;
+    BandStreams bs;
+    void *dbuf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    size_t dsize[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    void *stage[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    void *extra = nullptr; size_t extra_size = 0;
+    ~HostCall()
+    {
+        if (bs.compute) { cudaStreamSynchronize(bs.compute); cudaStreamSynchronize(bs.copy); }
+        for (int b = 0; b < 2; b++) for (int m = 0; m < 4; m++) { if (dbuf[b][m]) pool_free(device, dbuf[b][m], dsize[b][m]); pinned_free(stage[b][m]); }
+        if (extra) pool_free(device, extra, extra_size);
+        release_streams(device, bs);
+    }
+};
+
+}  // namespace
+
 int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
                 int64_t row_begin, int64_t row_end, double *const out[4], int device)
 {
     if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
     DeviceScope scope;
     int rc;
+    if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
     if ((rc = upload(ts, device, 0))) return rc;        // no-op when already resident
     DeviceSet *dset = resident(ts, device);
     const int64_t N = ts->host.N;
     if (row_begin < 0 || row_end > N || row_begin > row_end) { set_error("row range outside [0,N]"); return TD_ERR_ARG; }
     const int64_t pairs = condensed_offset(N, row_end) - condensed_offset(N, row_begin);
     if (pairs <= 0) return TD_OK;
+    for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && !out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(device));
-    void *dbuf[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t dsize[4] = {0, 0, 0, 0};
-    auto cleanup = [&] { for (int m = 0; m < 4; m++) if (dbuf[m]) pool_free(device, dbuf[m], dsize[m]); };
+
+    const std::vector<int64_t> cuts = plan_bands(N, row_begin, row_end, (int64_t)(band_bytes_target() / sizeof(double)));
+    const int n_bands = (int)cuts.size() - 1;
+    int64_t max_band = 0;
+    for (int k = 0; k < n_bands; k++) max_band = std::max(max_band, condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]));
+    HostCall hc; hc.device = device;
+    bool pageable[4] = {false, false, false, false}, any_pageable = false;
     for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u) {
-        if (!out[m]) { cleanup(); set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
-        cudaError_t e = pool_alloc(device, (size_t)pairs * sizeof(double), &dbuf[m], &dsize[m]);
-        if (e != cudaSuccess) { cleanup(); set_error("cudaMalloc of %lld bytes failed: %s", (long long)pairs * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+        pageable[m] = !is_pinned(out[m]); any_pageable |= pageable[m];
+        for (int b = 0; b < std::min(n_bands, 2); b++) {
+            cudaError_t e = pool_alloc(device, (size_t)max_band * sizeof(double), &hc.dbuf[b][m], &hc.dsize[b][m]);
+            if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)max_band * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+            if (pageable[m]) {
+                e = pinned_alloc((size_t)max_band * sizeof(double), &hc.stage[b][m]);
+                if (e != cudaSuccess) { set_error("cudaHostAlloc of %lld bytes failed: %s", (long long)max_band * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+            }
+        }
     }
-    cudaStream_t st = 0;
-    rc = td_pairwise_device(ts, metric_mask, normalise, min_overlap, overlap_fail_value, row_begin, row_end, dbuf, st);
-    if (rc) { cleanup(); return rc; }
-    for (int m = 0; m < 4; m++) if (dbuf[m]) {
-        cudaError_t e = cudaMemcpyAsync(out[m], dbuf[m], (size_t)pairs * sizeof(double), cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) { cleanup(); set_error("D2H copy failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    const BandStreams &bs = hc.bs;
+    const int64_t p_first = condensed_offset(N, row_begin);
+    auto drain = [&](int k) -> int {                       // host side of band k: wait for its copy, move pageable outputs on
+        CUDA_TRY(cudaEventSynchronize(bs.copied[k & 1]));
+        const int64_t p0 = condensed_offset(N, cuts[k]) - p_first, n = condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]);
+        for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && pageable[m]) host_copy(out[m] + p0, hc.stage[k & 1][m], (size_t)n * sizeof(double));
+        return TD_OK;
+    };
+    for (int k = 0; k < n_bands; k++) {
+        const int b = k & 1;
+        const int64_t p0 = condensed_offset(N, cuts[k]) - p_first, n = condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]);
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(bs.compute, bs.copied[b], 0));        // the band buffers are free again
+        if ((rc = run_pairwise(ts, dset, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, cuts[k], cuts[k + 1], hc.dbuf[b], bs.compute))) return rc;
+        CUDA_TRY(cudaEventRecord(bs.done[b], bs.compute));
+        CUDA_TRY(cudaStreamWaitEvent(bs.copy, bs.done[b], 0));
+        for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u)
+            CUDA_TRY(cudaMemcpyAsync(pageable[m] ? hc.stage[b][m] : (void *)(out[m] + p0), hc.dbuf[b][m], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, bs.copy));
+        CUDA_TRY(cudaEventRecord(bs.copied[b], bs.copy));
+        if (k >= 1 && any_pageable && (rc = drain(k - 1))) return rc;                   // under the kernels / copy of band k
     }
-    cudaError_t e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    if (any_pageable) { if ((rc = drain(n_bands - 1))) return rc; }
+    {
+        cudaError_t e = cudaStreamSynchronize(bs.copy);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(bs.compute);
+        if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    }
     return take_error_flag(dset);
+}
+
+int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overlap, double overlap_fail_value, double *out, int device)
+{
+    if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    if (metric < 0 || metric > 3) { set_error("unknown metric %d", metric); return TD_ERR_ARG; }
+    DeviceScope scope;
+    int rc;
+    if ((rc = upload(ts, device, 0))) return rc;
+    DeviceSet *dset = resident(ts, device);
+    const int64_t N = ts->host.N, pairs = N * (N - 1) / 2;
+    if (N == 1) { out[0] = 0.0; return TD_OK; }
+    CUDA_TRY(cudaSetDevice(device));
+    HostCall hc; hc.device = device;
+    {
+        cudaError_t e = pool_alloc(device, (size_t)pairs * sizeof(double), &hc.extra, &hc.extra_size);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)pairs * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    }
+    // bands of whole rows of the square matrix
+    const int64_t rows_per_band = std::max<int64_t>(32, (int64_t)(band_bytes_target() / sizeof(double)) / N / 32 * 32);
+    const int n_bands = (int)((N + rows_per_band - 1) / rows_per_band);
+    const bool pageable = !is_pinned(out);
+    for (int b = 0; b < std::min(n_bands, 2); b++) {
+        cudaError_t e = pool_alloc(device, (size_t)rows_per_band * N * sizeof(double), &hc.dbuf[b][0], &hc.dsize[b][0]);
+        if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+        if (pageable && (e = pinned_alloc((size_t)rows_per_band * N * sizeof(double), &hc.stage[b][0])) != cudaSuccess) { set_error("cudaHostAlloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    const BandStreams &bs = hc.bs;
+    void *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    d_out[metric] = hc.extra;
+    if ((rc = run_pairwise(ts, dset, 1u << metric, normalise, min_overlap, overlap_fail_value, false, 0, 0, N, d_out, bs.compute))) return rc;
+    auto drain = [&](int k) -> int {
+        CUDA_TRY(cudaEventSynchronize(bs.copied[k & 1]));
+        const int64_t r0 = (int64_t)k * rows_per_band, r1 = std::min(N, r0 + rows_per_band);
+        if (pageable) host_copy(out + r0 * N, hc.stage[k & 1][0], (size_t)(r1 - r0) * N * sizeof(double));
+        return TD_OK;
+    };
+    for (int k = 0; k < n_bands; k++) {
+        const int b = k & 1;
+        const int64_t r0 = (int64_t)k * rows_per_band, r1 = std::min(N, r0 + rows_per_band);
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(bs.compute, bs.copied[b], 0));
+        CUDA_TRY(launch_square_rows((const double *)hc.extra, (double *)hc.dbuf[b][0], N, r0, r1, bs.compute));
+        launch_counter_add(1);
+        CUDA_TRY(cudaEventRecord(bs.done[b], bs.compute));
+        CUDA_TRY(cudaStreamWaitEvent(bs.copy, bs.done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(pageable ? hc.stage[b][0] : (void *)(out + r0 * N), hc.dbuf[b][0], (size_t)(r1 - r0) * N * sizeof(double), cudaMemcpyDeviceToHost, bs.copy));
+        CUDA_TRY(cudaEventRecord(bs.copied[b], bs.copy));
+        if (k >= 1 && pageable && (rc = drain(k - 1))) return rc;
+    }
+    if (pageable && (rc = drain(n_bands - 1))) return rc;
+    {
+        cudaError_t e = cudaStreamSynchronize(bs.copy);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(bs.compute);
+        if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+    }
+    return take_error_flag(dset);
+}
+
+int td_alloc_pinned(int64_t bytes, void **out)
+{
+    if (!out || bytes < 0) { set_error("bad argument"); return TD_ERR_ARG; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); set_error("no CUDA device available: pinned host memory needs one"); return TD_ERR_NO_DEVICE; }
+    cudaError_t e = pinned_alloc((size_t)bytes, out);
+    if (e != cudaSuccess) { set_error("cudaHostAlloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    return TD_OK;
+}
+
+int td_free_pinned(void *p)
+{
+    if (!pinned_free(p)) { set_error("pointer was not allocated by td_alloc_pinned"); return TD_ERR_ARG; }
+    return TD_OK;
 }
 
 int td_check_errors(td_treeset *ts, int device)
@@ -872,6 +1189,7 @@ int td_trim_cache(int device)
         if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); continue; }
         pool_trim(dev);
     }
+    if (device < 0) pinned_trim();
     return TD_OK;
 }
 

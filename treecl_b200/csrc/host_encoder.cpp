@@ -761,3 +761,88 @@ int encode_kendall_colijn(const char *const *newick, int64_t N, double lambda, i
 }
 
 }  // namespace td
+
+// ------------------------------------------------------------------------------------------------------------
+// Serialised form of an encoded set (td_treeset_serialize / td_treeset_deserialize): encode once, ship the bytes to the other ranks
+// (one broadcast) instead of parsing and encoding the same trees in every process.  Little-endian, this build's layout; a version
+// word guards against mixing builds.
+// ------------------------------------------------------------------------------------------------------------
+namespace td {
+
+namespace {
+constexpr uint64_t kSerialMagic = 0x3154455345455254ull;      // "TREESET1"
+constexpr uint32_t kSerialVersion = 2;
+
+struct Writer {
+    std::vector<unsigned char> *out; size_t size = 0;         // out == nullptr: only measure
+    void raw(const void *p, size_t n) { if (out) { const unsigned char *b = (const unsigned char *)p; out->insert(out->end(), b, b + n); } size += n; }
+    template <class T> void pod(const T &v) { raw(&v, sizeof v); }
+    template <class T> void vec(const std::vector<T> &v) { const uint64_t n = v.size(); pod(n); raw(v.data(), n * sizeof(T)); const uint64_t pad = (8 - (n * sizeof(T)) % 8) % 8, z = 0; raw(&z, pad); }
+};
+struct Reader {
+    const unsigned char *p, *end; bool ok = true;
+    void raw(void *dst, size_t n) { if (!ok || (size_t)(end - p) < n) { ok = false; return; } memcpy(dst, p, n); p += n; }
+    template <class T> void pod(T &v) { raw(&v, sizeof v); }
+    template <class T> void vec(std::vector<T> &v)
+    {
+        uint64_t n = 0; pod(n);
+        if (!ok || n > (uint64_t)(end - p) / sizeof(T)) { ok = false; return; }
+        v.resize(n); raw(v.data(), n * sizeof(T));
+        const size_t pad = (8 - (n * sizeof(T)) % 8) % 8;
+        if ((size_t)(end - p) < pad) { ok = false; return; }
+        p += pad;
+    }
+};
+
+template <class IO, class HS>
+void serial_fields(IO &io, HS &h)
+{
+    io.pod(h.N); io.pod(h.n_taxa); io.pod(h.W); io.pod(h.max_splits); io.pod(h.max_shared); io.pod(h.max_tile_entries);
+    io.pod(h.uniform); io.pod(h.rooted); io.pod(h.dict_size); io.pod(h.dict_shared); io.pod(h.total_splits);
+    io.pod(h.heavy_rows); io.pod(h.heavy_events); io.pod(h.heavy_common); io.pod(h.total_common); io.pod(h.mean_common); io.pod(h.sh_stride);
+    io.vec(h.n_splits); io.vec(h.n_leaves); io.vec(h.tree_rooted); io.vec(h.n_shared); io.vec(h.leafmask);
+    io.vec(h.sum_len); io.vec(h.norm); io.vec(h.single_l1); io.vec(h.single_l2); io.vec(h.q1); io.vec(h.q2); io.vec(h.q1_light); io.vec(h.q2t);
+    io.vec(h.masks); io.vec(h.lens); io.vec(h.ids); io.vec(h.leaflen);
+    io.vec(h.shared); io.vec(h.shared_x); io.vec(h.post_tree); io.vec(h.post_end); io.vec(h.post_len);
+}
+}  // namespace
+
+size_t serialize_set(const HostSet &hs, std::vector<unsigned char> *out)
+{
+    Writer w{out};
+    w.pod(kSerialMagic); w.pod(kSerialVersion); const uint32_t rec = (uint32_t)sizeof(SplitRec); w.pod(rec);
+    std::string joined;
+    for (size_t i = 0; i < hs.labels.size(); i++) { if (i) joined.push_back('\n'); joined += hs.labels[i]; }
+    const std::vector<char> lab(joined.begin(), joined.end());
+    w.vec(lab);
+    serial_fields(w, hs);
+    return w.size;
+}
+
+int deserialize_set(const void *data, size_t bytes, HostSet &hs)
+{
+    Reader r{(const unsigned char *)data, (const unsigned char *)data + bytes};
+    uint64_t magic = 0; uint32_t version = 0, rec = 0;
+    r.pod(magic); r.pod(version); r.pod(rec);
+    if (!r.ok || magic != kSerialMagic || version != kSerialVersion || rec != sizeof(SplitRec)) { set_error("not a serialised tree set of this library version"); return TD_ERR_ARG; }
+    std::vector<char> lab; r.vec(lab);
+    serial_fields(r, hs);
+    if (!r.ok || r.p != r.end) { set_error("serialised tree set is truncated or has trailing bytes"); return TD_ERR_ARG; }
+    hs.labels.clear();
+    for (size_t b = 0; b < lab.size();) { size_t e = b; while (e < lab.size() && lab[e] != '\n') e++; hs.labels.emplace_back(lab.data() + b, e - b); b = e + 1; }
+    // consistency of the sizes the kernels index with (a corrupted buffer must not become an out-of-bounds read on the device)
+    const size_t N = (size_t)hs.N, S = (size_t)std::max(hs.max_splits, 1);
+    auto per_tree = [&](size_t n) { return n == N; };
+    const bool sane = hs.N >= 1 && hs.n_taxa >= 0 && hs.W >= 1 && hs.W >= (hs.n_taxa + 63) / 64 && hs.sh_stride >= 2 && hs.max_splits >= 0
+        && (int)hs.labels.size() == hs.n_taxa
+        && per_tree(hs.n_splits.size()) && per_tree(hs.n_shared.size()) && per_tree(hs.tree_rooted.size()) && hs.leafmask.size() >= N * (size_t)hs.W
+        && per_tree(hs.sum_len.size()) && per_tree(hs.norm.size()) && per_tree(hs.single_l1.size()) && per_tree(hs.single_l2.size())
+        && per_tree(hs.q1.size()) && per_tree(hs.q2.size()) && per_tree(hs.q1_light.size()) && per_tree(hs.q2t.size())
+        && hs.leaflen.size() >= N * (size_t)hs.n_taxa && hs.lens.size() >= N * S && hs.masks.size() >= N * S * (size_t)hs.W && hs.ids.size() >= N * S
+        && hs.shared.size() == N * (size_t)hs.sh_stride && hs.shared_x.size() == hs.shared.size()
+        && hs.post_end.size() == hs.post_tree.size() && hs.post_len.size() == hs.post_tree.size();
+    if (!sane) { set_error("serialised tree set is inconsistent"); return TD_ERR_ARG; }
+    return TD_OK;
+}
+
+}  // namespace td

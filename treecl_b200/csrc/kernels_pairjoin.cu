@@ -668,32 +668,27 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 }
 
 
-// Recompute the queued pairs additively (no Q + E subtraction) and overwrite their wrf / euc entries.  One warp per pair:
-// lanes stride over the taxa and over both trees' shared-split lists (membership by binary search in the other list);
-// fixed lane assignment + shuffle-tree reduction => the same bits on every run.
+// Recompute the queued pairs additively (no Q + E subtraction) and overwrite their wrf / euc entries.  One thread per pair running
+// exact_pair() - the very function a tile kernel falls back to when the work list is full, so a pair gets the same bits either way.
 template <bool RECT>
 __global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, const uint32_t mask)
 {
     const unsigned n = min(*p.wl_count, p.wl_capacity);
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned w = warp; w < n; w += n_warps) {
+    for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
         const int2 ij = p.wl_pairs[w];
         const int64_t i = ij.x, j = ij.y;
         double s1, s2;
-        exact_pair_warp(p, i, j, lane, s1, s2);
-        if (lane == 0) {
-            const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
-            if (mask & 2u) {
-                double v = s1;
-                if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
-                p.out[1][idx] = v;
-            }
-            if (mask & 4u) {
-                double v = sqrt(s2);
-                if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
-                p.out[2][idx] = v;
-            }
+        exact_pair(p, i, j, s1, s2);
+        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
+        if (mask & 2u) {
+            double v = s1;
+            if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
+            p.out[1][idx] = v;
+        }
+        if (mask & 4u) {
+            double v = sqrt(s2);
+            if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
+            p.out[2][idx] = v;
         }
     }
 }

@@ -26,6 +26,8 @@
 #include <cudaTypedefs.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -371,6 +373,9 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
         if constexpr (kWRF) sc_q1 = p.q1[tree];
         if constexpr (kEUC) sc_q2 = p.q2t[tree];
     }
+    // the other threads must not poll the stage barriers before thread 0 has initialised them (the shared memory still holds whatever the
+    // previous CTA - of any kernel - left there); the loads requested above stay in flight across the barrier
+    if constexpr (kWeighted) __syncthreads();
     TRACE(1);
     // ---- this tile's events: one aligned load per record.  The first EVR records of every thread are requested now and applied after
     // the leaf sums (their latency hides behind the tensor-core work).
@@ -738,21 +743,28 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
     *launches = 0;
     if (p.n_tiles <= 0) return cudaSuccess;
     const bool weighted = (mask & 6u) != 0;
+    // TREEDIST_SYNC_DEBUG: synchronise after every launch and say which kernel failed (debug aid; kills the overlap)
+    static const bool sync_debug = getenv("TREEDIST_SYNC_DEBUG") != nullptr;
+    auto checked = [&](cudaError_t e, const char *what) {
+        if (e == cudaSuccess && sync_debug) e = cudaStreamSynchronize(st);
+        if (sync_debug) fprintf(stderr, "[treedist] %s (mask %u): %s\n", what, mask, cudaGetErrorString(e));
+        return e;
+    };
     cudaError_t e = cudaSuccess;
     {
         // the row groups of all tile rows of this launch (p.rg0 = first group of the first tile row): the kernel writes their rows of
         // the segment table completely, rows outside [row_begin, row_end) as empty segments
         const long long groups = (long long)p.tri_rows * (TR / RG);
         const size_t smem_e = pairsplit_events_smem_bytes(mask, p.sh_stride, p.col_tiles_total);
-        e = rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, smem_e, st);
+        e = checked(rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, smem_e, st), "pair_events_kernel");
         ++*launches;
         if (e != cudaSuccess) return e;
     }
-    e = launch_pairsplit_tiles(mask, rect, p, st);
+    e = checked(launch_pairsplit_tiles(mask, rect, p, st), "pair_dense_kernel");
     ++*launches;
     if (e != cudaSuccess || !weighted) return e;
     ++*launches;
-    return launch_exact_fixup(mask, rect, p, n_sms, st);
+    return checked(launch_exact_fixup(mask, rect, p, n_sms, st), "exact_fixup_kernel");
 }
 
 }  // namespace td

@@ -260,4 +260,43 @@ cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int
     return cudaGetLastError();
 }
 
+// Rows [r0, r1) of the SQUARE symmetric matrix (zero diagonal) from the condensed vector: scipy.spatial.distance.squareform on the
+// device (treeCl/collection.py:456), so that the drop-in call can copy the N x N matrix straight into the caller's memory.  32 x 32
+// tiles; tiles below the diagonal read the condensed vector along its contiguous direction and turn through shared memory.
+__global__ void square_rows_kernel(const double *__restrict__ cond, double *__restrict__ sq, int64_t N, int64_t r0, int64_t r1)
+{
+    __shared__ double tile[32][33];
+    const int64_t i0 = r0 + (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x;
+    if (j0 + 31 < i0) {
+        // strictly below the diagonal: value (i, j) = cond[(j, i)], contiguous along i for a fixed j
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int64_t j = j0 + r, i = i0 + tx;
+            tile[r][tx] = (i < r1 && j < N) ? cond[j * N - j * (j + 1) / 2 + (i - j - 1)] : 0.0;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int64_t i = i0 + r, j = j0 + tx;
+            if (i < r1 && j < N) sq[(i - r0) * N + j] = tile[tx][r];
+        }
+        return;
+    }
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t i = i0 + r, j = j0 + tx;
+        if (i >= r1 || j >= N) continue;
+        double v = 0.0;
+        if (j > i) v = cond[i * N - i * (i + 1) / 2 + (j - i - 1)];
+        else if (j < i) v = cond[j * N - j * (j + 1) / 2 + (i - j - 1)];
+        sq[(i - r0) * N + j] = v;
+    }
+}
+
+cudaError_t launch_square_rows(const double *cond, double *sq, int64_t N, int64_t r0, int64_t r1, cudaStream_t st)
+{
+    if (r1 <= r0) return cudaSuccess;
+    const dim3 grid((unsigned)((N + 31) / 32), (unsigned)((r1 - r0 + 31) / 32)), block(32, 8);
+    square_rows_kernel<<<grid, block, 0, st>>>(cond, sq, N, r0, r1);
+    return cudaGetLastError();
+}
+
 }  // namespace td

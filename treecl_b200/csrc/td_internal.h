@@ -71,6 +71,8 @@ int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, Hos
 int encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, HostSet &hs);
 int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted);
 int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
+size_t serialize_set(const HostSet &hs, std::vector<unsigned char> *out);      // out == nullptr: size only
+int deserialize_set(const void *data, size_t bytes, HostSet &hs);
 
 }  // namespace td
 

@@ -47,7 +47,7 @@ class DistanceMatrix(object):
         if nrow != ncol:
             raise ValueError('Not a square array')
         new_instance = cls()
-        new_instance.df = pd.DataFrame(array)
+        new_instance.df = pd.DataFrame(array, copy=False)          # (pandas 3 would copy the N x N array otherwise)
         try:
             new_instance.set_names(names)
         except ValueError as err:     # distance_matrix.py:486-488: reported, not raised
