@@ -184,6 +184,10 @@ int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask,
 int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out,
                            int out_is_u16, void *stream);
 
+/* Same with a HOST output buffer (uint16 condensed, rows [row_begin, row_end)): row bands, the kernels of band k under the
+ * device-to-host copy of band k - 1 (BASELINE config 4: "tiles streamed to pinned host").  Pinned `out` (td_alloc_pinned): direct copies. */
+int td_rf_incidence(td_treeset *ts, int64_t row_begin, int64_t row_end, uint16_t *out, int device);
+
 /* Counters of the last geodesic launch on this set (mean GTP iterations etc.), for DESIGN.md / bench.py. */
 typedef struct {
     uint64_t pairs, maxflow_solves, ratios, augmentations, launches;

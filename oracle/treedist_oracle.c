@@ -747,23 +747,36 @@ typedef struct {
 
 static long row_start(long i, long n) { return i * n - i * (i + 1) / 2; }   /* condensed index of (i, i+1) */
 
+/* row of condensed index p: the largest i with row_start(i) <= p */
+static long row_of(long p, long n)
+{
+    double b = 2.0 * (double)n - 1.0;
+    long i = (long)floor((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+    if (i < 0) i = 0;
+    while (i > 0 && row_start(i, n) > p) i--;
+    while (i + 1 < n - 1 && row_start(i + 1, n) <= p) i++;
+    return i;
+}
+
+/* threads pull chunks of 256 consecutive pairs of [pair_begin, pair_end): a bounded sample that lies in one or two long rows still
+ * keeps every thread busy */
 static void *worker(void *arg)
 {
     job_t *J = (job_t *)arg;
+    const long chunk = 256;
     for (;;) {
-        long i = __sync_fetch_and_add(&J->next_row, 1);
-        if (i >= J->n - 1 || J->rc) break;
-        long base = row_start(i, J->n);
-        if (base + (J->n - 1 - i) <= J->pair_begin || base >= J->pair_end) continue;
-        for (long j = i + 1; j < J->n; j++) {
-            long p = base + (j - i - 1);
-            if (p < J->pair_begin || p >= J->pair_end) continue;
+        long c = __sync_fetch_and_add(&J->next_row, 1);
+        long p = J->pair_begin + c * chunk, p_end = p + chunk < J->pair_end ? p + chunk : J->pair_end;
+        if (p >= J->pair_end || J->rc) break;
+        long i = row_of(p, J->n), j = i + 1 + (p - row_start(i, J->n));
+        for (; p < p_end; p++) {
             int rc; double d = 0;
             if (J->reparse) rc = orc_pair(J->nwk[i], J->nwk[j], J->metric, J->normalise, J->min_overlap, J->fail, &d);
             else if (J->all_same) rc = enc_distance(&J->encs[i], &J->encs[j], J->metric, J->normalise, &d);
             else rc = pair_trees(&J->trees[i], &J->trees[j], J->metric, J->normalise, J->min_overlap, J->fail, &d);
             if (rc) { if (!__sync_lock_test_and_set(&J->rc, rc)) memcpy(J->err, g_err, sizeof J->err); break; }
             J->out[p - J->pair_begin] = d;
+            if (++j >= J->n) { i++; j = i + 1; }
         }
     }
     return NULL;

@@ -382,6 +382,61 @@ def test_rectangular_variant(td, oracle_mod, pair_kernel, kind):
             assert_close(got, want)
 
 
+@pytest.mark.parametrize('kind', ['uniform', 'structured'])
+def test_host_calls_in_row_bands(td, oracle_mod, monkeypatch, kind):
+    """td_pairwise / td_pairwise_square / td_rf_incidence stream their result in row bands (kernels of band k under the copy of band
+    k - 1), into page-locked buffers directly and into pageable ones through a staging block: every way gives the same bytes."""
+    from treecl_b200 import _lib
+    n = 900
+    trees = make(kind, n, 24, seed=5)
+    ts = _lib.TreeSet(trees)
+    metrics = ('rf', 'wrf', 'euc', 'geo')
+    pairs = n * (n - 1) // 2
+    one = ts.pairwise(metrics, normalise=True)                                 # 3.2 MB per metric: a single band
+    for m in metrics:
+        want = oracle_mod.matrix(trees, m, normalise=True, nthreads=NTHREADS)
+        assert np.array_equal(one[m], want) if m == 'rf' else assert_close(one[m], want) is None
+    monkeypatch.setenv('TREEDIST_BAND_BYTES', str(1 << 18))                    # 13 bands
+    pinned = ts.pairwise(metrics, normalise=True)
+    pageable = ts.pairwise(metrics, normalise=True, out={m: np.full(pairs, -1.0) for m in metrics})
+    mixed_out = {'rf': np.full(pairs, -1.0), 'euc': _lib.pinned_empty(pairs)}
+    mixed = ts.pairwise(('rf', 'euc'), normalise=True, out=mixed_out)
+    for m in metrics:
+        assert np.array_equal(pinned[m], one[m]) and np.array_equal(pageable[m], one[m]), m
+    assert np.array_equal(mixed['rf'], one['rf']) and np.array_equal(mixed['euc'], one['euc'])
+    p0, p1 = _lib.condensed_offset(n, 37), _lib.condensed_offset(n, 801)
+    part = ts.pairwise(('wrf', 'geo'), normalise=True, row_begin=37, row_end=801)
+    assert np.array_equal(part['wrf'], one['wrf'][p0:p1]) and np.array_equal(part['geo'], one['geo'][p0:p1])
+    # the square form (squareform() on the device), banded, both kinds of destination
+    for m in ('rf', 'euc', 'geo'):
+        want = squareform(one[m])
+        assert np.array_equal(ts.pairwise_square(m, normalise=True), want), m
+        assert np.array_equal(ts.pairwise_square(m, normalise=True, out=np.full((n, n), -1.0)), want), m
+    monkeypatch.delenv('TREEDIST_BAND_BYTES')
+    assert np.array_equal(ts.pairwise_square('wrf', normalise=True), squareform(one['wrf']))
+    # uint16 RF streamed to the host
+    if kind == 'structured':
+        rf = oracle_mod.matrix(trees, 'rf', nthreads=NTHREADS)
+        monkeypatch.setenv('TREEDIST_BAND_BYTES', str(1 << 16))
+        assert np.array_equal(ts.rf_incidence().astype(np.float64), rf)
+        assert np.array_equal(ts.rf_incidence(out=np.zeros(pairs, dtype=np.uint16)).astype(np.float64), rf)
+        assert np.array_equal(ts.rf_incidence(row_begin=100, row_end=777).astype(np.float64),
+                              rf[_lib.condensed_offset(n, 100):_lib.condensed_offset(n, 777)])
+
+
+def test_drop_in_call_uses_the_square_entry(td, oracle_mod):
+    """Collection.get_inter_tree_distances on one GPU: N x N straight from the library (no scipy squareform), same values."""
+    trees = make('uniform', 257, 20, seed=12)
+    c = td.Collection(records=[td.Record('g%03d' % k, ml_tree=t) for k, t in enumerate(trees)])
+    for metric in ('rf', 'geo'):
+        dm = c.get_inter_tree_distances(metric, normalise=(metric == 'geo'), show_progress=False)
+        want = squareform(oracle_mod.matrix(trees, metric, normalise=(metric == 'geo'), nthreads=NTHREADS))
+        assert dm.values.shape == (257, 257) and dm.get_names() == c.names
+        assert np.array_equal(dm.values, want) if metric == 'rf' else assert_close(dm.values, want) is None
+        two = c.get_inter_tree_distances(metric, normalise=(metric == 'geo'), show_progress=False, devices=[0, 0])
+        assert np.array_equal(two.values, dm.values)
+
+
 def test_baseline_config_2_full_vs_oracle(td, oracle_mod):
     """BASELINE configs[1] = the bench workload (5,000 x 50, seed of bench.py): EVERY entry of the rf, euc and wrf matrices against
     the oracle (12.5 M pairs per metric), plus the size-independent properties."""

@@ -85,6 +85,7 @@ def load():
         lib.td_treeset_deserialize.argtypes = [vp, i64, ctypes.POINTER(vp)]
     if hasattr(lib, 'td_pairwise_square'):
         lib.td_pairwise_square.argtypes = [vp, i32, i32, i32, dbl, vp, i32]
+        lib.td_rf_incidence.argtypes = [vp, i64, i64, vp, i32]
         lib.td_alloc_pinned.argtypes = [i64, ctypes.POINTER(vp)]
         lib.td_free_pinned.argtypes = [vp]
     if hasattr(lib, 'td_check_errors'):         # (absent from older builds loaded through TREEDIST_LIB for A/B timing)
@@ -292,6 +293,17 @@ class TreeSet(object):
             row_end = self.n_trees
         check(self._lib.td_rf_incidence_device(self._h, int(bool(normalise)), int(row_begin), int(row_end),
                                                ctypes.c_void_p(d_out_ptr), int(bool(out_is_u16)), ctypes.c_void_p(stream)))
+
+    def rf_incidence(self, row_begin=0, row_end=None, device=0, out=None):
+        """Exact RF of rows [row_begin, row_end) as uint16, streamed in row bands into host memory (td_rf_incidence)."""
+        if row_end is None:
+            row_end = self.n_trees
+        n = self.n_trees
+        pairs = condensed_offset(n, row_end) - condensed_offset(n, row_begin)
+        arr = out if out is not None else pinned_empty(pairs, np.uint16)
+        assert arr.dtype == np.uint16 and arr.size >= pairs and arr.flags.c_contiguous
+        check(self._lib.td_rf_incidence(self._h, int(row_begin), int(row_end), arr.ctypes.data, int(device)))
+        return arr
 
     def pairwise(self, metrics, normalise=False, min_overlap=4, overlap_fail_value=0.0, row_begin=0, row_end=None,
                  device=0, out=None):

@@ -965,12 +965,9 @@ namespace {
 // two bands stay L2 / HBM friendly, large enough that a band is thousands of tiles
 size_t band_bytes_target()
 {
-    static const size_t v = [] {
-        const char *e = getenv("TREEDIST_BAND_BYTES");
-        if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 10); if (end != e && x >= (1u << 20)) return (size_t)x; }
-        return (size_t)(32u << 20);
-    }();
-    return v;
+    const char *e = getenv("TREEDIST_BAND_BYTES");
+    if (e && *e) { char *end = nullptr; const unsigned long long x = strtoull(e, &end, 10); if (end != e && x >= (1u << 16)) return (size_t)x; }
+    return (size_t)(32u << 20);
 }
 
 bool is_pinned(const void *p)
@@ -1033,12 +1030,15 @@ struct HostCall {                       // everything a host-buffer call owns; r
 
 }  // namespace
 
-int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
-                int64_t row_begin, int64_t row_end, double *const out[4], int device)
+// rows [row_begin, row_end) of the requested matrices into HOST buffers.  u16_rf: metric_mask is RF alone and out[TD_RF] is uint16
+// (the int8 tcgen05 incidence contraction with its packed epilogue, BASELINE config 4); otherwise all outputs are double.
+static int host_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                         int64_t row_begin, int64_t row_end, void *const out[4], bool u16_rf, int device)
 {
     if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
     DeviceScope scope;
     int rc;
+    const size_t esz = u16_rf ? sizeof(uint16_t) : sizeof(double);
     if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
     if ((rc = upload(ts, device, 0))) return rc;        // no-op when already resident
     DeviceSet *dset = resident(ts, device);
@@ -1049,7 +1049,7 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && !out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(device));
 
-    const std::vector<int64_t> cuts = plan_bands(N, row_begin, row_end, (int64_t)(band_bytes_target() / sizeof(double)));
+    const std::vector<int64_t> cuts = plan_bands(N, row_begin, row_end, (int64_t)(band_bytes_target() / esz));
     const int n_bands = (int)cuts.size() - 1;
     int64_t max_band = 0;
     for (int k = 0; k < n_bands; k++) max_band = std::max(max_band, condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]));
@@ -1058,11 +1058,11 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u) {
         pageable[m] = !is_pinned(out[m]); any_pageable |= pageable[m];
         for (int b = 0; b < std::min(n_bands, 2); b++) {
-            cudaError_t e = pool_alloc(device, (size_t)max_band * sizeof(double), &hc.dbuf[b][m], &hc.dsize[b][m]);
-            if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)max_band * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+            cudaError_t e = pool_alloc(device, (size_t)max_band * esz, &hc.dbuf[b][m], &hc.dsize[b][m]);
+            if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)(max_band * esz), cudaGetErrorString(e)); return TD_ERR_NOMEM; }
             if (pageable[m]) {
-                e = pinned_alloc((size_t)max_band * sizeof(double), &hc.stage[b][m]);
-                if (e != cudaSuccess) { set_error("cudaHostAlloc of %lld bytes failed: %s", (long long)max_band * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+                e = pinned_alloc((size_t)max_band * esz, &hc.stage[b][m]);
+                if (e != cudaSuccess) { set_error("cudaHostAlloc of %lld bytes failed: %s", (long long)(max_band * esz), cudaGetErrorString(e)); return TD_ERR_NOMEM; }
             }
         }
     }
@@ -1072,18 +1072,20 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
     auto drain = [&](int k) -> int {                       // host side of band k: wait for its copy, move pageable outputs on
         CUDA_TRY(cudaEventSynchronize(bs.copied[k & 1]));
         const int64_t p0 = condensed_offset(N, cuts[k]) - p_first, n = condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]);
-        for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && pageable[m]) host_copy(out[m] + p0, hc.stage[k & 1][m], (size_t)n * sizeof(double));
+        for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && pageable[m]) host_copy((char *)out[m] + (size_t)p0 * esz, hc.stage[k & 1][m], (size_t)n * esz);
         return TD_OK;
     };
     for (int k = 0; k < n_bands; k++) {
         const int b = k & 1;
         const int64_t p0 = condensed_offset(N, cuts[k]) - p_first, n = condensed_offset(N, cuts[k + 1]) - condensed_offset(N, cuts[k]);
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(bs.compute, bs.copied[b], 0));        // the band buffers are free again
-        if ((rc = run_pairwise(ts, dset, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, cuts[k], cuts[k + 1], hc.dbuf[b], bs.compute))) return rc;
+        if (u16_rf) rc = run_rf_incidence(ts, dset, 0, cuts[k], cuts[k + 1], hc.dbuf[b][TD_RF], 1, bs.compute);
+        else rc = run_pairwise(ts, dset, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, cuts[k], cuts[k + 1], hc.dbuf[b], bs.compute);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(bs.done[b], bs.compute));
         CUDA_TRY(cudaStreamWaitEvent(bs.copy, bs.done[b], 0));
         for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u)
-            CUDA_TRY(cudaMemcpyAsync(pageable[m] ? hc.stage[b][m] : (void *)(out[m] + p0), hc.dbuf[b][m], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, bs.copy));
+            CUDA_TRY(cudaMemcpyAsync(pageable[m] ? hc.stage[b][m] : (void *)((char *)out[m] + (size_t)p0 * esz), hc.dbuf[b][m], (size_t)n * esz, cudaMemcpyDeviceToHost, bs.copy));
         CUDA_TRY(cudaEventRecord(bs.copied[b], bs.copy));
         if (k >= 1 && any_pageable && (rc = drain(k - 1))) return rc;                   // under the kernels / copy of band k
     }
@@ -1094,6 +1096,24 @@ int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_ove
         if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     }
     return take_error_flag(dset);
+}
+
+int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                int64_t row_begin, int64_t row_end, double *const out[4], int device)
+{
+    if (!out) { set_error("null argument"); return TD_ERR_ARG; }
+    void *const o[4] = {out[0], out[1], out[2], out[3]};
+    return host_pairwise(ts, metric_mask, normalise, min_overlap, overlap_fail_value, row_begin, row_end, o, false, device);
+}
+
+int td_rf_incidence(td_treeset *ts, int64_t row_begin, int64_t row_end, uint16_t *out, int device)
+{
+    if (!ts || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    const HostSet &h = ts->host;
+    if (!h.uniform) { set_error("the incidence path needs one shared leaf set"); return TD_ERR_UNSUPPORTED; }
+    if (h.max_splits > 32767) { set_error("too many splits per tree for the u16 epilogue"); return TD_ERR_UNSUPPORTED; }
+    void *const o[4] = {out, nullptr, nullptr, nullptr};
+    return host_pairwise(ts, TD_MASK(TD_RF), 0, 4, 0.0, row_begin, row_end, o, true, device);
 }
 
 int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overlap, double overlap_fail_value, double *out, int device)
