@@ -396,6 +396,7 @@ def test_host_calls_in_row_bands(td, oracle_mod, monkeypatch, kind):
     for m in metrics:
         want = oracle_mod.matrix(trees, m, normalise=True, nthreads=NTHREADS)
         assert np.array_equal(one[m], want) if m == 'rf' else assert_close(one[m], want) is None
+    one_rf_euc = ts.pairwise(('rf', 'euc'), normalise=True)                    # (another template instantiation: compare like with like)
     monkeypatch.setenv('TREEDIST_BAND_BYTES', str(1 << 18))                    # 13 bands
     pinned = ts.pairwise(metrics, normalise=True)
     pageable = ts.pairwise(metrics, normalise=True, out={m: np.full(pairs, -1.0) for m in metrics})
@@ -403,17 +404,18 @@ def test_host_calls_in_row_bands(td, oracle_mod, monkeypatch, kind):
     mixed = ts.pairwise(('rf', 'euc'), normalise=True, out=mixed_out)
     for m in metrics:
         assert np.array_equal(pinned[m], one[m]) and np.array_equal(pageable[m], one[m]), m
-    assert np.array_equal(mixed['rf'], one['rf']) and np.array_equal(mixed['euc'], one['euc'])
+    assert np.array_equal(mixed['rf'], one_rf_euc['rf']) and np.array_equal(mixed['euc'], one_rf_euc['euc'])
     p0, p1 = _lib.condensed_offset(n, 37), _lib.condensed_offset(n, 801)
     part = ts.pairwise(('wrf', 'geo'), normalise=True, row_begin=37, row_end=801)
     assert np.array_equal(part['wrf'], one['wrf'][p0:p1]) and np.array_equal(part['geo'], one['geo'][p0:p1])
     # the square form (squareform() on the device), banded, both kinds of destination
     for m in ('rf', 'euc', 'geo'):
-        want = squareform(one[m])
+        want = squareform(ts.pairwise((m,), normalise=True)[m])               # (a metric alone may run another kernel than in a group: like with like)
+        assert_close(want, squareform(one[m]))
         assert np.array_equal(ts.pairwise_square(m, normalise=True), want), m
         assert np.array_equal(ts.pairwise_square(m, normalise=True, out=np.full((n, n), -1.0)), want), m
     monkeypatch.delenv('TREEDIST_BAND_BYTES')
-    assert np.array_equal(ts.pairwise_square('wrf', normalise=True), squareform(one['wrf']))
+    assert np.array_equal(ts.pairwise_square('wrf', normalise=True), squareform(ts.pairwise(('wrf',), normalise=True)['wrf']))
     # uint16 RF streamed to the host
     if kind == 'structured':
         rf = oracle_mod.matrix(trees, 'rf', nthreads=NTHREADS)

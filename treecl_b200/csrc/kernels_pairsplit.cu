@@ -21,6 +21,7 @@
 //   the incidence contraction.  With ALL shared splits as rows no events are needed at all (the split-extended form of api.cu).
 // (Q + E) subtracts; cells whose correction nearly cancels Q are queued for exact_fixup_kernel, which recomputes them additively in a
 // fixed order: results are bit-reproducible, independent of the row sharding, and identical trees give exactly 0.
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
@@ -32,6 +33,8 @@
 
 #include "kernels.h"
 #include "exact_pair.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace td {
 
@@ -116,6 +119,13 @@ __device__ __forceinline__ FixScale fix_scale(double q)
     return f;
 }
 
+// Programmatic dependent launch: pair_dense_kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization right behind
+// pair_events_kernel, whose CTAs all raise the trigger first thing - so tile CTAs start on SMs the events kernel no longer fills and run
+// their TMA + fp64 tensor-core phase under its tail; griddepcontrol.wait (a no-op in a normal launch) then blocks until the events
+// kernel has completed and its segment table and records are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -135,12 +145,15 @@ __host__ __device__ constexpr int rec_bytes(int wmode) { return wmode == 0 ? 4 :
 
 constexpr int RG = 16;                // trees per row group: one CTA of pair_events_kernel; a 64-row tile reads 64 / RG segments
 
-// One CTA per ROW GROUP of RG consecutive trees: all events (i, j) with i in the group, binned by column tile j / 32.
+// One CLUSTER of P CTAs (P = 1, 2, 4 or 8, chosen at launch so that the grid is at least two waves on any GPU share) per ROW GROUP of RG
+// consecutive trees: all events (i, j) with i in the group, binned by column tile j / 32.  CTA `part` of the cluster owns the shared-list
+// positions pos = part (mod P) of the group's trees.
 //   entries : the group's shared-list entries, each with its position x in the postings; entry (d, i) owns the events
 //             (i, post_tree[b]) for b in (x, post_end[x])
 //   count   : a warp walks EVW entries at a time, lane b takes the b-th later holder of each: no searching, coalesced reads of a
 //             posting list, EVW independent reads in flight per lane; a shared-memory histogram over the column tiles counts them
-//   place   : block scan of the histogram, ONE global atomicAdd claims the group's contiguous range of the event buffer
+//   place   : the CTAs read each other's histograms through distributed shared memory: bin totals, block scan, ONE global atomicAdd
+//             (CTA 0) claims the group's contiguous range of the event buffer; CTA q starts bin c behind the events of CTAs < q
 //   fill    : the same walk again, slots from shared-memory atomics, one aligned record store per event
 // and the (offset, count) of every (row group, column tile) segment goes to the segment table for pair_dense_kernel.
 // Nothing but the range claim touches a global atomic, and there is no separate count / scan / fill launch.
@@ -158,12 +171,16 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     double *ent_len = reinterpret_cast<double *>(ev_smem);                                 // [n_ent]     (weighted only, else unused)
     uint32_t *ent_n = reinterpret_cast<uint32_t *>(ev_smem + (WMODE ? (size_t)n_ent * 8 : 0));     // [n_ent + 1] events of the entry
     int *ent_x = reinterpret_cast<int *>(ent_n + n_ent + 1);                               // [n_ent] position in the postings
-    uint32_t *hist = reinterpret_cast<uint32_t *>(ent_x + n_ent);                          // [ct]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ent_x + n_ent);                          // [ct] this CTA's counts, then its cursors
+    uint32_t *bin_total = hist + ct, *bin_before = bin_total + ct;                         // [ct] events of the whole cluster / of the CTAs before this one
     __shared__ uint32_t warp_sum[EVT / 32];
     __shared__ uint32_t s_base;
 
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned n_parts = cluster.num_blocks(), part = cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rg = blockIdx.x + p.rg0, tree0 = rg * RG;
+    const int rg = (int)(blockIdx.x / n_parts) + p.rg0, tree0 = rg * RG;
+    griddep_launch_dependents();                           // the tile kernel may start filling free SMs (it waits before it reads our output)
 
     // block-wide exclusive scan of one value per thread; returns the exclusive prefix, the total through `total`
     auto block_scan = [&](uint32_t v, uint32_t &total) -> uint32_t {
@@ -181,28 +198,28 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
         return before + incl - v;
     };
 
-    // ---- entries (e = position * RG + local tree) and their sizes ------------------------------------------------------------------------
+    // ---- this CTA's entries (q = m * RG + local tree, shared-list position pos = part + m * n_parts) and their sizes ------------------------
     for (int c = tid; c < ct; c += EVT) hist[c] = 0u;
-    const int per = (n_ent + EVT - 1) / EVT, e_lo = min(tid * per, n_ent), e_hi = min(e_lo + per, n_ent);
-    for (int e = e_lo; e < e_hi; e++) {
-        const int i = tree0 + (e & (RG - 1)), pos = e / RG;
+    const int n_own = ((p.sh_stride - (int)part + (int)n_parts - 1) / (int)n_parts) * RG;
+    for (int q = tid; q < n_own; q += EVT) {
+        const int i = tree0 + (q & (RG - 1)), pos = (q / RG) * (int)n_parts + (int)part;
         int x = -1;
         if (i >= p.row_begin && i < p.row_end) x = p.shared_x[(size_t)i * p.sh_stride + pos];
         if (x >= 0 && p.heavy_rows > 0 && p.shared[(size_t)i * p.sh_stride + pos].pad < (uint32_t)p.heavy_rows) x = -1;    // a row of the matrix, no events
         uint32_t n = 0;
-        if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[e] = p.post_len[x]; }
-        ent_x[e] = x; ent_n[e] = n;
+        if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[q] = p.post_len[x]; }
+        ent_x[q] = x; ent_n[q] = n;
     }
     __syncthreads();
 
     // ---- count: a warp walks EVW entries at a time, lane b takes the b-th later holder of each (no search; EVW independent reads) ----------
-    for (int e0 = warp * EVW; e0 < n_ent; e0 += (EVT / 32) * EVW) {
+    for (int e0 = warp * EVW; e0 < n_own; e0 += (EVT / 32) * EVW) {
         int x[EVW]; uint32_t n[EVW], n_max = 0;
 #pragma unroll
         for (int u = 0; u < EVW; u++) {
             const int e = e0 + u;
             x[u] = -1; n[u] = 0;
-            if (e < n_ent) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
+            if (e < n_own) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
             n_max = max(n_max, n[u]);
         }
         for (uint32_t b = lane; b < n_max; b += 32) {
@@ -215,18 +232,34 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
         }
     }
     __syncthreads();
-    // ---- place: scan the histogram, claim the range, publish the segment table --------------------------------------------------------------
+    // ---- place: bin totals over the cluster, scan, claim the range, publish the segment table --------------------------------------------------
+    cluster.sync();                                        // every CTA's histogram is complete
     {
         const int cper = (ct + EVT - 1) / EVT, c_lo = min(tid * cper, ct), c_hi = min(c_lo + cper, ct);
         uint32_t sum = 0;
-        for (int c = c_lo; c < c_hi; c++) sum += hist[c];
+        for (int c = c_lo; c < c_hi; c++) {
+            uint32_t tot = 0, before = 0;
+            for (unsigned q = 0; q < n_parts; q++) {
+                const uint32_t h = q == part ? hist[c] : *cluster.map_shared_rank(&hist[c], q);
+                if (q < part) before += h;
+                tot += h;
+            }
+            bin_total[c] = tot; bin_before[c] = before; sum += tot;
+        }
         uint32_t total;
         uint32_t at = block_scan(sum, total);
-        if (tid == 0) s_base = total ? atomicAdd(p.ev_cursor, total) : 0u;
-        __syncthreads();
+        if (part == 0 && tid == 0) {
+            const uint32_t base = total ? atomicAdd(p.ev_cursor, total) : 0u;
+            for (unsigned q = 0; q < n_parts; q++) *cluster.map_shared_rank(&s_base, q) = base;
+        }
+        cluster.sync();                                    // s_base has arrived everywhere, nobody reads a remote histogram any more
         at += s_base;
         uint2 *seg = p.seg + (size_t)rg * ct;
-        for (int c = c_lo; c < c_hi; c++) { const uint32_t n = hist[c]; seg[c] = make_uint2(at, n); hist[c] = at; at += n; }
+        for (int c = c_lo; c < c_hi; c++) {
+            const uint32_t n = bin_total[c];
+            if (part == 0) seg[c] = make_uint2(at, n);
+            hist[c] = at + bin_before[c]; at += n;
+        }
     }
     __syncthreads();
     // ---- fill ----------------------------------------------------------------------------------------------------------------------------
@@ -250,13 +283,13 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
             }
         }
     };
-    for (int e0 = warp * EVW; e0 < n_ent; e0 += (EVT / 32) * EVW) {
+    for (int e0 = warp * EVW; e0 < n_own; e0 += (EVT / 32) * EVW) {
         int x[EVW]; uint32_t n[EVW], n_max = 0;
 #pragma unroll
         for (int u = 0; u < EVW; u++) {
             const int e = e0 + u;
             x[u] = -1; n[u] = 0;
-            if (e < n_ent) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
+            if (e < n_own) { x[u] = ent_x[e]; n[u] = ent_n[e]; }
             n_max = max(n_max, n[u]);
         }
         for (uint32_t b = lane; b < n_max; b += 32) {
@@ -358,13 +391,18 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             for (int c = 0; c < NSTAGE && c < n_chunks; c++) issue_chunk(c, c);
         }
     }
-    // this tile's events: one segment per row group
+    // this tile's events: one segment per row group.  The table is the events kernel's output: nothing of it is touched before
+    // griddep_wait() (see above); requested after the first leaf chunk, consumed after the second
     uint2 sg[TR / RG];
-    {
+#pragma unroll
+    for (int q = 0; q < TR / RG; q++) sg[q] = make_uint2(0u, 0u);
+    auto load_segments = [&]() {
+        if (!p.seg) return;                                // no table: no events
+        griddep_wait();
         const uint2 *segp = p.seg + (size_t)(tile_r * (TR / RG)) * p.col_tiles_total + tile_c;
 #pragma unroll
-        for (int q = 0; q < TR / RG; q++) sg[q] = p.seg ? segp[(size_t)q * p.col_tiles_total] : make_uint2(0u, 0u);   // no table: no events
-    }
+        for (int q = 0; q < TR / RG; q++) sg[q] = segp[(size_t)q * p.col_tiles_total];
+    };
     // ---- per-tree scalars: requested now (threads 0..95), parked in registers, put into shared memory just before the epilogue -------
     int sc_s = 0; double sc_q1 = 0.0, sc_q2 = 0.0;
     if (tid < TR + TC) {
@@ -410,7 +448,7 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
 #pragma unroll
         for (int e = 0; e < EVR; e++) { pre[e][0] = make_int4(0, 0, 0, 0); pre[e][1] = pre[e][0]; if (tid + e * NT < n_ev) load_rec(tid + e * NT, pre[e][0], pre[e][1]); }
     };
-    if (!kWeighted || n_chunks == 0) prefetch_events();
+    if (!kWeighted || n_chunks == 0) { load_segments(); prefetch_events(); }
     auto apply_events = [&]() {
 #pragma unroll
         for (int e = 0; e < EVR; e++) if (tid + e * NT < n_ev) apply_rec(pre[e][0], pre[e][1]);
@@ -455,7 +493,8 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
             } else {
                 for (int k0 = 0; k0 < k_here; k0 += 4) step4(k0);
             }
-            if (chunk == 0) prefetch_events();
+            if (chunk == 0) load_segments();
+            if (chunk == (n_chunks > 1 ? 1 : 0)) prefetch_events();
             if (chunk + NSTAGE < n_chunks) {               // refill this stage once every warp is done with it
                 __syncthreads();
                 if (tid == 0) issue_chunk(chunk + NSTAGE, stage);
@@ -593,8 +632,9 @@ __global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_co
 #endif
 }
 
+// pdl: the launch directly follows pair_events_kernel on `st` and may start before it has finished (programmatic dependent launch)
 template <uint32_t MASK, bool RECT>
-cudaError_t launch_dense(const PairParams &p, dim3 grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dense(const PairParams &p, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
 {
     auto k = p.normalise ? pair_dense_kernel<MASK, RECT, true> : pair_dense_kernel<MASK, RECT, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -602,33 +642,43 @@ cudaError_t launch_dense(const PairParams &p, dim3 grid, size_t smem, cudaStream
     CUtensorMap ma, mb;
     if (p.tmap_a && p.tmap_b) { memcpy(&ma, p.tmap_a, sizeof ma); memcpy(&mb, p.tmap_b, sizeof mb); }
     else { if (MASK & 6u) return cudaErrorInvalidValue; memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb); }
-    k<<<grid, NT, smem, st>>>(p, ma, mb);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, p, ma, mb);
 }
 
 template <bool RECT>
-cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, dim3 grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dense_mask(uint32_t mask, const PairParams &p, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
 {
     switch (mask & 7u) {
-        case 1: return launch_dense<1, RECT>(p, grid, smem, st);
-        case 2: return launch_dense<2, RECT>(p, grid, smem, st);
-        case 3: return launch_dense<3, RECT>(p, grid, smem, st);
-        case 4: return launch_dense<4, RECT>(p, grid, smem, st);
-        case 5: return launch_dense<5, RECT>(p, grid, smem, st);
-        case 6: return launch_dense<6, RECT>(p, grid, smem, st);
-        case 7: return launch_dense<7, RECT>(p, grid, smem, st);
+        case 1: return launch_dense<1, RECT>(p, grid, smem, st, pdl);
+        case 2: return launch_dense<2, RECT>(p, grid, smem, st, pdl);
+        case 3: return launch_dense<3, RECT>(p, grid, smem, st, pdl);
+        case 4: return launch_dense<4, RECT>(p, grid, smem, st, pdl);
+        case 5: return launch_dense<5, RECT>(p, grid, smem, st, pdl);
+        case 6: return launch_dense<6, RECT>(p, grid, smem, st, pdl);
+        case 7: return launch_dense<7, RECT>(p, grid, smem, st, pdl);
     }
     return cudaErrorInvalidValue;
 }
 
 template <bool RECT>
-cudaError_t launch_events(int wmode, const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
+cudaError_t launch_events(int wmode, const PairParams &p, unsigned groups, unsigned parts, size_t smem, cudaStream_t st)
 {
     auto run = [&](auto k) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, EVT, smem, st>>>(p);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(groups * parts); cfg.blockDim = dim3(EVT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = parts; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k, p);
     };
     switch (wmode) {
         case 0: return run(pair_events_kernel<0, RECT>);
@@ -722,20 +772,22 @@ long long pairsplit_tiles(bool rect, PairParams &p)
 size_t pairsplit_events_smem_bytes(uint32_t mask, int sh_stride, int col_tiles_total)
 {
     const size_t n_ent = (size_t)RG * sh_stride;
-    return (wmode_of(mask) ? n_ent * 8 : 0) + (n_ent + 1) * 4 + n_ent * 4 + (size_t)col_tiles_total * 4 + 16;
+    return (wmode_of(mask) ? n_ent * 8 : 0) + (n_ent + 1) * 4 + n_ent * 4 + (size_t)col_tiles_total * 12 + 16;
 }
 int pairsplit_row_group() { return RG; }
 
 // the tile kernel alone (p carries the tile geometry; p.seg == nullptr: no events)
-cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st)
+static cudaError_t launch_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st, bool pdl)
 {
     if (p.n_tiles <= 0) return cudaSuccess;
     const size_t smem_d = pairsplit_dense_smem_bytes(mask);
     // rectangular: (column tiles, tile rows); triangular: tile rows u and R-1-u folded into one grid row
     const dim3 grid = rect ? dim3((unsigned)p.tiles_x, (unsigned)p.tri_rows)
                            : dim3((unsigned)(2 * (p.tiles_x - 2 * p.tile_row0) - 2 * (p.tri_rows - 1)), (unsigned)((p.tri_rows + 1) / 2));
-    return rect ? launch_dense_mask<true>(mask, p, grid, smem_d, st) : launch_dense_mask<false>(mask, p, grid, smem_d, st);
+    return rect ? launch_dense_mask<true>(mask, p, grid, smem_d, st, pdl) : launch_dense_mask<false>(mask, p, grid, smem_d, st, pdl);
 }
+
+cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st) { return launch_tiles(mask, rect, p, st, false); }
 
 // p must carry the tile geometry (pairsplit_tiles), the postings, the segment table and the event buffer; *ev_cursor must be zero
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches)
@@ -756,11 +808,17 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         // the segment table completely, rows outside [row_begin, row_end) as empty segments
         const long long groups = (long long)p.tri_rows * (TR / RG);
         const size_t smem_e = pairsplit_events_smem_bytes(mask, p.sh_stride, p.col_tiles_total);
-        e = checked(rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, smem_e, st), "pair_events_kernel");
+        // CTAs per row group (a thread-block cluster): at least two waves of 2 CTAs per SM whatever share of the rows this launch has
+        unsigned parts = 1;
+        if (const char *f = getenv("TREEDIST_EVENT_PARTS")) parts = (unsigned)atoi(f);
+        else while (parts < 8 && groups * parts < 4ll * n_sms) parts *= 2;
+        if (parts != 1 && parts != 2 && parts != 4 && parts != 8) parts = 1;
+        e = checked(rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st), "pair_events_kernel");
         ++*launches;
         if (e != cudaSuccess) return e;
     }
-    e = checked(launch_pairsplit_tiles(mask, rect, p, st), "pair_dense_kernel");
+    static const bool no_pdl = getenv("TREEDIST_NO_PDL") != nullptr;
+    e = checked(launch_tiles(mask, rect, p, st, !no_pdl && !sync_debug), "pair_dense_kernel");
     ++*launches;
     if (e != cudaSuccess || !weighted) return e;
     ++*launches;
