@@ -148,6 +148,9 @@ CASES = [
     (97, 64, 'uniform'), (70, 65, 'uniform'), (66, 100, 'uniform'), (40, 200, 'uniform'),
     (150, 30, 'structured'), (100, 100, 'structured'),
     (333, 12, 'uniform'),          # five tile rows, N not a multiple of 16 / 32 / 64, many common splits per pair
+    # more than 255 shared splits per tree (byte counters of the tile kernel: rf from the incidence contraction) and lists too long
+    # for the shared-memory merge kernel (big-tree kernel as the last resort): no tree size is refused
+    (40, 300, 'structured'), (24, 300, 'uniform'), (20, 520, 'structured'),
 ]
 
 
@@ -203,7 +206,9 @@ def test_rf_wrf_euc_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm, pair_
 @pytest.mark.parametrize('n_trees,n_taxa,kind', [(2, 4, 'uniform'), (3, 5, 'uniform'), (120, 10, 'uniform'),
                                                  (150, 20, 'uniform'), (200, 30, 'uniform'), (60, 35, 'uniform'),
                                                  (50, 50, 'uniform'), (30, 67, 'uniform'), (24, 100, 'uniform'), (16, 131, 'uniform'),
-                                                 (150, 30, 'structured'), (60, 60, 'structured'), (40, 120, 'structured')])
+                                                 (150, 30, 'structured'), (60, 60, 'structured'), (40, 120, 'structured'),
+                                                 # more than 128 internal edges per tree: the big-tree kernel (no size limit, as in the reference)
+                                                 (16, 132, 'uniform'), (16, 200, 'uniform'), (8, 300, 'uniform'), (24, 200, 'structured'), (6, 520, 'structured')])
 @pytest.mark.parametrize('norm', [False, True])
 def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     from treecl_b200 import _lib
@@ -216,7 +221,7 @@ def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     assert st['pairs'] == n_trees * (n_trees - 1) // 2 and st['ratios'] >= 0
 
 
-@pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30), (110, 16)])
+@pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30), (110, 16), (160, 14), (260, 10)])
 @pytest.mark.parametrize('norm', [False, True])
 def test_different_leaf_sets_vs_oracle(td, oracle_mod, n_taxa, n_trees, norm):
     """Pairs with different leaf sets (restrict-then-join kernel) against the oracle's tree-level pruning.

@@ -241,6 +241,11 @@ struct DeviceSet {
     size_t ev_block_bytes = 0, ev_block_got = 0;
     cudaEvent_t ev_done = nullptr;
     int *error_flag = nullptr;
+    // per-warp scratch of the big-tree kernel (one launch at a time per set: later launches wait on big_done)
+    std::mutex big_mu;
+    unsigned char *big_scratch = nullptr;
+    size_t big_bytes = 0, big_got = 0;
+    cudaEvent_t big_done = nullptr;
     size_t max_smem_optin = 0;
     td_geo_stats geo_stats{};
     std::vector<std::pair<size_t, void *>> allocs;      // pool blocks owned by this set
@@ -275,6 +280,8 @@ static void free_device(DeviceSet *d)
     for (auto &b : d->allocs) pool_free(d->device, b.second, b.first);
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev_block) pool_free(d->device, d->ev_block, d->ev_block_got);
+    if (d->big_done) cudaEventDestroy(d->big_done);
+    if (d->big_scratch) pool_free(d->device, d->big_scratch, d->big_got);
     if (cur >= 0) cudaSetDevice(cur);
     delete d;
 }
@@ -453,7 +460,8 @@ static bool hybrid_applies(const HostSet &h, const DeviceSet *d, uint32_t m3, bo
 }
 
 // postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
-static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, void *const d_out[4], cudaStream_t st)
+static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, void *const d_out[4], cudaStream_t st,
+                         bool rf_apart = false)
 {
     const long long tiles = pairsplit_tiles(rect, p);
     if (tiles <= 0) return TD_OK;
@@ -501,9 +509,11 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
         p.q1 = d->q1_light;                                   // wrf: the heavy splits are part of the L1 sum over the rows
         mk = m3 & 6u;                                         // rf comes from the incidence contraction (the events only count light splits)
     }
+    if (rf_apart) mk = m3 & 6u;                               // more common splits than a byte counts: rf from the incidence contraction as well
+    int launches = 0;
+    if (mk) {
     CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
     CUDA_TRY(cudaMemsetAsync(p.ev_cursor, 0, sizeof(uint32_t), st));
-    int launches = 0;
     unsigned long long *trace = nullptr;
     const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
     if (trace_path) { CUDA_TRY(cudaMalloc(&trace, (size_t)tiles * 64)); CUDA_TRY(cudaMemsetAsync(trace, 0, (size_t)tiles * 64, st)); p.trace = trace; }
@@ -516,8 +526,9 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
         if (FILE *f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, host.size(), f); fclose(f); }
     }
     CUDA_TRY(cudaEventRecord(d->ev_done, st));
+    }
     launch_counter_add(launches);
-    if (hybrid && (m3 & 1u)) {
+    if ((hybrid || rf_apart) && (m3 & 1u)) {
         if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
         int rc = run_rf_incidence(ts, d, p.normalise, p.row_begin, p.row_end, d_out[TD_RF], 0, st);
         if (rc) return rc;
@@ -613,13 +624,47 @@ static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams 
     return TD_OK;
 }
 
+// Trees with more than 128 internal edges (or more than 3 mask words): the big-tree kernel, whose per-split state lives in a per-warp
+// slab of global memory.  g carries the pair range and the outputs (g.outs / g.metric_mask).
+constexpr size_t kBigScratchBudget = 6ull << 30;
+
+static int run_bigtree(td_treeset *ts, DeviceSet *d, GeoParams &g, int general, cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    if (h.max_splits > bigtree_max_splits() || h.W > 64) {
+        set_error("trees with %d internal edges over %d taxa (%d mask words) exceed the big-tree kernel (at most %d internal edges, 4096 taxa)",
+                  h.max_splits, h.n_taxa, h.W, bigtree_max_splits());
+        return TD_ERR_UNSUPPORTED;
+    }
+    const size_t warp_bytes = bigtree_warp_bytes(h.max_splits, h.W, h.n_taxa);
+    const int blocks = bigtree_blocks(g.p_end - g.p_begin, d->sm_count, warp_bytes, kBigScratchBudget);
+    const size_t need = warp_bytes * 4 * (size_t)blocks;
+    std::lock_guard<std::mutex> guard(d->big_mu);
+    if (!d->big_done) CUDA_TRY(cudaEventCreateWithFlags(&d->big_done, cudaEventDisableTiming));
+    if (need > d->big_bytes) {
+        CUDA_TRY(cudaEventSynchronize(d->big_done));
+        if (d->big_scratch) pool_free(d->device, d->big_scratch, d->big_got);
+        d->big_scratch = nullptr; d->big_bytes = 0;
+        void *blk = nullptr; size_t got = 0;
+        cudaError_t e = pool_alloc(d->device, need, &blk, &got);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes of big-tree scratch failed: %s", (long long)need, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+        d->big_scratch = (unsigned char *)blk; d->big_bytes = need; d->big_got = got;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(st, d->big_done, 0));
+    CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(launch_bigtree(g, general, h.max_splits, d->big_scratch, blocks, st));
+    CUDA_TRY(cudaEventRecord(d->big_done, st));
+    launch_counter_add(1);
+    return TD_OK;
+}
+
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
     const HostSet &h = ts->host;
+    const bool big = h.max_splits > 128 || h.W > 3;
     if (!h.uniform) {
         // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
-        if (h.max_splits > 128 || h.W > 3) { set_error("the restrict-then-join kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         CUDA_TRY(cudaSetDevice(d->device));
         { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
         GeoParams g{};
@@ -635,6 +680,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
         if (g.p_end > g.p_begin) {
+            if (big) return run_bigtree(ts, d, g, 1, st);
             CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
             CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
             launch_counter_add(1);
@@ -654,7 +700,11 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                                && pairjoin_smem_bytes(m3, slots) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         // events the postings pipeline can generate at most: all (pair, common split) incidences, minus those of the heavy rows in its hybrid form
         const int64_t ev_capacity = std::max<int64_t>(h.total_common - (hybrid_applies(h, d, m3, rect) ? h.heavy_events : 0), 1);
-        const bool split_fits = h.max_shared <= 255 && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
+        // the tile kernel counts a pair's common splits in one byte per cell: with more than 255 shared splits per tree RF has to come from
+        // the incidence contraction (int32 accumulators), as in the hybrid form; without RF the counters are not read at all
+        const bool rf_apart = (m3 & 1u) && h.max_shared > 255 && !hybrid_applies(h, d, m3, rect);
+        const bool rf_apart_ok = !rf_apart || (!rect && rf_incidence_fits(h) && h.dict_shared > 0);
+        const bool split_fits = rf_apart_ok && (d->leaf_maps || !weighted) && ev_capacity < (1ll << 31) && split_event_bytes(d, ev_capacity, 32) <= kEventBytesMax
                                 && pairsplit_events_smem_bytes(m3, d->sh_stride, (int)((d->N + 31) / 32)) <= std::min<size_t>(d->max_smem_optin, 200 * 1024);
         // Kernel choice by a cost model in picoseconds per pair, calibrated on one B200 (tools/kernel_choice.py, tools/rf_dense_sharing.py):
         //   postings pipeline      11 + 13.4 x (expected common splits per pair): work follows the events; in its hybrid form the
@@ -692,7 +742,23 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
             goto geodesic;
         }
         const int tile = (use_join || use_ext) ? 64 : pick_tile(d, weighted);
-        if (!tile) { set_error("shared-split lists too long for the shared-memory merge kernel (stride %d)", d->sh_stride); return TD_ERR_UNSUPPORTED; }
+        if (!tile) {
+            // lists too long for the shared-memory merge kernel and no other form applies: the big-tree kernel (one warp per pair) serves
+            // rf / wrf / euc as well - slower, but no tree size is refused
+            CUDA_TRY(cudaSetDevice(d->device));
+            { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
+            GeoParams g{};
+            g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
+            g.leafmask = d->leafmask; g.rooted = d->rooted;
+            g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);
+            g.metric_mask = m3; g.min_overlap = min_overlap; g.fail_value = fail_value;
+            for (int m = 0; m < 3; m++) { g.outs[m] = (double *)d_out[m]; if ((m3 >> m & 1u) && !g.outs[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; } }
+            g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
+            if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
+            else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
+            if (g.p_end > g.p_begin) { int rc = run_bigtree(ts, d, g, 0, st); if (rc) return rc; }
+            goto geodesic;
+        }
         PairParams p{};
         p.leafT = d->leafT; p.ldT = d->Npad; p.shared = d->shared; p.sh_stride = d->sh_stride; p.nsplits = d->nsplits; p.nshared = d->nshared;
         p.sum_len = d->sum_len; p.norm = d->norm; p.single_l1 = d->single_l1; p.single_l2 = d->single_l2;
@@ -718,7 +784,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                 CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
             }
             if (use_ext) { int rc = run_split_rows(ts, d, m3, p, d_out, st); if (rc) return rc; }
-            else if (use_split) { int rc = run_pairsplit(ts, d, m3, rect, p, ev_capacity, d_out, st); if (rc) return rc; }
+            else if (use_split) { int rc = run_pairsplit(ts, d, m3, rect, p, ev_capacity, d_out, st, rf_apart); if (rc) return rc; }
             else {
                 if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
                 else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
@@ -729,7 +795,6 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
 geodesic:
     if (mask & TD_MASK(TD_GEO)) {
         if (!d_out[TD_GEO]) { set_error("output pointer for the geodesic metric is null"); return TD_ERR_ARG; }
-        if (h.max_splits > 128 || h.W > 3) { set_error("geodesic kernel holds at most 128 internal edges per tree (got %d)", h.max_splits); return TD_ERR_UNSUPPORTED; }
         { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
         GeoParams g{};
         g.ids = d->ids; g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
@@ -737,7 +802,10 @@ geodesic:
         g.out = (double *)d_out[TD_GEO]; g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
         if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
-        if (g.p_end > g.p_begin) {
+        if (g.p_end > g.p_begin && big) {
+            g.outs[3] = g.out; g.metric_mask = 8u;
+            int rc = run_bigtree(ts, d, g, 0, st); if (rc) return rc;
+        } else if (g.p_end > g.p_begin) {
             CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
             CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
             launch_counter_add(1);

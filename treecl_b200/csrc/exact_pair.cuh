@@ -9,7 +9,7 @@
 
 namespace td {
 
-static __device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2)
+static __device__ __forceinline__ void exact_pair_inline(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2)
 {
     s1 = 0.0; s2 = 0.0;
     const SplitRec *A = p.shared + i * p.sh_stride, *B = p.shared + j * p.sh_stride;
@@ -29,5 +29,8 @@ static __device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, i
         s1 += fabs(d); s2 = fma(d, d, s2);
     }
 }
+
+// out-of-line form for the tile kernels (rare path; keeps their register allocation free of it)
+static __device__ __noinline__ void exact_pair(const PairParams &p, int64_t i, int64_t j, double &s1, double &s2) { exact_pair_inline(p, i, j, s1, s2); }
 
 }  // namespace td

@@ -103,6 +103,12 @@ size_t geodesic_smem_bytes(int cap, int W, int warps);
 // pairs with different leaf sets (non-uniform sets): restrict-then-join, all four metrics
 cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
 
+// trees with more than 128 internal edges (kernels_bigtrees.cu): all four metrics, same or different leaf sets, per-warp global scratch
+size_t bigtree_warp_bytes(int max_splits, int W, int n_taxa);
+int bigtree_max_splits();
+int bigtree_blocks(int64_t pairs, int n_sms, size_t warp_bytes, size_t scratch_budget);
+cudaError_t launch_bigtree(const GeoParams &g, int general, int max_splits, unsigned char *scratch, int blocks, cudaStream_t st);
+
 // int8 tcgen05 split-incidence RF (kernels_incidence.cu)
 size_t incidence_smem_bytes();
 int incidence_tile();

@@ -671,14 +671,14 @@ __global__ void __launch_bounds__(NTP, 2) pairjoin_persistent(const PairParams p
 // Recompute the queued pairs additively (no Q + E subtraction) and overwrite their wrf / euc entries.  One thread per pair running
 // exact_pair() - the very function a tile kernel falls back to when the work list is full, so a pair gets the same bits either way.
 template <bool RECT>
-__global__ void __launch_bounds__(128) exact_fixup_kernel(const PairParams p, const uint32_t mask)
+__global__ void __launch_bounds__(256) exact_fixup_kernel(const PairParams p, const uint32_t mask)
 {
     const unsigned n = min(*p.wl_count, p.wl_capacity);
     for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
         const int2 ij = p.wl_pairs[w];
         const int64_t i = ij.x, j = ij.y;
         double s1, s2;
-        exact_pair(p, i, j, s1, s2);
+        exact_pair_inline(p, i, j, s1, s2);                // (inlined: a call would give this usually empty kernel a stack frame)
         const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
         if (mask & 2u) {
             double v = s1;
@@ -781,8 +781,9 @@ size_t pairjoin_smem_bytes(uint32_t mask, int table_slots)
 
 cudaError_t launch_exact_fixup(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st)
 {
-    if (rect) exact_fixup_kernel<true><<<8 * n_sms, 128, 0, st>>>(p, mask);
-    else exact_fixup_kernel<false><<<8 * n_sms, 128, 0, st>>>(p, mask);
+    // two CTAs per SM (grid-stride over the work list): the list is empty for ordinary data, the launch has to cost next to nothing
+    if (rect) exact_fixup_kernel<true><<<2 * n_sms, 256, 0, st>>>(p, mask);
+    else exact_fixup_kernel<false><<<2 * n_sms, 256, 0, st>>>(p, mask);
     return cudaGetLastError();
 }
 
