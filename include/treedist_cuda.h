@@ -188,6 +188,28 @@ int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int
  * device-to-host copy of band k - 1 (BASELINE config 4: "tiles streamed to pinned host").  Pinned `out` (td_alloc_pinned): direct copies. */
 int td_rf_incidence(td_treeset *ts, int64_t row_begin, int64_t row_end, uint16_t *out, int device);
 
+/* ---- consumers of the matrix on the device ------------------------------------------------------- */
+
+/* Classical multidimensional scaling, DistanceMatrix.embedding(dimensions, 'cmds') of the reference:
+ *     double_centre                treeCl/distance_matrix.py:58-74     B = -1/2 J D^2 J
+ *     eigen                        treeCl/distance_matrix.py:285-298   eigenvalues descending (np.linalg.eigh)
+ *     _embedding_classical_mds     treeCl/distance_matrix.py:301-315   coords = evecs[:, :dims] * sqrt(|vals[:dims]|)
+ * but only the `dimensions` leading eigenpairs are computed (blocked subspace iteration with Rayleigh-Ritz on the fp64 tensor cores),
+ * and in td_cmds the N x N matrix never leaves the GPU: only the N x dimensions embedding does.  Eigenvectors are defined up to sign, as
+ * with eigh.  1 <= dimensions <= 12.  The iteration stops when the leading eigenvalues move by less than `tol` (relative; <= 0: 1e-13) twice in a
+ * row, or after max_iter (<= 0: 2000) products; *iterations / *residual (last relative eigenvalue change) report how it ended - a
+ * matrix whose leading eigenvalues are (nearly) degenerate, e.g. independent random trees, converges slowly and has no well-defined
+ * embedding in the reference either.
+ *   td_cmds_device : condensed matrix already on the device (output of td_pairwise_device), coordinates stay on the device
+ *   td_cmds        : distances of `metric` computed on the device, embedded there; coords[n_trees * dimensions] (row-major), host
+ *   td_cmds_host   : square symmetric matrix in host memory (what DistanceMatrix.to_array() holds) */
+int td_cmds_device(const double *d_condensed, int64_t n_trees, int dimensions, double *d_coords, double *eigenvalues, int max_iter, double tol,
+                   int *iterations, double *residual, void *stream);
+int td_cmds(td_treeset *ts, int metric, int normalise, int min_overlap, double overlap_fail_value, int dimensions, double *coords,
+            double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device);
+int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol,
+                 int *iterations, double *residual, int device);
+
 /* Counters of the last geodesic launch on this set (mean GTP iterations etc.), for DESIGN.md / bench.py. */
 typedef struct {
     uint64_t pairs, maxflow_solves, ratios, augmentations, launches;

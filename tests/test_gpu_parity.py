@@ -444,6 +444,64 @@ def test_drop_in_call_uses_the_square_entry(td, oracle_mod):
         assert np.array_equal(two.values, dm.values)
 
 
+class TestClassicalMDS:
+    """SURVEY 8(f)-3, first slice: DistanceMatrix.embedding(dims, 'cmds') with the matrix on the device - double-centring and the leading
+    eigenpairs by blocked subspace iteration on the fp64 tensor cores.  Eigenvalues <= 1e-8 relative, coordinates up to the sign of each
+    axis."""
+
+    @staticmethod
+    def check(coords, vals, want_coords, want_vals, dims):
+        want_vals = np.asarray(want_vals)[:dims]
+        assert np.all(np.abs(vals - want_vals) <= 1e-8 * np.abs(want_vals)), (vals, want_vals)
+        scale = np.abs(want_coords).max()
+        for j in range(dims):
+            s = np.sign(np.dot(coords[:, j], want_coords[:, j]))
+            assert np.allclose(s * coords[:, j], want_coords[:, j], rtol=0, atol=1e-6 * scale), j
+
+    def test_reference_goldens(self, td):
+        """tests/golden/mds_golden.json: outputs of the reference's own functions (treeCl/distance_matrix.py:58-74,285-315)."""
+        import json
+        from treecl_b200 import _lib
+        with open(os.path.join(GOLDEN, 'mds_golden.json')) as fh:
+            cases = json.load(fh)
+        for name, c in cases.items():
+            m, dims = np.array(c['matrix']), c['dimensions']
+            coords, vals, info = _lib.cmds_host(m, dims)
+            self.check(coords, vals, np.array(c['coords']), c['eigenvalues'], dims)
+            dm = td.DistanceMatrix.from_array(m, ['n%d' % k for k in range(len(m))])
+            emb = dm.embedding(dims, 'cmds')
+            assert emb.values.shape == (len(m), dims) and list(emb.df.index) == dm.get_names()
+            assert np.array_equal(emb.values, coords)
+        with pytest.raises(NotImplementedError):
+            dm.embedding(3, 'spectral')
+        with pytest.raises(td.OptionError):
+            dm.embedding(3, 'nope')
+
+    @pytest.mark.parametrize('n_trees,n_taxa,metric,dims', [(300, 24, 'euc', 3), (777, 40, 'geo', 4), (1500, 30, 'rf', 5)])
+    def test_tree_sets_never_leave_the_device(self, td, oracle_mod, n_trees, n_taxa, metric, dims):
+        """td_cmds: distances -> square -> double-centre -> eigenpairs all on the GPU, against the oracle chain on the oracle's matrix."""
+        from treecl_b200 import _lib, synth
+        trees = synth.structured_trees(n_trees, n_taxa, n_classes=dims + 2, class_nni=n_taxa // 3, lam=0.7, seed=41 + dims)
+        ts = _lib.TreeSet(trees)
+        coords, vals, info = ts.cmds(metric, dims)
+        want_coords, want_vals = oracle_mod.mds.classical_mds(squareform(oracle_mod.matrix(trees, metric, nthreads=NTHREADS)), dims)
+        assert info['iterations'] < 2000, info
+        self.check(coords, vals, want_coords, want_vals, dims)
+        # the same through the device-pointer entry on the library's own condensed matrix
+        import torch
+        pairs = n_trees * (n_trees - 1) // 2
+        d = torch.empty(pairs, dtype=torch.float64, device='cuda:0')
+        ts.upload(0)
+        st = torch.cuda.current_stream().cuda_stream
+        ts.pairwise_device((metric,), {metric: d.data_ptr()}, stream=st)
+        out = torch.empty(n_trees * dims, dtype=torch.float64, device='cuda:0')
+        v2 = np.empty(dims)
+        import ctypes
+        it, res = ctypes.c_int(), ctypes.c_double()
+        _lib.check(_lib.load().td_cmds_device(d.data_ptr(), n_trees, dims, out.data_ptr(), v2.ctypes.data, 0, 0.0, ctypes.byref(it), ctypes.byref(res), st))
+        assert np.array_equal(v2, vals) and np.array_equal(out.cpu().numpy().reshape(n_trees, dims), coords)
+
+
 def test_baseline_config_2_full_vs_oracle(td, oracle_mod):
     """BASELINE configs[1] = the bench workload (5,000 x 50, seed of bench.py): EVERY entry of the rf, euc and wrf matrices against
     the oracle (12.5 M pairs per metric), plus the size-independent properties."""

@@ -81,3 +81,26 @@ def test_metric_axioms_small(oracle_mod):
     # geodesic is squeezed between the Euclidean lower bound and the cone path
     geo = oracle_mod.matrix(trees, 'geo'); euc = oracle_mod.matrix(trees, 'euc')
     assert (geo >= euc - 1e-12).all()
+
+
+def test_mds_restatement_matches_the_reference_functions():
+    """oracle/mds.py against tests/golden/mds_golden.json = outputs of the reference's own double_centre / eigen /
+    _embedding_classical_mds (treeCl/distance_matrix.py:58-74,285-298,301-315), produced by tests/golden/make_mds_golden.py."""
+    import json
+    import oracle
+    with open(os.path.join(GOLDEN, 'mds_golden.json')) as fh:
+        cases = json.load(fh)
+    assert set(cases) == {'geo_dm_15', 'clustered_64'}
+    for name, c in cases.items():
+        m, dims = np.array(c['matrix']), c['dimensions']
+        dbc = oracle.mds.double_centre(m)
+        assert np.allclose(dbc, np.array(c['double_centre']), rtol=1e-13, atol=1e-13), name
+        vals, vecs = oracle.mds.eigen(dbc)
+        want_vals = np.array(c['eigenvalues'])
+        assert np.allclose(vals, want_vals, rtol=1e-10, atol=1e-10 * abs(want_vals).max()), name
+        coords, _ = oracle.mds.classical_mds(m, dims)
+        want = np.array(c['coords'])
+        # eigenvectors are defined up to sign: compare column by column after aligning the signs
+        for j in range(dims):
+            s = np.sign(np.dot(coords[:, j], want[:, j]))
+            assert np.allclose(s * coords[:, j], want[:, j], rtol=1e-8, atol=1e-9 * abs(want).max()), (name, j)

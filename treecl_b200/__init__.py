@@ -9,7 +9,7 @@ Everything is computed by libtreedist_cuda.so (hand-written sm_100a kernels); th
 """
 from . import kendallcolijn, parutils, tasks, treedist  # noqa: F401
 from .collection import Collection, Record  # noqa: F401
-from .distance_matrix import DistanceMatrix  # noqa: F401
+from .distance_matrix import CoordinateMatrix, DistanceMatrix  # noqa: F401
 from .errors import OptionError  # noqa: F401
 from .tree import Tree  # noqa: F401
 

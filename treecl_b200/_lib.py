@@ -88,6 +88,11 @@ def load():
         lib.td_rf_incidence.argtypes = [vp, i64, i64, vp, i32]
         lib.td_alloc_pinned.argtypes = [i64, ctypes.POINTER(vp)]
         lib.td_free_pinned.argtypes = [vp]
+    if hasattr(lib, 'td_cmds'):
+        pd_, pi_ = ctypes.POINTER(dbl), ctypes.POINTER(i32)
+        lib.td_cmds_device.argtypes = [vp, i64, i32, vp, vp, i32, dbl, pi_, pd_, vp]
+        lib.td_cmds.argtypes = [vp, i32, i32, i32, dbl, i32, vp, vp, i32, dbl, pi_, pd_, i32]
+        lib.td_cmds_host.argtypes = [vp, i64, i32, vp, vp, i32, dbl, pi_, pd_, i32]
     if hasattr(lib, 'td_check_errors'):         # (absent from older builds loaded through TREEDIST_LIB for A/B timing)
         lib.td_check_errors.argtypes = [vp, i32]
         lib.td_trim_cache.argtypes = [i32]
@@ -332,6 +337,17 @@ class TreeSet(object):
                                            arr.ctypes.data, int(device)))
         return arr
 
+    def cmds(self, metric, dimensions=3, normalise=False, min_overlap=4, overlap_fail_value=0.0, max_iter=0, tol=0.0, device=0):
+        """Classical MDS embedding of the `metric` matrix, computed where the matrix is: distances, double-centring and the leading
+        eigenpairs all stay on the GPU, only the N x dimensions coordinates come back (td_cmds; treeCl/distance_matrix.py:301-315).
+        Returns (coords, eigenvalues, info)."""
+        coords = np.empty((self.n_trees, int(dimensions)), dtype=np.float64)
+        vals = np.empty(int(dimensions), dtype=np.float64)
+        it, res = ctypes.c_int(), ctypes.c_double()
+        check(self._lib.td_cmds(self._h, METRIC_INDEX[metric], int(bool(normalise)), int(min_overlap), float(overlap_fail_value), int(dimensions),
+                                coords.ctypes.data, vals.ctypes.data, int(max_iter), float(tol), ctypes.byref(it), ctypes.byref(res), int(device)))
+        return coords, vals, {'iterations': it.value, 'last_relative_change': res.value}
+
     def check_errors(self, device=0):
         """After pairwise_device / pairwise_rect_device and a stream synchronise: raises if a launch flagged an error (mixed rooting,
         geodesic iteration cap); clears the flag."""
@@ -368,6 +384,20 @@ def device_count():
     c = ctypes.c_int()
     load().td_device_count(ctypes.byref(c))
     return c.value
+
+
+def cmds_host(square, dimensions=3, max_iter=0, tol=0.0, device=0):
+    """Classical MDS of a square symmetric distance matrix held in host memory (td_cmds_host).  Returns (coords, eigenvalues, info)."""
+    lib = load()
+    sq = np.ascontiguousarray(square, dtype=np.float64)
+    assert sq.ndim == 2 and sq.shape[0] == sq.shape[1]
+    n = sq.shape[0]
+    coords = np.empty((n, int(dimensions)), dtype=np.float64)
+    vals = np.empty(int(dimensions), dtype=np.float64)
+    it, res = ctypes.c_int(), ctypes.c_double()
+    check(lib.td_cmds_host(sq.ctypes.data, n, int(dimensions), coords.ctypes.data, vals.ctypes.data, int(max_iter), float(tol),
+                           ctypes.byref(it), ctypes.byref(res), int(device)))
+    return coords, vals, {'iterations': it.value, 'last_relative_change': res.value}
 
 
 def trim_cache(device=-1):

@@ -1241,6 +1241,85 @@ int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overla
     return take_error_flag(dset);
 }
 
+// ---- classical MDS of a device-resident matrix --------------------------------------------------------------------------------
+namespace {
+// cond: condensed matrix on `device` (rows 0..n); coords: n x dims on the device.  Synchronous.
+int cmds_on_device(int device, const double *cond, const double *square_host, int64_t n, int dims, double *d_coords, double *eigenvalues, int max_iter,
+                   double tol, int *iterations, double *residual, cudaStream_t st)
+{
+    if (n < 2 || dims < 1 || dims > cmds_block() - 4 || dims >= n) { set_error("cmds: need 1 <= dimensions <= %d and dimensions < n_trees", cmds_block() - 4); return TD_ERR_ARG; }
+    if (max_iter <= 0) max_iter = 2000;
+    if (!(tol > 0.0)) tol = 1e-13;
+    struct Own { int device; void *sq = nullptr, *work = nullptr, *pin = nullptr; size_t sq_got = 0, work_got = 0;
+                 ~Own() { if (sq) pool_free(device, sq, sq_got); if (work) pool_free(device, work, work_got); pinned_free(pin); } } own{device};
+    cudaError_t e = pool_alloc(device, (size_t)n * n * sizeof(double), &own.sq, &own.sq_got);
+    if (e == cudaSuccess) e = pool_alloc(device, cmds_workspace_doubles(n) * sizeof(double), &own.work, &own.work_got);
+    if (e != cudaSuccess) { set_error("cudaMalloc of the %lld x %lld matrix failed: %s", (long long)n, (long long)n, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    if ((e = pinned_alloc(3 * 16 * 16 * sizeof(double) + 64, &own.pin)) != cudaSuccess) { set_error("cudaHostAlloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    if (cond) { CUDA_TRY(launch_square_rows(cond, (double *)own.sq, n, 0, n, st)); launch_counter_add(1); }
+    else CUDA_TRY(cudaMemcpyAsync(own.sq, square_host, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(run_cmds((double *)own.sq, n, dims, (double *)own.work, (double *)own.pin, d_coords, eigenvalues, max_iter, tol, iterations, residual, st));
+    return TD_OK;
+}
+}  // namespace
+
+int td_cmds_device(const double *d_condensed, int64_t n_trees, int dimensions, double *d_coords, double *eigenvalues, int max_iter, double tol,
+                   int *iterations, double *residual, void *stream)
+{
+    if (!d_condensed || !d_coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    DeviceScope scope;
+    cudaPointerAttributes attr;
+    CUDA_TRY(cudaPointerGetAttributes(&attr, d_condensed));
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { set_error("the condensed matrix is not device memory"); return TD_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(attr.device));
+    return cmds_on_device(attr.device, d_condensed, nullptr, n_trees, dimensions, d_coords, eigenvalues, max_iter, tol, iterations, residual, (cudaStream_t)stream);
+}
+
+int td_cmds(td_treeset *ts, int metric, int normalise, int min_overlap, double overlap_fail_value, int dimensions, double *coords, double *eigenvalues,
+            int max_iter, double tol, int *iterations, double *residual, int device)
+{
+    if (!ts || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    if (metric < 0 || metric > 3) { set_error("unknown metric %d", metric); return TD_ERR_ARG; }
+    DeviceScope scope;
+    int rc;
+    if ((rc = upload(ts, device, 0))) return rc;
+    DeviceSet *dset = resident(ts, device);
+    const int64_t N = ts->host.N, pairs = N * (N - 1) / 2;
+    CUDA_TRY(cudaSetDevice(device));
+    HostCall hc; hc.device = device;
+    cudaError_t e = pool_alloc(device, (size_t)std::max<int64_t>(pairs, 1) * sizeof(double), &hc.extra, &hc.extra_size);
+    if (e == cudaSuccess) e = pool_alloc(device, (size_t)N * dimensions * sizeof(double) + 64, &hc.dbuf[0][0], &hc.dsize[0][0]);
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    void *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    d_out[metric] = hc.extra;
+    if ((rc = run_pairwise(ts, dset, 1u << metric, normalise, min_overlap, overlap_fail_value, false, 0, 0, N, d_out, hc.bs.compute))) return rc;
+    if ((rc = cmds_on_device(device, (const double *)hc.extra, nullptr, N, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)N * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
+    CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    return take_error_flag(dset);
+}
+
+int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol, int *iterations,
+                 double *residual, int device)
+{
+    if (!square || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); set_error("no CUDA device available; libtreedist_cuda has no CPU fallback"); return TD_ERR_NO_DEVICE; }
+    if (device < 0 || device >= count) { set_error("device %d out of range", device); return TD_ERR_ARG; }
+    DeviceScope scope;
+    CUDA_TRY(cudaSetDevice(device));
+    HostCall hc; hc.device = device;
+    cudaError_t e = pool_alloc(device, (size_t)n_trees * std::max(dimensions, 1) * sizeof(double) + 64, &hc.dbuf[0][0], &hc.dsize[0][0]);
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    int rc;
+    if ((rc = cmds_on_device(device, nullptr, square, n_trees, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)n_trees * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
+    CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    return TD_OK;
+}
+
 int td_alloc_pinned(int64_t bytes, void **out)
 {
     if (!out || bytes < 0) { set_error("bad argument"); return TD_ERR_ARG; }

@@ -109,6 +109,12 @@ int bigtree_max_splits();
 int bigtree_blocks(int64_t pairs, int n_sms, size_t warp_bytes, size_t scratch_budget);
 cudaError_t launch_bigtree(const GeoParams &g, int general, int max_splits, unsigned char *scratch, int blocks, cudaStream_t st);
 
+// classical MDS on the device-resident matrix (kernels_embed.cu)
+size_t cmds_workspace_doubles(int64_t n);
+int cmds_block();
+cudaError_t run_cmds(double *sq, int64_t n, int dims, double *work, double *h_pinned, double *d_coords, double *eigenvalues, int max_iter, double tol,
+                     int *iterations, double *residual, cudaStream_t st);
+
 // int8 tcgen05 split-incidence RF (kernels_incidence.cu)
 size_t incidence_smem_bytes();
 int incidence_tile();
