@@ -66,7 +66,7 @@ typedef struct {
     int32_t device;          /* device the set is resident on, -1 if not uploaded                            */
     int32_t n_postings;      /* entries of the shared-split postings (= sum over trees of their shared-list lengths)      */
     int32_t heavy_rows;      /* shared splits (by descending multiplicity) the hybrid tile kernel takes as matrix rows     */
-    int32_t reserved;
+    int32_t n_groups;        /* non-uniform sets: leaf-set groups served by the uniform kernels (-1 until the first matrix call)   */
     double mean_common;      /* expected number of common splits of a random pair of the set                              */
     double heavy_common;     /* ... of which the heavy rows cover                                                          */
 } td_info;

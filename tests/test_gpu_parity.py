@@ -255,6 +255,47 @@ def test_different_leaf_sets_vs_oracle(td, oracle_mod, n_taxa, n_trees, norm):
     assert np.array_equal(a, got['geo'][p0:p1])
 
 
+def test_leaf_set_groups(td, oracle_mod, monkeypatch):
+    """treeCl/treedist.py:63-68 prunes only the pairs whose leaf sets differ.  A set in which a few trees miss taxa: the trees that share a
+    leaf set form groups served by the uniform kernels (own dictionary), only the pairs across groups take the restrict-then-join kernel.
+    Every entry against the oracle, all four metrics; the grouped result equals the ungrouped one (TREEDIST_NO_GROUPS) to rounding."""
+    from treecl_b200 import _lib, synth
+    n, taxa = 700, 20
+    rng = np.random.default_rng(5)
+    full = synth.structured_trees(n, taxa, n_classes=4, class_nni=5, lam=1.0, seed=15)
+    labels = synth.taxon_labels(taxa)
+    trees = list(full)
+    miss3 = {labels[i] for i in range(taxa) if i not in (2, 7, 11)}
+    for k in rng.choice(n, size=120, replace=False)[:60]:
+        trees[k] = td.Tree(full[k]).prune_to_subset(miss3).newick                  # a second group: 60 trees without three taxa
+    for k in rng.choice(n, size=12, replace=False):
+        keep = rng.choice(taxa, size=int(rng.integers(10, taxa)), replace=False)
+        trees[k] = td.Tree(full[k]).prune_to_subset({labels[i] for i in keep}).newick   # odd trees, each with a leaf set of its own
+    ts = _lib.TreeSet(trees)
+    assert ts.info.uniform == 0
+    metrics = ('rf', 'wrf', 'euc', 'geo')
+    got = ts.pairwise(metrics, normalise=True, min_overlap=11, overlap_fail_value=-2.0)
+    assert ts.info.n_groups == 2
+    for m in metrics:
+        want = oracle_mod.matrix(trees, m, normalise=True, min_overlap=11, overlap_fail_value=-2.0, nthreads=NTHREADS)
+        assert (want == -2.0).any()
+        assert np.array_equal(got[m], want) if m == 'rf' else assert_close(got[m], want) is None
+    # row ranges cut through the groups: same bytes as the one-shot call for the same metrics
+    whole = ts.pairwise(('wrf', 'geo'), normalise=True, min_overlap=11, overlap_fail_value=-2.0)
+    assert_close(whole['wrf'], got['wrf'], rtol=1e-12)
+    for a, b in ((0, 250), (250, 251), (251, n)):
+        part = ts.pairwise(('wrf', 'geo'), normalise=True, min_overlap=11, overlap_fail_value=-2.0, row_begin=a, row_end=b)
+        p0, p1 = _lib.condensed_offset(n, a), _lib.condensed_offset(n, b)
+        assert np.array_equal(part['wrf'], whole['wrf'][p0:p1]) and np.array_equal(part['geo'], whole['geo'][p0:p1])
+    # ungrouped: every pair through the restrict-then-join kernel
+    monkeypatch.setenv('TREEDIST_NO_GROUPS', '1')
+    plain = _lib.TreeSet(trees)
+    ref = plain.pairwise(metrics, normalise=True, min_overlap=11, overlap_fail_value=-2.0)
+    assert plain.info.n_groups == 0
+    for m in metrics:
+        assert np.array_equal(got[m], ref[m]) if m == 'rf' else assert_close(got[m], ref[m], rtol=1e-12) is None
+
+
 def test_mixed_rooting_is_refused(td):
     from treecl_b200 import _lib
     ts = _lib.TreeSet(['((A:1,B:1):1,(C:1,D:1):1);', '((A:1,B:1):1,C:1,D:1);', '((A:1,C:1):1,B:1,D:1);'])

@@ -35,7 +35,7 @@ class td_info(ctypes.Structure):
                 ('max_splits', ctypes.c_int32), ('max_shared', ctypes.c_int32), ('uniform', ctypes.c_int32),
                 ('rooted', ctypes.c_int32), ('dict_size', ctypes.c_int64), ('dict_shared', ctypes.c_int64),
                 ('total_splits', ctypes.c_int64), ('device', ctypes.c_int32), ('n_postings', ctypes.c_int32),
-                ('heavy_rows', ctypes.c_int32), ('reserved', ctypes.c_int32), ('mean_common', ctypes.c_double),
+                ('heavy_rows', ctypes.c_int32), ('n_groups', ctypes.c_int32), ('mean_common', ctypes.c_double),
                 ('heavy_common', ctypes.c_double)]
 
 

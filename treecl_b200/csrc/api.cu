@@ -241,6 +241,14 @@ struct DeviceSet {
     size_t ev_block_bytes = 0, ev_block_got = 0;
     cudaEvent_t ev_done = nullptr;
     int *error_flag = nullptr;
+    // leaf-set groups of a non-uniform set: group id per tree, per group the member list and a scratch matrix per metric (the group's own
+    // condensed slice before it is scattered into the set's matrix; one launch at a time per set: later launches wait on grp_done)
+    int32_t *group_of = nullptr;
+    std::vector<int32_t *> grp_members;
+    std::mutex grp_mu;
+    void *grp_tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t grp_tmp_bytes = 0, grp_tmp_got[4] = {0, 0, 0, 0};
+    cudaEvent_t grp_done = nullptr;
     // per-warp scratch of the big-tree kernel (one launch at a time per set: later launches wait on big_done)
     std::mutex big_mu;
     unsigned char *big_scratch = nullptr;
@@ -280,6 +288,8 @@ static void free_device(DeviceSet *d)
     for (auto &b : d->allocs) pool_free(d->device, b.second, b.first);
     if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->ev_block) pool_free(d->device, d->ev_block, d->ev_block_got);
+    if (d->grp_done) cudaEventDestroy(d->grp_done);
+    for (int m = 0; m < 4; m++) if (d->grp_tmp[m]) pool_free(d->device, d->grp_tmp[m], d->grp_tmp_got[m]);
     if (d->big_done) cudaEventDestroy(d->big_done);
     if (d->big_scratch) pool_free(d->device, d->big_scratch, d->big_got);
     if (cur >= 0) cudaSetDevice(cur);
@@ -624,6 +634,49 @@ static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams 
     return TD_OK;
 }
 
+// ---- leaf-set groups of a non-uniform set ---------------------------------------------------------------------------------------------------
+constexpr int kMinGroup = 48;                       // fewer trees with one leaf set are not worth kernels of their own
+
+static int ensure_groups(td_treeset *ts)
+{
+    std::lock_guard<std::mutex> guard(ts->groups_mu);
+    if (ts->groups_built) return TD_OK;
+    const HostSet &h = ts->host;
+    ts->group_of.assign((size_t)h.N, -1);
+    if (!h.uniform && !getenv("TREEDIST_NO_GROUPS")) {
+        // bucket by (rootedness, leaf mask)
+        std::vector<int32_t> order((size_t)h.N);
+        for (int64_t i = 0; i < h.N; i++) order[(size_t)i] = (int32_t)i;
+        auto key_less = [&](int32_t a, int32_t b) {
+            if (h.tree_rooted[a] != h.tree_rooted[b]) return h.tree_rooted[a] < h.tree_rooted[b];
+            const int c = memcmp(&h.leafmask[(size_t)a * h.W], &h.leafmask[(size_t)b * h.W], (size_t)h.W * 8);
+            return c != 0 ? c < 0 : a < b;
+        };
+        std::sort(order.begin(), order.end(), key_less);
+        for (size_t lo = 0; lo < order.size();) {
+            size_t hi = lo + 1;
+            while (hi < order.size() && h.tree_rooted[order[hi]] == h.tree_rooted[order[lo]]
+                   && !memcmp(&h.leafmask[(size_t)order[hi] * h.W], &h.leafmask[(size_t)order[lo] * h.W], (size_t)h.W * 8)) hi++;
+            if ((int)(hi - lo) >= kMinGroup) {
+                td_treeset::Group g;
+                g.members.assign(order.begin() + lo, order.begin() + hi);          // ascending (ties of the sort are broken by index)
+                g.sub = new (std::nothrow) td_treeset();
+                if (!g.sub) { set_error("out of memory"); return TD_ERR_NOMEM; }
+                int rc;
+                try { rc = encode_group(h, g.members, 0, g.sub->host); }
+                catch (const std::bad_alloc &) { set_error("out of memory while encoding a leaf-set group"); rc = TD_ERR_NOMEM; }
+                if (rc) { delete g.sub; return rc; }
+                g.sub->groups_built = true;                                          // a group is uniform: no groups of its own
+                for (int32_t t : g.members) ts->group_of[(size_t)t] = (int32_t)ts->groups.size();
+                ts->groups.push_back(std::move(g));
+            }
+            lo = hi;
+        }
+    }
+    ts->groups_built = true;
+    return TD_OK;
+}
+
 // Trees with more than 128 internal edges (or more than 3 mask words): the big-tree kernel, whose per-split state lives in a per-warp
 // slab of global memory.  g carries the pair range and the outputs (g.outs / g.metric_mask).
 constexpr size_t kBigScratchBudget = 6ull << 30;
@@ -658,6 +711,61 @@ static int run_bigtree(td_treeset *ts, DeviceSet *d, GeoParams &g, int general, 
     return TD_OK;
 }
 
+static int upload(td_treeset *ts, int device, cudaStream_t st);
+static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
+                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st);
+
+// Same-group pairs of a non-uniform set: every group runs the uniform kernels on its own sub-set (local rows that fall into
+// [row_begin, row_end)) into a scratch matrix, which is then scattered into the set's condensed matrix.
+static int run_groups(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    std::lock_guard<std::mutex> guard(d->grp_mu);
+    if (!d->grp_done) CUDA_TRY(cudaEventCreateWithFlags(&d->grp_done, cudaEventDisableTiming));
+    if (d->grp_members.empty()) {
+        d->grp_members.assign(ts->groups.size(), nullptr);
+        for (size_t k = 0; k < ts->groups.size(); k++) {
+            int rc = dev_alloc(d, &d->grp_members[k], ts->groups[k].members.size()); if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(d->grp_members[k], ts->groups[k].members.data(), ts->groups[k].members.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    const int64_t p_base = condensed_offset(h.N, row_begin);
+    for (size_t k = 0; k < ts->groups.size(); k++) {
+        td_treeset::Group &g = ts->groups[k];
+        const int64_t n_local = (int64_t)g.members.size();
+        const int64_t a0 = std::lower_bound(g.members.begin(), g.members.end(), (int32_t)row_begin) - g.members.begin();
+        const int64_t a1 = std::lower_bound(g.members.begin(), g.members.end(), (int32_t)std::min<int64_t>(row_end, INT32_MAX)) - g.members.begin();
+        const int64_t local_pairs = condensed_offset(n_local, a1) - condensed_offset(n_local, a0);
+        if (local_pairs <= 0) continue;
+        int rc;
+        if ((rc = upload(g.sub, d->device, st))) return rc;
+        DeviceSet *sd = resident(g.sub, d->device);
+        const size_t need = (size_t)local_pairs * sizeof(double);
+        CUDA_TRY(cudaStreamWaitEvent(st, d->grp_done, 0));                         // the scratch matrices are free again
+        if (need > d->grp_tmp_bytes) {
+            CUDA_TRY(cudaEventSynchronize(d->grp_done));
+            for (int m = 0; m < 4; m++) if (d->grp_tmp[m]) { pool_free(d->device, d->grp_tmp[m], d->grp_tmp_got[m]); d->grp_tmp[m] = nullptr; }
+            d->grp_tmp_bytes = need;
+        }
+        void *tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int m = 0; m < 4; m++) if (mask >> m & 1u) {
+            if (!d->grp_tmp[m]) {                                                  // (every scratch matrix holds grp_tmp_bytes)
+                cudaError_t e = pool_alloc(d->device, d->grp_tmp_bytes, &d->grp_tmp[m], &d->grp_tmp_got[m]);
+                if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes of group scratch failed: %s", (long long)d->grp_tmp_bytes, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+            }
+            tmp[m] = d->grp_tmp[m];
+        }
+        if ((rc = run_pairwise(g.sub, sd, mask, normalise, 4, 0.0, false, 0, a0, a1, tmp, st))) return rc;
+        for (int m = 0; m < 4; m++) if (mask >> m & 1u) {
+            CUDA_TRY(launch_scatter_group((const double *)tmp[m], (double *)d_out[m], d->grp_members[k], n_local, a0, a1, h.N, p_base, st));
+            launch_counter_add(1);
+        }
+        CUDA_TRY(cudaEventRecord(d->grp_done, st));
+    }
+    return TD_OK;
+}
+
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
 {
@@ -667,9 +775,20 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
         CUDA_TRY(cudaSetDevice(d->device));
         { int rc = upload_full_lists(ts, d, st); if (rc) return rc; }
+        // trees that share a leaf set with enough others form groups served by the uniform kernels (triangular launches only)
+        { int rc = ensure_groups(ts); if (rc) return rc; }
+        const bool grouped = !rect && !ts->groups.empty();
+        if (grouped) {
+            std::lock_guard<std::mutex> guard(d->grp_mu);
+            if (!d->group_of) {
+                int rc = dev_alloc(d, &d->group_of, (size_t)h.N); if (rc) return rc;
+                CUDA_TRY(cudaMemcpyAsync(d->group_of, ts->group_of.data(), (size_t)h.N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+            }
+        }
         GeoParams g{};
         g.lens = d->lens; g.masks = d->masks; g.nsplits = d->nsplits; g.leaflen = d->leaflen; g.norm = d->norm;
-        g.leafmask = d->leafmask; g.rooted = d->rooted;
+        g.leafmask = d->leafmask; g.rooted = d->rooted; g.group_of = grouped ? d->group_of : nullptr;
         g.N = d->N; g.stride = d->stride; g.n_taxa = d->n_taxa; g.W = d->W; g.normalise = normalise; g.flow_rows = std::max(h.max_splits, 1);
         g.metric_mask = mask; g.min_overlap = min_overlap; g.fail_value = fail_value;
         for (int m = 0; m < 4; m++) {
@@ -680,10 +799,13 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
         if (g.p_end > g.p_begin) {
-            if (big) return run_bigtree(ts, d, g, 1, st);
-            CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
-            CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
-            launch_counter_add(1);
+            if (big) { int rc = run_bigtree(ts, d, g, 1, st); if (rc) return rc; }
+            else {
+                CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+                CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
+                launch_counter_add(1);
+            }
+            if (grouped) return run_groups(ts, d, mask, normalise, row_begin, row_end, d_out, st);
         }
         return TD_OK;
     }
@@ -818,6 +940,12 @@ geodesic:
 
 using namespace td;
 
+td_treeset::~td_treeset()
+{
+    for (Group &g : groups) delete g.sub;
+    for (DeviceSet *d : devs) free_device(d);
+}
+
 namespace {
 // the entry points select the set's GPU; the caller's current device is put back on the way out
 struct DeviceScope {
@@ -826,13 +954,24 @@ struct DeviceScope {
     ~DeviceScope() { if (saved >= 0) cudaSetDevice(saved); }
 };
 
-// reads and clears the sticky error flag of a resident set (the caller has synchronised the launches it asks about)
-int take_error_flag(DeviceSet *d)
+// reads and clears the sticky error flag of a resident set and of its leaf-set groups (the caller has synchronised the launches it asks about)
+int take_error_flag(td_treeset *ts, DeviceSet *d)
 {
     int flag = 0;
     CUDA_TRY(cudaSetDevice(d->device));
     CUDA_TRY(cudaMemcpy(&flag, d->error_flag, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) CUDA_TRY(cudaMemset(d->error_flag, 0, sizeof flag));
+    {
+        std::lock_guard<std::mutex> guard(ts->groups_mu);
+        for (td_treeset::Group &g : ts->groups) {
+            DeviceSet *sd = resident(g.sub, d->device);
+            if (!sd) continue;
+            int f = 0;
+            CUDA_TRY(cudaMemcpy(&f, sd->error_flag, sizeof f, cudaMemcpyDeviceToHost));
+            if (f) CUDA_TRY(cudaMemset(sd->error_flag, 0, sizeof f));
+            flag |= f;
+        }
+    }
     if (flag & 2) { set_error("cannot compare a rooted with an unrooted tree (undefined in the reference as well)"); return TD_ERR_MIXED_ROOTING; }
     if (flag & 1) { set_error("geodesic kernel hit its iteration cap on at least one pair (result is NaN there)"); return TD_ERR_CUDA; }
     return TD_OK;
@@ -919,7 +1058,6 @@ void td_treeset_free(td_treeset *ts)
 {
     if (!ts) return;
     DeviceScope scope;
-    for (DeviceSet *d : ts->devs) free_device(d);
     delete ts;
 }
 
@@ -932,6 +1070,7 @@ int td_treeset_info(const td_treeset *ts, td_info *info)
     info->uniform = h.uniform; info->rooted = h.rooted; info->dict_size = h.dict_size; info->dict_shared = h.dict_shared;
     info->total_splits = h.total_splits; info->device = -1; info->n_postings = (int32_t)h.post_tree.size();
     info->heavy_rows = h.heavy_rows; info->mean_common = h.mean_common; info->heavy_common = h.heavy_common;
+    info->n_groups = ts->groups_built ? (int32_t)ts->groups.size() : -1;
     for (DeviceSet *d : ts->devs) if (d) { info->device = d->device; break; }
     return TD_OK;
 }
@@ -1163,7 +1302,7 @@ static int host_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, in
         if (e == cudaSuccess) e = cudaStreamSynchronize(bs.compute);
         if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     }
-    return take_error_flag(dset);
+    return take_error_flag(ts, dset);
 }
 
 int td_pairwise(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
@@ -1238,7 +1377,7 @@ int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overla
         if (e == cudaSuccess) e = cudaStreamSynchronize(bs.compute);
         if (e != cudaSuccess) { set_error("kernel execution failed: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
     }
-    return take_error_flag(dset);
+    return take_error_flag(ts, dset);
 }
 
 // ---- classical MDS of a device-resident matrix --------------------------------------------------------------------------------
@@ -1297,7 +1436,7 @@ int td_cmds(td_treeset *ts, int metric, int normalise, int min_overlap, double o
     if ((rc = cmds_on_device(device, (const double *)hc.extra, nullptr, N, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute))) return rc;
     CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)N * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
     CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
-    return take_error_flag(dset);
+    return take_error_flag(ts, dset);
 }
 
 int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol, int *iterations,
@@ -1343,7 +1482,7 @@ int td_check_errors(td_treeset *ts, int device)
     DeviceScope scope;
     DeviceSet *d; int rc;
     if ((rc = check_ready(ts, device, &d))) return rc;
-    return take_error_flag(d);
+    return take_error_flag(ts, d);
 }
 
 int td_trim_cache(int device)

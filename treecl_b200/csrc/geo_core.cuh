@@ -121,6 +121,50 @@ __device__ __forceinline__ int find_id(const uint32_t *arr, int n, uint32_t key)
 
 __device__ __forceinline__ int64_t tri_row_start(int64_t i, int64_t N) { return i * N - i * (i + 1) / 2; }
 
+// Work distribution of the warp-per-pair kernels that may SKIP pairs (kernels_general.cu, kernels_bigtrees.cu): a warp takes a chunk of 32
+// consecutive pair indices from the launch's work counter, every lane decodes its own pair and tests whether it is wanted - pairs of two
+// trees of the same leaf-set group (GeoParams::group_of) belong to that group's uniform kernels - and the warp then walks the wanted
+// pairs of the chunk one by one.  A set with a few odd trees costs the odd pairs plus one ballot per 32 skipped pairs.
+struct PairFeed {
+    uint32_t pending = 0;
+    int64_t base = 0, my_ti = 0, my_tj = 0;
+};
+
+__device__ __forceinline__ void decode_pair(const GeoParams &p, int64_t pidx, int64_t &ti, int64_t &tj)
+{
+    if (p.rect) { ti = pidx / p.rect_cols; tj = p.rect_split + pidx % p.rect_cols; return; }
+    const double Nd = (double)p.N;
+    int64_t i = (int64_t)floor(((2.0 * Nd - 1.0) - sqrt((2.0 * Nd - 1.0) * (2.0 * Nd - 1.0) - 8.0 * (double)pidx)) * 0.5);
+    if (i < 0) i = 0; if (i > p.N - 2) i = p.N - 2;
+    while (i + 1 <= p.N - 2 && tri_row_start(i + 1, p.N) <= pidx) i++;
+    while (i > 0 && tri_row_start(i, p.N) > pidx) i--;
+    ti = i; tj = pidx - tri_row_start(i, p.N) + i + 1;
+}
+
+// false: no work left.  All lanes of the warp call it together and receive the same pair.
+__device__ __forceinline__ bool next_pair(const GeoParams &p, PairFeed &f, int lane, int64_t &pidx, int64_t &ti, int64_t &tj)
+{
+    while (f.pending == 0) {
+        unsigned long long wk = 0;
+        if (lane == 0) wk = atomicAdd(p.work_counter, 1ull);
+        wk = __shfl_sync(FULL, wk, 0);
+        f.base = p.p_begin + (int64_t)wk * 32;
+        if (f.base >= p.p_end) return false;
+        const int64_t mine = f.base + lane;
+        bool want = mine < p.p_end;
+        if (want) {
+            decode_pair(p, mine, f.my_ti, f.my_tj);
+            if (p.group_of) { const int ga = p.group_of[f.my_ti]; want = ga < 0 || ga != p.group_of[f.my_tj]; }
+        }
+        f.pending = __ballot_sync(FULL, want);
+    }
+    const int src = __ffs(f.pending) - 1;
+    f.pending &= f.pending - 1;
+    pidx = f.base + src;
+    ti = __shfl_sync(FULL, f.my_ti, src); tj = __shfl_sync(FULL, f.my_tj, src);
+    return true;
+}
+
 template <int H, int W>
 struct WarpSmem {
     static constexpr int CAP = 32 * H;

@@ -491,7 +491,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     hs = HostSet();
     hs.N = N; hs.n_taxa = n_taxa; hs.W = W; hs.labels = labels;
     hs.n_splits.resize(N); hs.n_leaves.resize(N); hs.tree_rooted.resize(N); hs.n_shared.assign(N, 0);
-    hs.leafmask.resize((size_t)N * W); hs.sum_len.resize(N); hs.norm.resize(N);
+    hs.leafmask.resize((size_t)N * W); hs.sum_len.resize(N); hs.norm.resize(N); hs.sum_sq.resize(N);
     hs.single_l1.assign(N, 0.0); hs.single_l2.assign(N, 0.0);
     hs.q1.assign(N, 0.0); hs.q2.assign(N, 0.0);
     int smax = 0; bool uniform = true; int64_t total = 0;
@@ -499,7 +499,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         const TreeEnc &e = enc[i];
         hs.n_splits[i] = (int)e.lens.size(); hs.n_leaves[i] = e.n_leaves; hs.tree_rooted[i] = e.rooted;
         memcpy(&hs.leafmask[(size_t)i * W], e.leafmask.data(), W * 8);
-        hs.sum_len[i] = e.sum_len; hs.norm[i] = std::sqrt(e.sum_sq);
+        hs.sum_len[i] = e.sum_len; hs.norm[i] = std::sqrt(e.sum_sq); hs.sum_sq[i] = e.sum_sq;
         smax = std::max(smax, hs.n_splits[i]); total += hs.n_splits[i];
         if (e.rooted != enc[0].rooted || memcmp(e.leafmask.data(), enc[0].leafmask.data(), W * 8)) uniform = false;
     }
@@ -763,6 +763,34 @@ int encode_kendall_colijn(const char *const *newick, int64_t N, double lambda, i
 }  // namespace td
 
 // ------------------------------------------------------------------------------------------------------------
+// Leaf-set groups.  The per-tree encodings of the members are rebuilt from the parent's packed arrays (a non-uniform set keeps every tree's
+// masks sorted by mask, which is what finish_encode expects) and go through the same dictionary / postings build as a fresh set.
+// ------------------------------------------------------------------------------------------------------------
+namespace td {
+
+int encode_group(const HostSet &parent, const std::vector<int32_t> &members, int n_threads, HostSet &sub)
+{
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int W = parent.W, n_taxa = parent.n_taxa;
+    const size_t stride = (size_t)std::max(parent.max_splits, 1);
+    std::vector<TreeEnc> enc(members.size());
+    for (size_t k = 0; k < members.size(); k++) {
+        const size_t t = (size_t)members[k];
+        TreeEnc &e = enc[k];
+        const int S = parent.n_splits[t];
+        e.rooted = parent.tree_rooted[t]; e.n_leaves = parent.n_leaves[t];
+        e.leafmask.assign(parent.leafmask.begin() + t * W, parent.leafmask.begin() + (t + 1) * W);
+        e.masks.assign(parent.masks.begin() + t * stride * W, parent.masks.begin() + (t * stride + S) * W);
+        e.lens.assign(parent.lens.begin() + t * stride, parent.lens.begin() + t * stride + S);
+        e.leaflen.assign(parent.leaflen.begin() + t * n_taxa, parent.leaflen.begin() + (t + 1) * n_taxa);
+        e.sum_len = parent.sum_len[t]; e.sum_sq = parent.sum_sq[t];
+    }
+    return finish_encode(enc, parent.labels, n_threads, sub, [](const char *) {});
+}
+
+}  // namespace td
+
+// ------------------------------------------------------------------------------------------------------------
 // Serialised form of an encoded set (td_treeset_serialize / td_treeset_deserialize): encode once, ship the bytes to the other ranks
 // (one broadcast) instead of parsing and encoding the same trees in every process.  Little-endian, this build's layout; a version
 // word guards against mixing builds.
@@ -771,7 +799,7 @@ namespace td {
 
 namespace {
 constexpr uint64_t kSerialMagic = 0x3154455345455254ull;      // "TREESET1"
-constexpr uint32_t kSerialVersion = 2;
+constexpr uint32_t kSerialVersion = 3;
 
 struct Writer {
     std::vector<unsigned char> *out; size_t size = 0;         // out == nullptr: only measure
@@ -801,7 +829,7 @@ void serial_fields(IO &io, HS &h)
     io.pod(h.uniform); io.pod(h.rooted); io.pod(h.dict_size); io.pod(h.dict_shared); io.pod(h.total_splits);
     io.pod(h.heavy_rows); io.pod(h.heavy_events); io.pod(h.heavy_common); io.pod(h.total_common); io.pod(h.mean_common); io.pod(h.sh_stride);
     io.vec(h.n_splits); io.vec(h.n_leaves); io.vec(h.tree_rooted); io.vec(h.n_shared); io.vec(h.leafmask);
-    io.vec(h.sum_len); io.vec(h.norm); io.vec(h.single_l1); io.vec(h.single_l2); io.vec(h.q1); io.vec(h.q2); io.vec(h.q1_light); io.vec(h.q2t);
+    io.vec(h.sum_len); io.vec(h.norm); io.vec(h.sum_sq); io.vec(h.single_l1); io.vec(h.single_l2); io.vec(h.q1); io.vec(h.q2); io.vec(h.q1_light); io.vec(h.q2t);
     io.vec(h.masks); io.vec(h.lens); io.vec(h.ids); io.vec(h.leaflen);
     io.vec(h.shared); io.vec(h.shared_x); io.vec(h.post_tree); io.vec(h.post_end); io.vec(h.post_len);
 }
@@ -836,7 +864,7 @@ int deserialize_set(const void *data, size_t bytes, HostSet &hs)
     const bool sane = hs.N >= 1 && hs.n_taxa >= 0 && hs.W >= 1 && hs.W >= (hs.n_taxa + 63) / 64 && hs.sh_stride >= 2 && hs.max_splits >= 0
         && (int)hs.labels.size() == hs.n_taxa
         && per_tree(hs.n_splits.size()) && per_tree(hs.n_shared.size()) && per_tree(hs.tree_rooted.size()) && hs.leafmask.size() >= N * (size_t)hs.W
-        && per_tree(hs.sum_len.size()) && per_tree(hs.norm.size()) && per_tree(hs.single_l1.size()) && per_tree(hs.single_l2.size())
+        && per_tree(hs.sum_len.size()) && per_tree(hs.norm.size()) && per_tree(hs.sum_sq.size()) && per_tree(hs.n_leaves.size()) && per_tree(hs.single_l1.size()) && per_tree(hs.single_l2.size())
         && per_tree(hs.q1.size()) && per_tree(hs.q2.size()) && per_tree(hs.q1_light.size()) && per_tree(hs.q2t.size())
         && hs.leaflen.size() >= N * (size_t)hs.n_taxa && hs.lens.size() >= N * S && hs.masks.size() >= N * S * (size_t)hs.W && hs.ids.size() >= N * S
         && hs.shared.size() == N * (size_t)hs.sh_stride && hs.shared_x.size() == hs.shared.size()

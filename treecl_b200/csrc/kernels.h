@@ -68,6 +68,8 @@ cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64
 long long pairsplit_tiles(bool rect, PairParams &p);
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);
 cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st);
+cudaError_t launch_scatter_group(const double *tmp, double *out, const int32_t *members, int64_t n_local, int64_t a0, int64_t a1, int64_t N,
+                                 int64_t p_base, cudaStream_t st);
 cudaError_t launch_square_rows(const double *cond, double *sq, int64_t N, int64_t r0, int64_t r1, cudaStream_t st);
 cudaError_t launch_transpose_leaf(const double *src, double *dst, int64_t N, int n_taxa, int64_t ldT, cudaStream_t st);
 
@@ -80,6 +82,7 @@ struct GeoParams {
     const double *norm;       // [N]
     const uint64_t *leafmask; // [N][W] taxa present in each tree (general kernel)
     const int32_t *rooted;    // [N]
+    const int32_t *group_of;  // [N] leaf-set group served by uniform kernels (-1: none), or nullptr: the warp-per-pair kernels skip same-group pairs
     int64_t N;
     int stride, n_taxa, W;
     int flow_rows;                       // max internal edges of any tree of the set: the flow matrix is flow_rows x (flow_rows|1)

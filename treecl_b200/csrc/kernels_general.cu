@@ -127,22 +127,10 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
     bool failed = false;
     const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
 
+    PairFeed feed;
     for (;;) {
-        unsigned long long wk = 0;
-        if (lane == 0) wk = atomicAdd(p.work_counter, 1ull);
-        wk = __shfl_sync(FULL, wk, 0);
-        const int64_t pidx = p.p_begin + (int64_t)wk;
-        if (pidx >= p.p_end) break;
-        int64_t ti, tj;
-        if (p.rect) { ti = pidx / p.rect_cols; tj = p.rect_split + pidx % p.rect_cols; }
-        else {
-            const double Nd = (double)p.N;
-            int64_t i = (int64_t)floor(((2.0 * Nd - 1.0) - sqrt((2.0 * Nd - 1.0) * (2.0 * Nd - 1.0) - 8.0 * (double)pidx)) * 0.5);
-            if (i < 0) i = 0; if (i > p.N - 2) i = p.N - 2;
-            while (i + 1 <= p.N - 2 && tri_row_start(i + 1, p.N) <= pidx) i++;
-            while (i > 0 && tri_row_start(i, p.N) > pidx) i--;
-            ti = i; tj = pidx - tri_row_start(i, p.N) + i + 1;
-        }
+        int64_t pidx, ti, tj;
+        if (!next_pair(p, feed, lane, pidx, ti, tj)) break;
         st.pairs++;
         const int64_t o = pidx - p.p_base;
         auto write_all = [&](double v) {

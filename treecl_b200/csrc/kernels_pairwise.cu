@@ -14,6 +14,8 @@
 // All sums are over non-negative terms (no ||a||^2+||b||^2-2ab expansion), so identical trees give exactly 0.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 
 #include "kernels.h"
@@ -289,6 +291,32 @@ __global__ void square_rows_kernel(const double *__restrict__ cond, double *__re
         else if (j < i) v = cond[j * N - j * (j + 1) / 2 + (i - j - 1)];
         sq[(i - r0) * N + j] = v;
     }
+}
+
+// A leaf-set group's own condensed slice (local rows [a0, a1) of its n_local trees) into the condensed matrix of the whole set:
+// local pair (a, b) is the pair (members[a], members[b]) of the set.
+__global__ void scatter_group_kernel(const double *__restrict__ tmp, double *__restrict__ out, const int32_t *__restrict__ members, int64_t n_local,
+                                     int64_t a0, int64_t a1, int64_t N, int64_t p_base)
+{
+    const int64_t a = a0 + blockIdx.y;
+    if (a >= a1) return;
+    const int64_t local_base = (a * n_local - a * (a + 1) / 2) - (a0 * n_local - a0 * (a0 + 1) / 2);
+    const int64_t gi = members[a], row_base = gi * N - gi * (gi + 1) / 2 - gi - 1 - p_base;
+    for (int64_t b = a + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_local; b += (int64_t)gridDim.x * blockDim.x)
+        out[row_base + members[b]] = tmp[local_base + (b - a - 1)];
+}
+
+cudaError_t launch_scatter_group(const double *tmp, double *out, const int32_t *members, int64_t n_local, int64_t a0, int64_t a1, int64_t N,
+                                 int64_t p_base, cudaStream_t st)
+{
+    if (a1 <= a0) return cudaSuccess;
+    for (int64_t r = a0; r < a1; r += 65535) {                    // (grid.y limit)
+        const int64_t r1 = std::min(a1, r + 65535);
+        const int64_t tmp_off = (r * n_local - r * (r + 1) / 2) - (a0 * n_local - a0 * (a0 + 1) / 2);
+        const dim3 grid((unsigned)std::min<int64_t>(64, (n_local + 255) / 256), (unsigned)(r1 - r));
+        scatter_group_kernel<<<grid, 256, 0, st>>>(tmp + tmp_off, out, members, n_local, r, r1, N, p_base);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_square_rows(const double *cond, double *sq, int64_t N, int64_t r0, int64_t r1, cudaStream_t st)

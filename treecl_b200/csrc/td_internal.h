@@ -34,6 +34,7 @@ struct HostSet {
     std::vector<int32_t> n_splits, n_leaves, tree_rooted, n_shared;
     std::vector<uint64_t> leafmask;            // [N][W]
     std::vector<double> sum_len, norm;         // all edges incl. leaves: sum l, sqrt(sum l^2)
+    std::vector<double> sum_sq;                // sum l^2 (kept beside its root so that a leaf-set group re-encodes to the same norm bits)
     std::vector<double> single_l1, single_l2;  // sums over splits held by this tree only: sum |l|, sum l^2
     std::vector<double> q1, q2;                // sums over ALL internal splits: sum |l|, sum l^2
     std::vector<double> q1_light;              // q1 minus the lengths of the tree's HEAVY shared splits (compact index < heavy_rows)
@@ -71,6 +72,9 @@ int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, Hos
 int encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, HostSet &hs);
 int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted);
 int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
+// leaf-set group of a non-uniform set: the member trees (ascending indices into `parent`) re-encoded as a set of their own - uniform, with
+// its own split dictionary - for the fast kernels
+int encode_group(const HostSet &parent, const std::vector<int32_t> &members, int n_threads, HostSet &sub);
 size_t serialize_set(const HostSet &hs, std::vector<unsigned char> *out);      // out == nullptr: size only
 int deserialize_set(const void *data, size_t bytes, HostSet &hs);
 
@@ -80,4 +84,13 @@ struct td_treeset {
     td::HostSet host;
     std::mutex mu;                             // guards `devs`
     std::vector<td::DeviceSet *> devs;         // indexed by CUDA device ordinal; the set is replicated per GPU
+    // Leaf-set groups of a NON-uniform set (built on first use): trees with the same leaf set and rootedness, when there are enough of
+    // them, form a uniform sub-set served by the fast kernels; only pairs across groups take the warp-per-pair kernels
+    // (treeCl/treedist.py:63-68 prunes only the pairs whose leaf sets differ).
+    struct Group { std::vector<int32_t> members; td_treeset *sub = nullptr; };
+    std::mutex groups_mu;
+    bool groups_built = false;
+    std::vector<Group> groups;
+    std::vector<int32_t> group_of;             // [N] index into `groups`, -1: in no group
+    ~td_treeset();
 };
