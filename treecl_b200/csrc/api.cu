@@ -220,7 +220,7 @@ struct DeviceSet {
     std::atomic<uint32_t> next_worklist{0};
     int8_t *X = nullptr;               // split-incidence matrix [rows_x][d_pad] for the int8 tcgen05 RF path (built on demand)
     int64_t d_pad = 0, rows_x = 0;
-    alignas(64) unsigned char tmap[128];
+    alignas(64) unsigned char tmap[128], tmap_half[128];   // boxes of a whole tile / of the half a CTA multicasts to its cluster partner
     alignas(64) unsigned char tmap_leaf_a[128], tmap_leaf_b[128];   // TMA descriptors over leafT (postings pipeline)
     bool leaf_maps = false;
     // split-extended matrix [n_k + dict_shared][Npad] for the Euclidean metric of densely sharing sets (built on demand)
@@ -572,13 +572,14 @@ static int run_rf_incidence(td_treeset *ts, DeviceSet *d, int normalise, int64_t
             CUDA_TRY(cudaMemsetAsync(X, 0, (size_t)rows * d_pad, st));
             CUDA_TRY(launch_build_incidence(d->shared, d->sh_stride, h.N, d_pad, X, st));
             launch_counter_add(1);
-            cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap);
+            cudaError_t e = make_incidence_tensor_map(X, rows, d_pad, d->tmap, 0);
+            if (e == cudaSuccess) e = make_incidence_tensor_map(X, rows, d_pad, d->tmap_half, incidence_half());
             if (e != cudaSuccess) { set_error("cuTensorMapEncodeTiled failed (%s)", cudaGetErrorString(e)); return TD_ERR_CUDA; }
             CUDA_TRY(cudaStreamSynchronize(st));              // other streams may use the matrix from now on (as for leafH / leafX)
             d->X = X; d->d_pad = d_pad; d->rows_x = rows;
         }
     }
-    CUDA_TRY(launch_rf_incidence(d->tmap, d->nsplits, h.N, d->d_pad, row_begin, row_end, condensed_offset(h.N, row_begin), normalise,
+    CUDA_TRY(launch_rf_incidence(d->tmap, d->tmap_half, d->nsplits, h.N, d->d_pad, row_begin, row_end, condensed_offset(h.N, row_begin), normalise,
                                  out_is_u16, d_out, st));
     launch_counter_add(1);
     return TD_OK;

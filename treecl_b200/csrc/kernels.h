@@ -123,8 +123,9 @@ size_t incidence_smem_bytes();
 int incidence_tile();
 int incidence_bk();
 cudaError_t launch_build_incidence(const SplitRec *shared, int sh_stride, int64_t N, int64_t ldx, int8_t *X, cudaStream_t st);
-cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx, void *tmap_out);
-cudaError_t launch_rf_incidence(const void *tmap, const int32_t *nsplits, int64_t N, int64_t d_pad, int64_t row_begin, int64_t row_end,
+int incidence_half();
+cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx, void *tmap_out, int box_rows);     // box_rows 0: a whole tile
+cudaError_t launch_rf_incidence(const void *tmap, const void *tmap_half, const int32_t *nsplits, int64_t N, int64_t d_pad, int64_t row_begin, int64_t row_end,
                                 int64_t p_base, int normalise, int out_u16, void *out, cudaStream_t st);
 
 uint64_t launch_counter_add(uint64_t n);

@@ -6,18 +6,24 @@
 // This is the dense-sharing alternative to the merge / hash-join kernels: worthwhile when D is small (clustered gene
 // trees), pointless for independent random trees (D ~ N * S).  It is the only place tensor cores are used.
 //
-// One CTA per 128 x 128 tile of the upper triangle, 192 threads:
-//   warp 0     TMA producer : cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A (rows) and B (columns) k-slabs, 128 B of K each,
-//                             into a 3-stage shared-memory ring; completion on `full` mbarriers
-//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32) on shared-memory
-//                             descriptors, accumulating in TMEM (128 lanes x 128 columns of int32); tcgen05.commit frees the
-//                             ring slot (`empty` mbarriers) and finally signals `tmem_full`
-//   warps 2-5  epilogue     : tcgen05.ld 32x32b.x32 (one TMEM lane = one row per thread), RF transform, condensed store
+// One CTA per 256 x 256 tile of the upper triangle (one CTA per SM: the whole TMEM), 320 threads; two CTAs with horizontally adjacent
+// tiles form a cluster and share the A (row) slab: each loads one 128-row half of it and TMA-multicasts that half into both CTAs'
+// shared memory, so a CTA pulls 128 + 256 instead of 256 + 256 rows of K through L2 per k-step.  The 128 x 128 tiles of the first
+// version were L2-bound (ncu, profiles/r2_incidence_summary.txt: L2 72 %, tensor pipe 29 %): every tile pulls 2 x 128 rows of K
+// through L2; a 256 x 256 tile pulls 2 x 256 rows for four times the MMAs, i.e. half the L2 bytes per operation.
+//   warp 0     TMA producer : cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A (256 rows) and B (256 columns) k-slabs, 128 B of K each,
+//                             into a 3-stage shared-memory ring (64 KB per stage); completion on `full` mbarriers
+//   warp 1     MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32), two per k-step (the
+//                             two 128-row halves of A), accumulating in TMEM (128 lanes x 2 x 256 columns of int32); tcgen05.commit
+//                             frees the ring slot (`empty` mbarriers) and finally signals `tmem_full`
+//   warps 2-9  epilogue     : tcgen05.ld 32x32b.x32 (one TMEM lane = one row per thread; warps 2-5 the upper half of the tile, 6-9 the
+//                             lower), RF transform, condensed store
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -26,12 +32,14 @@ namespace td {
 
 namespace {
 
-constexpr int TILE = 128;            // rows and columns of an output tile = UMMA M and N
+constexpr int TILE = 256;            // rows and columns of an output tile: two UMMA M = 128 halves x UMMA N = 256
+constexpr int HALF = 128;            // UMMA M
 constexpr int BK = 128;              // bytes (= int8 elements) of K per stage = one 128-byte swizzle row
 constexpr int UMMA_K = 32;           // K per tcgen05.mma for 8-bit operands
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;
 constexpr uint32_t STAGE_BYTES = 2 * TILE * BK;      // A + B slab
+constexpr uint32_t TMEM_COLS = 512;  // 2 halves x 256 int32 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -61,7 +69,7 @@ __device__ __forceinline__ uint64_t umma_desc(const void *smem)
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(HALF >> 4) << 24);
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate)
 {
@@ -72,6 +80,30 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the same arrival on the barrier at this shared-memory offset in every CTA of `mask` (both CTAs of the pair wait for both consumers
+// before a ring slot - which both producers write into - is refilled)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// clusters (tile pairs) before tile row u when the first row has L0 tiles: sum over v < u of ceil((L0 - v) / 2)
+__host__ __device__ __forceinline__ long long pair_prefix(long long L0, long long u)
+{
+    auto S = [](long long m) { const long long q = m / 2; return q * (q + 1) + (m & 1) * (q + 1); };      // sum_{k=1..m} ceil(k / 2)
+    return S(L0) - S(L0 - u);
+}
 
 struct IncParams {
     const int32_t *nsplits;
@@ -80,49 +112,50 @@ struct IncParams {
     int tile_row0, tiles;        // first tile row, tile columns in total
     int k_blocks;                // Dpad / BK
     int normalise, out_u16;
+    int multicast;               // 1: the two CTAs of a cluster each load half of the shared A slab and multicast it; 0: every CTA loads its own
     void *out;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 2)
-rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half, const IncParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // [STAGES][A 16 KB | B 16 KB]; the 128-byte swizzle wants 1024-byte aligned slabs (the launch reserves the slack)
+    // [STAGES][A 32 KB | B 32 KB]; the 128-byte swizzle wants 1024-byte aligned slabs (the launch reserves the slack)
     unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
     uint64_t *tmem_full = empty + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
-    int32_t *s_cols = reinterpret_cast<int32_t *>(tmem_slot + 2);        // S_j of the tile's 128 columns
+    int32_t *s_cols = reinterpret_cast<int32_t *>(tmem_slot + 2);        // S_j of the tile's 256 columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // upper-triangular tile list, row-major from tile row p.tile_row0
+    // upper-triangular tile list, row-major from tile row p.tile_row0, two adjacent tiles of a row per cluster (a row with an odd number
+    // of tiles ends with a pair whose second tile lies beyond the matrix: it loads zeros and stores nothing)
+    const uint32_t rank = cluster_ctarank();
     int tile_r, tile_c;
     {
-        const long long t = blockIdx.x, L0 = p.tiles - p.tile_row0;
-        const double b = 2.0 * (double)L0 + 1.0;
-        long long u = (long long)floor((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
-        if (u < 0) u = 0;
-        while (u * L0 - u * (u - 1) / 2 > t) u--;
-        while ((u + 1) * L0 - (u + 1) * u / 2 <= t) u++;
-        tile_r = (int)u + p.tile_row0;
-        tile_c = tile_r + (int)(t - (u * L0 - u * (u - 1) / 2));
+        const long long c = blockIdx.x >> 1, L0 = p.tiles - p.tile_row0;
+        long long lo = 0, hi = L0;                                       // largest u with pair_prefix(u) <= c
+        while (lo + 1 < hi) { const long long mid = (lo + hi) >> 1; if (pair_prefix(L0, mid) <= c) lo = mid; else hi = mid; }
+        tile_r = (int)lo + p.tile_row0;
+        tile_c = tile_r + 2 * (int)(c - pair_prefix(L0, lo)) + (int)rank;
     }
     const int64_t i0 = (int64_t)tile_r * TILE, j0 = (int64_t)tile_c * TILE;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.multicast ? 2 : 1); }    // multicast: both CTAs' consumers
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                                     // TMEM: 128 columns x 128 lanes of int32
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TILE) : "memory");
+    if (warp == 1) {                                                     // TMEM: 512 columns x 128 lanes of int32 (all of it)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 64) { const int c = threadIdx.x - 64; s_cols[c] = (j0 + c < p.N) ? p.nsplits[j0 + c] : 0; }
+    if (threadIdx.x >= 64) { const int c = threadIdx.x - 64; s_cols[c] = (j0 + c < p.N) ? p.nsplits[j0 + c] : 0; }        // 256 threads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();                                                  // the partner's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -133,7 +166,9 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);                 // slot free (first pass returns immediately)
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 unsigned char *a = ring + (size_t)s * STAGE_BYTES, *b = a + TILE * BK;
-                tma_load_2d(a, &tmap, kb * BK, (int)i0, &full[s]);
+                // my half of the shared A slab goes to both CTAs (each barrier receives both halves and its own B slab: STAGE_BYTES)
+                if (p.multicast) tma_load_2d_multicast(a + rank * HALF * BK, &tmap_half, kb * BK, (int)i0 + (int)rank * HALF, &full[s], (uint16_t)3);
+                else tma_load_2d(a, &tmap, kb * BK, (int)i0, &full[s]);
                 tma_load_2d(b, &tmap, kb * BK, (int)j0, &full[s]);
             }
         }
@@ -145,17 +180,22 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned char *a = ring + (size_t)s * STAGE_BYTES, *b = a + TILE * BK;
                 const uint64_t da = umma_desc(a), db = umma_desc(b);
+                const uint64_t da2 = umma_desc(a + HALF * BK);           // rows 128..255 of the A slab
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++)                    // +32 bytes of K inside the swizzled row: start address += 2
+                for (int k = 0; k < BK / UMMA_K; k++) {                  // +32 bytes of K inside the swizzled row: start address += 2
                     umma_i8(tmem_base, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), (kb | k) ? 1u : 0u);
-                umma_commit(&empty[s]);                                  // arrives when the MMAs above have read the slot
+                    umma_i8(tmem_base + TILE, da2 + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), (kb | k) ? 1u : 0u);
+                }
+                if (p.multicast) umma_commit_multicast(&empty[s], (uint16_t)3);     // arrives (in both CTAs) when the MMAs above have read the slot
+                else umma_commit(&empty[s]);
             }
             umma_commit(tmem_full);                                      // accumulator complete
         }
     } else {
-        // ---- epilogue: this warp may touch TMEM lanes 32*(warp % 4) .. +31 -----------------------------------------------
-        const int q = warp & 3;
-        const int row = 32 * q + lane;
+        // ---- epilogue: this warp may touch TMEM lanes 32*(warp % 4) .. +31; warps 2-5 read the accumulator of the upper half of the
+        // tile (columns 0..255 of TMEM), warps 6-9 that of the lower half (columns 256..511)
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = HALF * half + 32 * q + lane;
         const int64_t i = i0 + row;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -165,7 +205,7 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
 #pragma unroll 1
         for (int c0 = 0; c0 < TILE; c0 += 32) {
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(TILE * half + c0);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -174,46 +214,50 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const IncParams p)
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row_ok) {
-                const int64_t jb = j0 + c0;
-                if (p.out_u16 && jb > i && jb + 31 < p.N) {
-                    // whole run valid: pack two results per 32-bit store (the condensed offset may be odd)
-                    uint16_t *o = reinterpret_cast<uint16_t *>(p.out) + (row_off + jb);
-                    uint32_t r[32];
+            const int64_t jb = j0 + c0;
+            if (!p.normalise) {
+                // Transposed store.  After tcgen05.ld a lane holds 32 columns of ONE row: storing from that layout makes every store
+                // instruction touch 32 different rows (32 sectors for 64 or 128 useful bytes).  The 32 x 32 block goes through shared
+                // memory (the ring is idle by now) so that a lane holds one COLUMN and a store instruction writes one contiguous row
+                // segment: 64 B (u16) or 256 B (f64) in 2-3 or 8 sectors.
+                int *blk = reinterpret_cast<int *>(ring) + (warp - 2) * (32 * 33);
 #pragma unroll
-                    for (int k = 0; k < 32; k++) r[k] = (uint32_t)(si + s_cols[c0 + k] - 2 * (int)v[k]) & 0xFFFFu;
-                    if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
-#pragma unroll
-                        for (int k = 0; k < 32; k += 2) reinterpret_cast<uint32_t *>(o)[k >> 1] = r[k] | (r[k + 1] << 16);
-                    } else {
-                        o[0] = (uint16_t)r[0];
-#pragma unroll
-                        for (int k = 1; k < 31; k += 2) reinterpret_cast<uint32_t *>(o + 1)[k >> 1] = r[k] | (r[k + 1] << 16);
-                        o[31] = (uint16_t)r[31];
+                for (int k = 0; k < 32; k++) blk[lane * 33 + k] = si + s_cols[c0 + k] - 2 * (int)v[k];
+                __syncwarp();
+                const int64_t j = jb + lane;
+                const int64_t r0 = i0 + HALF * half + 32 * q;                       // first row of the block
+                int64_t off = r0 * p.N - r0 * (r0 + 1) / 2 - r0 - 1 - p.p_base + j;  // condensed index of (r0, j); next row: + N - r - 2
+#pragma unroll 8
+                for (int rr = 0; rr < 32; rr++) {
+                    const int64_t r = r0 + rr;
+                    const int rf = blk[rr * 33 + lane];
+                    if (r >= p.row_begin && r < p.row_end && j > r && j < p.N) {
+                        if (p.out_u16) reinterpret_cast<uint16_t *>(p.out)[off] = (uint16_t)rf;
+                        else reinterpret_cast<double *>(p.out)[off] = (double)rf;
                     }
-                } else {
+                    off += p.N - r - 2;
+                }
+                __syncwarp();
+            } else if (row_ok) {
 #pragma unroll
-                    for (int k = 0; k < 32; k++) {
-                        const int64_t j = jb + k;
-                        if (j <= i || j >= p.N) continue;
-                        const int den = si + s_cols[c0 + k];
-                        const int rf = den - 2 * (int)v[k];
-                        if (p.out_u16) reinterpret_cast<uint16_t *>(p.out)[row_off + j] = (uint16_t)rf;
-                        else {
-                            double d = (double)rf;
-                            if (p.normalise) d = den ? d / (double)den : 0.0;
-                            reinterpret_cast<double *>(p.out)[row_off + j] = d;
-                        }
-                    }
+                for (int k = 0; k < 32; k++) {
+                    const int64_t j = jb + k;
+                    if (j <= i || j >= p.N) continue;
+                    const int den = si + s_cols[c0 + k];
+                    const int rf = den - 2 * (int)v[k];
+                    double d = (double)rf;
+                    d = den ? d / (double)den : 0.0;
+                    reinterpret_cast<double *>(p.out)[row_off + j] = d;
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();                                                  // no CTA leaves while its partner may still write to it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TILE) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -240,9 +284,9 @@ cudaError_t launch_build_incidence(const SplitRec *shared, int sh_stride, int64_
     return cudaGetLastError();
 }
 
-// 2-D tensor map over X [rows][ldx] int8, box 128 (K bytes) x 128 (rows), 128-byte swizzle.  Returns cudaErrorNotSupported if
+// 2-D tensor map over X [rows][ldx] int8, box 128 (K bytes) x 256 (rows), 128-byte swizzle.  Returns cudaErrorNotSupported if
 // the driver entry point is unavailable.
-cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx, void *tmap_out)
+cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx, void *tmap_out, int box_rows)
 {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -252,7 +296,7 @@ cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx
     auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     const cuuint64_t dims[2] = {(cuuint64_t)ldx, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ldx};                       // bytes between rows
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)TILE};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(box_rows > 0 ? box_rows : TILE)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(reinterpret_cast<CUtensorMap *>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(X), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -260,22 +304,26 @@ cudaError_t make_incidence_tensor_map(const int8_t *X, int64_t rows, int64_t ldx
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_rf_incidence(const void *tmap, const int32_t *nsplits, int64_t N, int64_t d_pad, int64_t row_begin, int64_t row_end,
+int incidence_half() { return HALF; }
+
+cudaError_t launch_rf_incidence(const void *tmap, const void *tmap_half, const int32_t *nsplits, int64_t N, int64_t d_pad, int64_t row_begin, int64_t row_end,
                                 int64_t p_base, int normalise, int out_u16, void *out, cudaStream_t st)
 {
     IncParams p{};
     p.nsplits = nsplits; p.N = N; p.row_begin = row_begin; p.row_end = row_end; p.p_base = p_base;
     p.tile_row0 = (int)(row_begin / TILE); p.tiles = (int)((N + TILE - 1) / TILE);
     p.k_blocks = (int)(d_pad / BK); p.normalise = normalise; p.out_u16 = out_u16; p.out = out;
+    { const char *e = getenv("TREEDIST_INC_MULTICAST"); p.multicast = e ? atoi(e) != 0 : 1; }
+    if (getenv("TREEDIST_INC_DEBUG_NOSTORE")) p.row_end = p.row_begin;      // measurement aid: the whole kernel minus its stores (every row masked)
     const int64_t tile_rows = (row_end + TILE - 1) / TILE - p.tile_row0;
     const int64_t L0 = p.tiles - p.tile_row0;
-    const int64_t grid = tile_rows * L0 - tile_rows * (tile_rows - 1) / 2;
-    if (grid <= 0 || p.k_blocks <= 0) return cudaSuccess;
+    const int64_t clusters = pair_prefix(L0, tile_rows);
+    if (clusters <= 0 || p.k_blocks <= 0) return cudaSuccess;
     const size_t smem = incidence_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    CUtensorMap map; memcpy(&map, tmap, sizeof map);
-    rf_incidence_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(map, p);
+    CUtensorMap map, map_half; memcpy(&map, tmap, sizeof map); memcpy(&map_half, tmap_half, sizeof map_half);
+    rf_incidence_kernel<<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
     return cudaGetLastError();
 }
 
