@@ -16,8 +16,8 @@
 //   warp 1     MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32), two per k-step (the
 //                             two 128-row halves of A), accumulating in TMEM (128 lanes x 2 x 256 columns of int32); tcgen05.commit
 //                             frees the ring slot (`empty` mbarriers) and finally signals `tmem_full`
-//   warps 2-9  epilogue     : tcgen05.ld 32x32b.x32 (one TMEM lane = one row per thread; warps 2-5 the upper half of the tile, 6-9 the
-//                             lower), RF transform, condensed store
+//   warps 2-17 epilogue     : tcgen05.ld 32x32b.x32 (one TMEM lane = one row per thread; four warps per lane quarter: upper / lower half
+//                             of the tile x left / right 128 columns), RF transform, transposition through shared memory, condensed store
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -37,7 +37,7 @@ constexpr int HALF = 128;            // UMMA M
 constexpr int BK = 128;              // bytes (= int8 elements) of K per stage = one 128-byte swizzle row
 constexpr int UMMA_K = 32;           // K per tcgen05.mma for 8-bit operands
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 576;        // TMA warp, MMA warp, 16 epilogue warps
 constexpr uint32_t STAGE_BYTES = 2 * TILE * BK;      // A + B slab
 constexpr uint32_t TMEM_COLS = 512;  // 2 halves x 256 int32 columns
 
@@ -92,6 +92,28 @@ __device__ __forceinline__ void tma_load_2d_multicast(void *dst, const CUtensorM
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// ---- cta_group::2 forms: the two CTAs of a cluster (one TPC) run ONE MMA of M = 256: each CTA supplies its own 128 rows of A and HALF of
+// the N = 256 rows of B (the tensor cores read the other half from the partner's shared memory), accumulators of a CTA's rows in its own
+// TMEM.  Only the even CTA (rank 0, the leader) issues MMAs and commits; the loads of both CTAs report to the leader's barrier.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even CTA of the pair
+constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)((2 * HALF) >> 4) << 24);   // M = 256
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    const uint32_t z = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_c), "l"(da), "l"(db), "r"(kIdesc2), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all()
 {
@@ -116,25 +138,42 @@ struct IncParams {
     void *out;
 };
 
+// TWO_SM = false: every CTA a 256 x 256 tile of its own (cta_group::1), the two CTAs of a cluster share the A slab by TMA multicast.
+// TWO_SM = true : the cluster computes a 512 x 256 tile with cta_group::2 MMAs - CTA `rank` owns rows [256 rank, 256 rank + 256) of it and
+//                 loads those 256 rows of A plus 128 of the 256 rows of B per k-step: 48 KB instead of 64 KB through its shared-memory
+//                 port for the same 256 x 256 x 128 products (the port, ~64 B / clk / SM, is what bounds the 1-SM form; ncu summary in
+//                 profiles/), with a 4-stage ring.
+template <bool TWO_SM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half, const IncParams p)
 {
+    constexpr uint32_t kStageBytes = TWO_SM ? (uint32_t)((TILE + HALF) * BK) : STAGE_BYTES;       // A 256 rows + B 128 / 256 rows
+    constexpr int kStages = TWO_SM ? 4 : STAGES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // [STAGES][A 32 KB | B 32 KB]; the 128-byte swizzle wants 1024-byte aligned slabs (the launch reserves the slack)
+    // [stages][A 32 KB | B 16 / 32 KB]; the 128-byte swizzle wants 1024-byte aligned slabs (the launch reserves the slack)
     unsigned char *ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    static_assert((uint32_t)kStages * kStageBytes == (uint32_t)STAGES * STAGE_BYTES, "both forms use the same 192 KB ring");
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + STAGES * STAGE_BYTES);
-    uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
+    uint64_t *empty = full + 4;
+    uint64_t *tmem_full = empty + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     int32_t *s_cols = reinterpret_cast<int32_t *>(tmem_slot + 2);        // S_j of the tile's 256 columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // upper-triangular tile list, row-major from tile row p.tile_row0, two adjacent tiles of a row per cluster (a row with an odd number
-    // of tiles ends with a pair whose second tile lies beyond the matrix: it loads zeros and stores nothing)
+    // upper-triangular tile list, row-major from tile row p.tile_row0.  1-SM form: two adjacent tiles of a row per cluster (a row with an
+    // odd number of tiles ends with a pair whose second tile lies beyond the matrix: it loads zeros and stores nothing).  2-SM form: a
+    // cluster is a 512-row x 256-column tile, i.e. tile rows 2R and 2R + 1 of one tile column c >= 2R (its lower half lies below the
+    // diagonal when c == 2R: computed, never stored).
     const uint32_t rank = cluster_ctarank();
     int tile_r, tile_c;
-    {
+    if constexpr (TWO_SM) {
+        const long long c = blockIdx.x >> 1, T = p.tiles - p.tile_row0;             // p.tile_row0 is even here
+        long long lo = 0, hi = (T + 1) / 2;                                          // largest R with R T - R (R - 1) <= c
+        while (lo + 1 < hi) { const long long mid = (lo + hi) >> 1; if (mid * T - mid * (mid - 1) <= c) lo = mid; else hi = mid; }
+        tile_r = p.tile_row0 + 2 * (int)lo + (int)rank;
+        tile_c = p.tile_row0 + 2 * (int)lo + (int)(c - (lo * T - lo * (lo - 1)));
+    } else {
         const long long c = blockIdx.x >> 1, L0 = p.tiles - p.tile_row0;
         long long lo = 0, hi = L0;                                       // largest u with pair_prefix(u) <= c
         while (lo + 1 < hi) { const long long mid = (lo + hi) >> 1; if (pair_prefix(L0, mid) <= c) lo = mid; else hi = mid; }
@@ -144,15 +183,21 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const int64_t i0 = (int64_t)tile_r * TILE, j0 = (int64_t)tile_c * TILE;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.multicast ? 2 : 1); }    // multicast: both CTAs' consumers
+        // empty: 1-SM multicast form: both CTAs' consumers release a slot; 2-SM form: the leader's commit, multicast to both CTAs
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (!TWO_SM && p.multicast) ? 2 : 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                                     // TMEM: 512 columns x 128 lanes of int32 (all of it)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO_SM) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
-    if (threadIdx.x >= 64) { const int c = threadIdx.x - 64; s_cols[c] = (j0 + c < p.N) ? p.nsplits[j0 + c] : 0; }        // 256 threads
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TILE) { const int c = threadIdx.x - 64; s_cols[c] = (j0 + c < p.N) ? p.nsplits[j0 + c] : 0; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync_all();                                                  // the partner's barriers exist before anything is multicast to them
@@ -162,39 +207,56 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < p.k_blocks; kb++) {
-                const int s = kb % STAGES; const uint32_t round = kb / STAGES;
+                const int s = kb % kStages; const uint32_t round = kb / kStages;
                 mbar_wait(&empty[s], (round & 1u) ^ 1u);                 // slot free (first pass returns immediately)
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                unsigned char *a = ring + (size_t)s * STAGE_BYTES, *b = a + TILE * BK;
-                // my half of the shared A slab goes to both CTAs (each barrier receives both halves and its own B slab: STAGE_BYTES)
-                if (p.multicast) tma_load_2d_multicast(a + rank * HALF * BK, &tmap_half, kb * BK, (int)i0 + (int)rank * HALF, &full[s], (uint16_t)3);
-                else tma_load_2d(a, &tmap, kb * BK, (int)i0, &full[s]);
-                tma_load_2d(b, &tmap, kb * BK, (int)j0, &full[s]);
+                unsigned char *a = ring + (size_t)s * kStageBytes, *b = a + TILE * BK;
+                if constexpr (TWO_SM) {
+                    // both CTAs' loads report to the LEADER's barrier, which expects the bytes of both (its own producer arms it)
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
+                    tma_load_2d_2sm(a, &tmap, kb * BK, (int)i0, &full[s]);                                       // my 256 rows of A
+                    tma_load_2d_2sm(b, &tmap_half, kb * BK, (int)j0 + (int)rank * HALF, &full[s]);               // my half of the 256 rows of B
+                } else {
+                    mbar_expect_tx(&full[s], kStageBytes);
+                    // my half of the shared A slab goes to both CTAs (each barrier receives both halves and its own B slab)
+                    if (p.multicast) tma_load_2d_multicast(a + rank * HALF * BK, &tmap_half, kb * BK, (int)i0 + (int)rank * HALF, &full[s], (uint16_t)3);
+                    else tma_load_2d(a, &tmap, kb * BK, (int)i0, &full[s]);
+                    tma_load_2d(b, &tmap, kb * BK, (int)j0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && (!TWO_SM || rank == 0)) {
             for (int kb = 0; kb < p.k_blocks; kb++) {
-                const int s = kb % STAGES; const uint32_t round = kb / STAGES;
+                const int s = kb % kStages; const uint32_t round = kb / kStages;
                 mbar_wait(&full[s], round & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned char *a = ring + (size_t)s * STAGE_BYTES, *b = a + TILE * BK;
+                const unsigned char *a = ring + (size_t)s * kStageBytes, *b = a + TILE * BK;
                 const uint64_t da = umma_desc(a), db = umma_desc(b);
                 const uint64_t da2 = umma_desc(a + HALF * BK);           // rows 128..255 of the A slab
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; k++) {                  // +32 bytes of K inside the swizzled row: start address += 2
-                    umma_i8(tmem_base, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), (kb | k) ? 1u : 0u);
-                    umma_i8(tmem_base + TILE, da2 + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), (kb | k) ? 1u : 0u);
+                    const uint64_t ko = (uint64_t)(k * (UMMA_K >> 4));
+                    if constexpr (TWO_SM) {
+                        umma_i8_2sm(tmem_base, da + ko, db + ko, (kb | k) ? 1u : 0u);
+                        umma_i8_2sm(tmem_base + TILE, da2 + ko, db + ko, (kb | k) ? 1u : 0u);
+                    } else {
+                        umma_i8(tmem_base, da + ko, db + ko, (kb | k) ? 1u : 0u);
+                        umma_i8(tmem_base + TILE, da2 + ko, db + ko, (kb | k) ? 1u : 0u);
+                    }
                 }
-                if (p.multicast) umma_commit_multicast(&empty[s], (uint16_t)3);     // arrives (in both CTAs) when the MMAs above have read the slot
+                // the slot is free (in both CTAs) once the MMAs above have read it
+                if constexpr (TWO_SM) umma_commit_2sm(&empty[s], (uint16_t)3);
+                else if (p.multicast) umma_commit_multicast(&empty[s], (uint16_t)3);
                 else umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);                                      // accumulator complete
+            if constexpr (TWO_SM) umma_commit_2sm(tmem_full, (uint16_t)3);          // accumulators complete, in both CTAs
+            else umma_commit(tmem_full);
         }
     } else {
-        // ---- epilogue: this warp may touch TMEM lanes 32*(warp % 4) .. +31; warps 2-5 read the accumulator of the upper half of the
-        // tile (columns 0..255 of TMEM), warps 6-9 that of the lower half (columns 256..511)
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        // ---- epilogue: this warp may touch TMEM lanes 32*(warp % 4) .. +31.  Sixteen warps: four per lane quarter, one for each
+        // (half of the tile = 256 TMEM columns) x (128 of its 256 columns): a warp drains four 32-column chunks, and the TMEM-load ->
+        // transposition -> store chains of sixteen warps overlap
+        const int q = warp & 3, part = (warp - 2) >> 2, half = part >> 1, col_lo = (part & 1) * (TILE / 2);
         const int row = HALF * half + 32 * q + lane;
         const int64_t i = i0 + row;
         mbar_wait(tmem_full, 0);
@@ -203,7 +265,7 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const int si = row_ok ? p.nsplits[i] : 0;
         const int64_t row_off = i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TILE; c0 += 32) {
+        for (int c0 = col_lo; c0 < col_lo + TILE / 2; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(TILE * half + c0);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -257,7 +319,8 @@ rf_incidence_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     cluster_sync_all();                                                  // no CTA leaves while its partner may still write to it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -272,7 +335,7 @@ __global__ void build_incidence_kernel(const SplitRec *__restrict__ shared, int 
 
 }  // namespace
 
-size_t incidence_smem_bytes() { return (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + TILE * 4 + 1024; }
+size_t incidence_smem_bytes() { return (size_t)STAGES * STAGE_BYTES + (2 * 4 + 1) * 8 + 16 + TILE * 4 + 1024; }
 int incidence_tile() { return TILE; }
 int incidence_bk() { return BK; }
 
@@ -315,15 +378,28 @@ cudaError_t launch_rf_incidence(const void *tmap, const void *tmap_half, const i
     p.k_blocks = (int)(d_pad / BK); p.normalise = normalise; p.out_u16 = out_u16; p.out = out;
     { const char *e = getenv("TREEDIST_INC_MULTICAST"); p.multicast = e ? atoi(e) != 0 : 1; }
     if (getenv("TREEDIST_INC_DEBUG_NOSTORE")) p.row_end = p.row_begin;      // measurement aid: the whole kernel minus its stores (every row masked)
+    if (p.k_blocks <= 0) return cudaSuccess;
+    const size_t smem = incidence_smem_bytes();
+    CUtensorMap map, map_half; memcpy(&map, tmap, sizeof map); memcpy(&map_half, tmap_half, sizeof map_half);
+    // TREEDIST_INC_2SM=0: the 1-SM form (every CTA a 256 x 256 tile); default: 512 x 256 tiles by cta_group::2 pairs
+    const char *two = getenv("TREEDIST_INC_2SM");
+    if (!two || atoi(two) != 0) {
+        p.tile_row0 &= ~1;                                                // pair tiles start at even tile rows (rows before row_begin are masked)
+        const int64_t T = p.tiles - p.tile_row0, pair_rows = ((row_end + TILE - 1) / TILE - p.tile_row0 + 1) / 2;
+        const int64_t clusters = pair_rows * T - pair_rows * (pair_rows - 1);
+        if (clusters <= 0) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        rf_incidence_kernel<true><<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
+        return cudaGetLastError();
+    }
     const int64_t tile_rows = (row_end + TILE - 1) / TILE - p.tile_row0;
     const int64_t L0 = p.tiles - p.tile_row0;
     const int64_t clusters = pair_prefix(L0, tile_rows);
-    if (clusters <= 0 || p.k_blocks <= 0) return cudaSuccess;
-    const size_t smem = incidence_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (clusters <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    CUtensorMap map, map_half; memcpy(&map, tmap, sizeof map); memcpy(&map_half, tmap_half, sizeof map_half);
-    rf_incidence_kernel<<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
+    rf_incidence_kernel<false><<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
     return cudaGetLastError();
 }
 
