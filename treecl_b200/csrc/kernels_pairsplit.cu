@@ -808,10 +808,12 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         // the segment table completely, rows outside [row_begin, row_end) as empty segments
         const long long groups = (long long)p.tri_rows * (TR / RG);
         const size_t smem_e = pairsplit_events_smem_bytes(mask, p.sh_stride, p.col_tiles_total);
-        // CTAs per row group (a thread-block cluster): at least two waves of 2 CTAs per SM whatever share of the rows this launch has
+        // CTAs per row group (a thread-block cluster).  One when the row groups alone fill the GPU (measured on the bench set: 316 groups,
+        // 1 CTA each 0.156 ms per step, clusters of 2 = 632 CTAs = 1.07 waves 0.160 ms); a launch over a share of the rows (multi-GPU
+        // row blocks: 76 - 106 groups) splits its groups until one wave of 2 CTAs per SM is full
         unsigned parts = 1;
         if (const char *f = getenv("TREEDIST_EVENT_PARTS")) parts = (unsigned)atoi(f);
-        else while (parts < 8 && groups * parts < 4ll * n_sms) parts *= 2;
+        else while (parts < 8 && groups * parts * 2 <= 2ll * n_sms) parts *= 2;
         if (parts != 1 && parts != 2 && parts != 4 && parts != 8) parts = 1;
         e = checked(rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st), "pair_events_kernel");
         ++*launches;
