@@ -145,6 +145,12 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
                        double overlap_fail_value, int64_t row_begin, int64_t row_end, void *const d_out[4],
                        void *stream);
 
+/* Two disjoint row blocks in one call (a multi-GPU rank's share under the folded assignment: a block of long rows from the top of the
+ * triangle and a block of short rows from the bottom, engine.folded_row_ranges).  Same results as two td_pairwise_device calls; the
+ * postings pipeline shares one events kernel and one fix-up kernel between the blocks.  d_out_a / d_out_b: the blocks' output tables. */
+int td_pairwise_device2(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                        const int64_t row_begin[2], const int64_t row_end[2], void *const d_out_a[4], void *const d_out_b[4], void *stream);
+
 /* The kernels cannot return a status: a pair that compares a rooted with an unrooted tree (undefined in the reference) or a
  * geodesic pair that hits the iteration cap leaves NaN in the output and raises a sticky flag on the resident set.  td_pairwise
  * reads it itself; after the asynchronous entry points (td_pairwise_device, td_pairwise_rect_device) call td_check_errors once the

@@ -402,6 +402,22 @@ def test_row_sharding_is_byte_identical(td, pair_kernel):
     assert np.array_equal(a, full['euc'][p0:p1])
     out = engine.pairwise_condensed(ts, ('rf', 'geo'), normalise=True, devices=[0] * 3)
     assert np.array_equal(out['rf'], full['rf']) and np.array_equal(out['geo'], full['geo'])
+    # a rank's two folded blocks in ONE call (td_pairwise_device2: shared events and fix-up kernels) = the same bytes
+    import torch
+    ts.upload(0)
+    st = torch.cuda.current_stream().cuda_stream
+    metrics = ('rf', 'wrf', 'euc', 'geo')
+    for parts in (2, 4):
+        for rank_blocks in engine.folded_row_ranges(n, parts, align=16):
+            bufs = [(a, b, {m: torch.full((max(_lib.condensed_offset(n, b) - _lib.condensed_offset(n, a), 1),), -1.0, dtype=torch.float64, device='cuda:0')
+                            for m in metrics}) for a, b in rank_blocks]
+            ts.pairwise_device_blocks(metrics, [(a, b, {m: t[m].data_ptr() for m in metrics}) for a, b, t in bufs], normalise=True, stream=st)
+            torch.cuda.synchronize()
+            ts.check_errors(0)
+            for a, b, t in bufs:
+                p0, p1 = _lib.condensed_offset(n, a), _lib.condensed_offset(n, b)
+                for m in metrics:
+                    assert np.array_equal(t[m][:p1 - p0].cpu().numpy(), full[m][p0:p1]), (parts, a, b, m)
 
 
 @pytest.mark.parametrize('pair_kernel', ['auto', 'merge', 'join', 'split'], indirect=True)

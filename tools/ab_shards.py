@@ -17,9 +17,13 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 times = []
 for r, blocks in enumerate(engine.folded_row_ranges(n, parts)):
     outs = [(a, b, {m: torch.empty(_lib.condensed_offset(n, b) - _lib.condensed_offset(n, a), dtype=torch.float64, device='cuda') for m in metrics}) for a, b in blocks]
+    blocks_dev = [(a, b, {m: o[m].data_ptr() for m in metrics}) for a, b, o in outs]
     def step():
-        for a, b, o in outs:
-            ts.pairwise_device(metrics, {m: o[m].data_ptr() for m in metrics}, row_begin=a, row_end=b, stream=st.cuda_stream)
+        if os.environ.get('AB_SEPARATE_CALLS'):
+            for a, b, o in outs:
+                ts.pairwise_device(metrics, {m: o[m].data_ptr() for m in metrics}, row_begin=a, row_end=b, stream=st.cuda_stream)
+        else:
+            ts.pairwise_device_blocks(metrics, blocks_dev, stream=st.cuda_stream)
     for _ in range(3): step()
     ms = []
     for _ in range(8):

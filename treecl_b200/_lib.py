@@ -77,6 +77,8 @@ def load():
     lib.td_condensed_offset.restype = i64
     lib.td_pairwise_device.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, vp]
     lib.td_pairwise.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, i32]
+    if hasattr(lib, 'td_pairwise_device2'):
+        lib.td_pairwise_device2.argtypes = [vp, u32, i32, i32, dbl, i64 * 2, i64 * 2, _c_void_p4, _c_void_p4, vp]
     lib.td_pairwise_rect_device.argtypes = [vp, i64, u32, i32, _c_void_p4, vp]
     lib.td_rf_incidence_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     lib.td_geo_get_stats.argtypes = [vp, ctypes.POINTER(td_geo_stats)]
@@ -283,6 +285,23 @@ class TreeSet(object):
         check(self._lib.td_pairwise_device(self._h, mask, int(bool(normalise)), int(min_overlap),
                                            float(overlap_fail_value), int(row_begin), int(row_end),
                                            _c_void_p4(*table), ctypes.c_void_p(stream)))
+
+    def pairwise_device_blocks(self, metrics, blocks, normalise=False, min_overlap=4, overlap_fail_value=0.0, stream=0):
+        """Kernels only, for one or two disjoint row blocks [(row_begin, row_end, {metric: device pointer}), ...] - a rank's share under
+        engine.folded_row_ranges.  Two blocks go through td_pairwise_device2 (one events kernel, one fix-up kernel for both)."""
+        if len(blocks) == 1:
+            a, b, ptrs = blocks[0]
+            return self.pairwise_device(metrics, ptrs, normalise, min_overlap, overlap_fail_value, a, b, stream)
+        assert len(blocks) == 2
+        mask, tables = 0, [[None] * 4, [None] * 4]
+        for m in metrics:
+            mask |= 1 << METRIC_INDEX[m]
+            for k in range(2):
+                tables[k][METRIC_INDEX[m]] = blocks[k][2][m]
+        i64x2 = ctypes.c_int64 * 2
+        check(self._lib.td_pairwise_device2(self._h, mask, int(bool(normalise)), int(min_overlap), float(overlap_fail_value),
+                                            i64x2(int(blocks[0][0]), int(blocks[1][0])), i64x2(int(blocks[0][1]), int(blocks[1][1])),
+                                            _c_void_p4(*tables[0]), _c_void_p4(*tables[1]), ctypes.c_void_p(stream)))
 
     def pairwise_rect_device(self, split, metrics, d_out_ptrs, normalise=False, stream=0):
         mask, table = 0, [None] * 4

@@ -470,11 +470,14 @@ static bool hybrid_applies(const HostSet &h, const DeviceSet *d, uint32_t m3, bo
 }
 
 // postings pipeline: claim the set's event buffers (growing them if needed), order this launch after the previous one that used them
+// a second row block handled by the same launch set (multi-GPU folded blocks)
+struct RowBlock { int64_t row_begin, row_end; void *const *d_out; };
+
 static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, PairParams &p, int64_t capacity, void *const d_out[4], cudaStream_t st,
-                         bool rf_apart = false)
+                         bool rf_apart = false, const RowBlock *second = nullptr)
 {
     const long long tiles = pairsplit_tiles(rect, p);
-    if (tiles <= 0) return TD_OK;
+    if (tiles <= 0 && !second) return TD_OK;
     std::lock_guard<std::mutex> g(d->ev_mu);
     const size_t need = split_event_bytes(d, capacity, pairsplit_record_bytes(m3));
     if (!d->ev_done) CUDA_TRY(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
@@ -527,7 +530,15 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
     unsigned long long *trace = nullptr;
     const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
     if (trace_path) { CUDA_TRY(cudaMalloc(&trace, (size_t)tiles * 64)); CUDA_TRY(cudaMemsetAsync(trace, 0, (size_t)tiles * 64, st)); p.trace = trace; }
-    CUDA_TRY(launch_pairsplit(mk, rect, p, d->sm_count, st, &launches));
+    PairParams pb{};
+    if (second) {                                             // block B: same buffers and tables, its own rows, outputs and tile geometry
+        pb = p;
+        pb.row_begin = second->row_begin; pb.row_end = second->row_end; pb.p_base = condensed_offset(d->N, second->row_begin);
+        for (int m = 0; m < 3; m++) pb.out[m] = (double *)second->d_out[m];
+        pairsplit_tiles(rect, pb);
+        pb.rg0 = pb.tile_row0 * (64 / pairsplit_row_group());
+    }
+    CUDA_TRY(launch_pairsplit(mk, rect, p, d->sm_count, st, &launches, second ? &pb : nullptr));
     if (trace) {
         std::vector<unsigned long long> host((size_t)tiles * 8);
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -542,6 +553,10 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
         if (!d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
         int rc = run_rf_incidence(ts, d, p.normalise, p.row_begin, p.row_end, d_out[TD_RF], 0, st);
         if (rc) return rc;
+        if (second) {
+            if (!second->d_out[TD_RF]) { set_error("output pointer for metric 0 is null"); return TD_ERR_ARG; }
+            if ((rc = run_rf_incidence(ts, d, p.normalise, second->row_begin, second->row_end, second->d_out[TD_RF], 0, st))) return rc;
+        }
     }
     return TD_OK;
 }
@@ -714,7 +729,7 @@ static int run_bigtree(td_treeset *ts, DeviceSet *d, GeoParams &g, int general, 
 
 static int upload(td_treeset *ts, int device, cudaStream_t st);
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
-                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st);
+                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st, const RowBlock *second = nullptr);
 
 // Same-group pairs of a non-uniform set: every group runs the uniform kernels on its own sub-set (local rows that fall into
 // [row_begin, row_end)) into a scratch matrix, which is then scattered into the set's condensed matrix.
@@ -767,11 +782,19 @@ static int run_groups(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise
     return TD_OK;
 }
 
+// second: another row block of the same matrix computed by the same call (two folded blocks of a multi-GPU rank): the postings pipeline
+// then shares one events kernel and one fix-up kernel between the blocks; every other path simply runs the blocks one after the other
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
-                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st)
+                        int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st, const RowBlock *second)
 {
     const HostSet &h = ts->host;
     const bool big = h.max_splits > 128 || h.W > 3;
+    if (second && (!h.uniform || rect || second->row_end <= second->row_begin)) {
+        int rc = run_pairwise(ts, d, mask, normalise, min_overlap, fail_value, rect, split, row_begin, row_end, d_out, st, nullptr);
+        if (rc || second->row_end <= second->row_begin) return rc;
+        return run_pairwise(ts, d, mask, normalise, min_overlap, fail_value, rect, split, second->row_begin, second->row_end, second->d_out, st, nullptr);
+    }
+    bool second_m3_done = false;                      // rf / wrf / euc of the second block went into the merged launch set
     if (!h.uniform) {
         // pairs may differ in leaf set: restrict-then-join kernel, one warp per pair, all requested metrics at once
         CUDA_TRY(cudaSetDevice(d->device));
@@ -907,7 +930,11 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
                 CUDA_TRY(cudaMemsetAsync(p.wl_count, 0, sizeof(unsigned), st));
             }
             if (use_ext) { int rc = run_split_rows(ts, d, m3, p, d_out, st); if (rc) return rc; }
-            else if (use_split) { int rc = run_pairsplit(ts, d, m3, rect, p, ev_capacity, d_out, st, rf_apart); if (rc) return rc; }
+            else if (use_split) {
+                if (second) for (int m = 0; m < 3; m++) if ((m3 >> m & 1u) && !second->d_out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+                int rc = run_pairsplit(ts, d, m3, rect, p, ev_capacity, d_out, st, rf_apart, second); if (rc) return rc;
+                second_m3_done = second != nullptr;
+            }
             else {
                 if (use_join) CUDA_TRY(launch_pairjoin(m3, rect, p, d->sm_count, !(force && !strcmp(force, "join_tile")), st));
                 else CUDA_TRY(launch_pairwise(m3, rect, p, tile_rows, tile_cols, tile, st));
@@ -933,6 +960,10 @@ geodesic:
             CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
             launch_counter_add(1);
         }
+    }
+    if (second) {                                     // what the merged launch set did not cover for the second block
+        const uint32_t rest = second_m3_done ? (mask & TD_MASK(TD_GEO)) : mask;
+        if (rest) return run_pairwise(ts, d, rest, normalise, min_overlap, fail_value, rect, split, second->row_begin, second->row_end, second->d_out, st, nullptr);
     }
     return TD_OK;
 }
@@ -1151,6 +1182,27 @@ int td_pairwise_device(td_treeset *ts, uint32_t metric_mask, int normalise, int 
     if ((rc = device_of(d_out, metric_mask, &device))) return rc;
     if ((rc = check_ready(ts, device, &d))) return rc;
     return run_pairwise(ts, d, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, row_begin, row_end, d_out, (cudaStream_t)stream);
+}
+
+int td_pairwise_device2(td_treeset *ts, uint32_t metric_mask, int normalise, int min_overlap, double overlap_fail_value,
+                        const int64_t row_begin[2], const int64_t row_end[2], void *const d_out_a[4], void *const d_out_b[4], void *stream)
+{
+    if (!ts || !row_begin || !row_end || !d_out_a || !d_out_b) { set_error("null argument"); return TD_ERR_ARG; }
+    DeviceScope scope;
+    const int64_t N = ts->host.N;
+    if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
+    for (int b = 0; b < 2; b++)
+        if (row_begin[b] < 0 || row_end[b] > N || row_begin[b] > row_end[b]) { set_error("row range [%lld,%lld) outside [0,%lld]", (long long)row_begin[b], (long long)row_end[b], (long long)N); return TD_ERR_ARG; }
+    if (row_end[0] > row_begin[1] && row_end[1] > row_begin[0]) { set_error("the two row blocks overlap"); return TD_ERR_ARG; }
+    int device, dev_b, rc; DeviceSet *d;
+    if ((rc = device_of(d_out_a, metric_mask, &device))) return rc;
+    if ((rc = device_of(d_out_b, metric_mask, &dev_b))) return rc;
+    if (device != dev_b) { set_error("output pointers live on different GPUs"); return TD_ERR_ARG; }
+    if ((rc = check_ready(ts, device, &d))) return rc;
+    if (row_end[0] <= row_begin[0])
+        return run_pairwise(ts, d, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, row_begin[1], row_end[1], d_out_b, (cudaStream_t)stream);
+    const RowBlock second{row_begin[1], row_end[1], d_out_b};
+    return run_pairwise(ts, d, metric_mask, normalise, min_overlap, overlap_fail_value, false, 0, row_begin[0], row_end[0], d_out_a, (cudaStream_t)stream, &second);
 }
 
 int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4], void *stream)

@@ -47,6 +47,11 @@ struct PairParams {
     int tri_rows;             // postings pipeline: tile rows of this launch
     int normalise;
     double *out[3];           // rf, wrf, euc (device)
+    // second row block of the same launch set (multi-GPU folded blocks: a rank's long-row and short-row block share ONE events kernel and
+    // ONE exact fix-up kernel).  Only those two kernels look at these fields; row_end2 <= row_begin2: no second block
+    int64_t row_begin2, row_end2, p_base2;
+    int rg0b, groups_a;       // events kernel: row groups [0, groups_a) of the grid belong to block A (from rg0), the rest to block B (from rg0b)
+    double *out2[3];          // fix-up kernel: pairs with i >= row_begin2 write here, relative to p_base2
 };
 
 size_t pairwise_smem_bytes(int tile, int sh_stride, bool weighted);
@@ -66,7 +71,7 @@ int pairsplit_row_group();
 cudaError_t make_leaf_tensor_maps(const double *leafT, int64_t ldT, int n_k, void *tmap_a, void *tmap_b);
 cudaError_t launch_build_split_rows(const SplitRec *shared, int sh_stride, int64_t N, int64_t ld, double *rows, int max_rows, cudaStream_t st);
 long long pairsplit_tiles(bool rect, PairParams &p);
-cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches);
+cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches, const PairParams *second = nullptr);
 cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st);
 cudaError_t launch_scatter_group(const double *tmp, double *out, const int32_t *members, int64_t n_local, int64_t a0, int64_t a1, int64_t N,
                                  int64_t p_base, cudaStream_t st);

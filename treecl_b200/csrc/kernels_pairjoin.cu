@@ -679,16 +679,19 @@ __global__ void __launch_bounds__(256) exact_fixup_kernel(const PairParams p, co
         const int64_t i = ij.x, j = ij.y;
         double s1, s2;
         exact_pair_inline(p, i, j, s1, s2);                // (inlined: a call would give this usually empty kernel a stack frame)
-        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - p.p_base)) + j;
+        // (a launch set of two row blocks shares this kernel: rows of the second block write to its own outputs)
+        const bool second = !RECT && p.row_end2 > p.row_begin2 && i >= p.row_begin2 && i < p.row_end2;
+        const int64_t idx = (RECT ? i * p.n_cols - p.col_offset : (i * p.N - i * (i + 1) / 2 - i - 1 - (second ? p.p_base2 : p.p_base))) + j;
+        double *const *out = second ? p.out2 : p.out;
         if (mask & 2u) {
             double v = s1;
             if (p.normalise) { const double den = p.sum_len[i] + p.sum_len[j]; v = den != 0.0 ? v / den : 0.0; }
-            p.out[1][idx] = v;
+            out[1][idx] = v;
         }
         if (mask & 4u) {
             double v = sqrt(s2);
             if (p.normalise) { const double den = p.norm[i] + p.norm[j]; v = den != 0.0 ? v / den : 0.0; }
-            p.out[2][idx] = v;
+            out[2][idx] = v;
         }
     }
 }

@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned n_parts = cluster.num_blocks(), part = cluster.block_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rg = (int)(blockIdx.x / n_parts) + p.rg0, tree0 = rg * RG;
+    const int g_idx = (int)(blockIdx.x / n_parts);
+    const int rg = g_idx < p.groups_a ? g_idx + p.rg0 : g_idx - p.groups_a + p.rg0b, tree0 = rg * RG;       // (second row block: see PairParams)
     griddep_launch_dependents();                           // the tile kernel may start filling free SMs (it waits before it reads our output)
 
     // block-wide exclusive scan of one value per thread; returns the exclusive prefix, the total through `total`
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
     for (int q = tid; q < n_own; q += EVT) {
         const int i = tree0 + (q & (RG - 1)), pos = (q / RG) * (int)n_parts + (int)part;
         int x = -1;
-        if (i >= p.row_begin && i < p.row_end) x = p.shared_x[(size_t)i * p.sh_stride + pos];
+        if ((i >= p.row_begin && i < p.row_end) || (i >= p.row_begin2 && i < p.row_end2)) x = p.shared_x[(size_t)i * p.sh_stride + pos];
         if (x >= 0 && p.heavy_rows > 0 && p.shared[(size_t)i * p.sh_stride + pos].pad < (uint32_t)p.heavy_rows) x = -1;    // a row of the matrix, no events
         uint32_t n = 0;
         if (x >= 0) { n = (uint32_t)(p.post_end[x] - x - 1); if constexpr (WMODE) ent_len[q] = p.post_len[x]; }
@@ -790,10 +791,10 @@ static cudaError_t launch_tiles(uint32_t mask, bool rect, const PairParams &p, c
 cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st) { return launch_tiles(mask, rect, p, st, false); }
 
 // p must carry the tile geometry (pairsplit_tiles), the postings, the segment table and the event buffer; *ev_cursor must be zero
-cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int n_sms, cudaStream_t st, int *launches)
+cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p_in, int n_sms, cudaStream_t st, int *launches, const PairParams *second)
 {
     *launches = 0;
-    if (p.n_tiles <= 0) return cudaSuccess;
+    if (p_in.n_tiles <= 0 && (!second || second->n_tiles <= 0)) return cudaSuccess;
     const bool weighted = (mask & 6u) != 0;
     // TREEDIST_SYNC_DEBUG: synchronise after every launch and say which kernel failed (debug aid; kills the overlap)
     static const bool sync_debug = getenv("TREEDIST_SYNC_DEBUG") != nullptr;
@@ -802,11 +803,19 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
         if (sync_debug) fprintf(stderr, "[treedist] %s (mask %u): %s\n", what, mask, cudaGetErrorString(e));
         return e;
     };
+    // p: block A plus, for the events and fix-up kernels, the row range / outputs of block B
+    PairParams p = p_in;
+    long long groups = (long long)p.tri_rows * (TR / RG);
+    p.groups_a = (int)groups; p.row_begin2 = p.row_end2 = 0; p.rg0b = 0; p.p_base2 = 0;
+    if (second) {
+        p.row_begin2 = second->row_begin; p.row_end2 = second->row_end; p.p_base2 = second->p_base; p.rg0b = second->rg0;
+        for (int m = 0; m < 3; m++) p.out2[m] = second->out[m];
+        groups += (long long)second->tri_rows * (TR / RG);
+    }
     cudaError_t e = cudaSuccess;
     {
         // the row groups of all tile rows of this launch (p.rg0 = first group of the first tile row): the kernel writes their rows of
-        // the segment table completely, rows outside [row_begin, row_end) as empty segments
-        const long long groups = (long long)p.tri_rows * (TR / RG);
+        // the segment table completely, rows outside the row range(s) as empty segments
         const size_t smem_e = pairsplit_events_smem_bytes(mask, p.sh_stride, p.col_tiles_total);
         // CTAs per row group (a thread-block cluster).  One when the row groups alone fill the GPU (measured on the bench set: 316 groups,
         // 1 CTA each 0.156 ms per step, clusters of 2 = 632 CTAs = 1.07 waves 0.160 ms); a launch over a share of the rows (multi-GPU
@@ -822,7 +831,14 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p, int 
     static const bool no_pdl = getenv("TREEDIST_NO_PDL") != nullptr;
     e = checked(launch_tiles(mask, rect, p, st, !no_pdl && !sync_debug), "pair_dense_kernel");
     ++*launches;
-    if (e != cudaSuccess || !weighted) return e;
+    if (e != cudaSuccess) return e;
+    if (second) {
+        // block B's tiles: a launch of its own geometry reading the same segment table and records; it may start under block A's tail
+        e = checked(launch_tiles(mask, rect, *second, st, !no_pdl && !sync_debug), "pair_dense_kernel (second block)");
+        ++*launches;
+        if (e != cudaSuccess) return e;
+    }
+    if (!weighted) return e;
     ++*launches;
     return checked(launch_exact_fixup(mask, rect, p, n_sms, st), "exact_fixup_kernel");
 }
