@@ -185,6 +185,12 @@ int td_free_pinned(void *p);
 int td_pairwise_rect_device(td_treeset *ts, int64_t split, uint32_t metric_mask, int normalise, void *const d_out[4],
                             void *stream);
 
+/* The same for two SEPARATELY encoded sets and host buffers: out[metric][q * n_reference + r] = distance(query tree q, reference tree r),
+ * the block treeCl/bootstrap.py:174-218 fills with a doubly nested Python loop over _fast_geo (run_optimise_bootstrap_coords,
+ * run_out_of_sample_mds, run_analytical_fit).  Both sets must share one taxon table (same leaf labels); the library joins their split
+ * dictionaries, uploads the joint set, runs the rectangular kernels and copies the block back.  Synchronous. */
+int td_pairwise_rect(td_treeset *query, td_treeset *reference, uint32_t metric_mask, int normalise, double *const out[4], int device);
+
 /* Exact RF through the int8 tcgen05 split-incidence contraction C = X * X^T (uniform sets whose shared-split
  * dictionary is small enough); RF = S_i + S_j - 2 C_ij.  d_out: uint16 or double condensed, device pointer. */
 int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out,

@@ -559,6 +559,31 @@ class TestClassicalMDS:
         assert np.array_equal(v2, vals) and np.array_equal(out.cpu().numpy().reshape(n_trees, dims), coords)
 
 
+@pytest.mark.parametrize('kind', ['uniform', 'structured'])
+def test_query_reference_block_of_two_separate_sets(td, oracle_mod, kind):
+    """SURVEY 8(f)-1 as the reference uses it (treeCl/bootstrap.py:174-218): bootstrap trees against reference trees, the two lists
+    encoded SEPARATELY, host buffers in and out (td_pairwise_rect).  Every entry against the oracle's pair function."""
+    from treecl_b200 import _lib
+    trees = make(kind, 90, 25, seed=52)
+    q, r = trees[:35], trees[35:]
+    want = {m: squareform(oracle_mod.matrix(trees, m, nthreads=NTHREADS))[:35, 35:] for m in ('rf', 'wrf', 'euc', 'geo')}
+    tq, tr = _lib.TreeSet(q), _lib.TreeSet(r)
+    got = _lib.pairwise_rect(tq, tr, ('rf', 'wrf', 'euc', 'geo'))
+    for m in want:
+        assert got[m].shape == (35, 55)
+        assert np.array_equal(got[m], want[m]) if m == 'rf' else assert_close(got[m], want[m]) is None
+    block = td.bootstrap.query_reference_distances(q, r, 'geo')
+    assert_close(block, want['geo'])
+    # query trees on another leaf set: the block comes from the square path (restrict-then-join), still the oracle's values
+    labels = ['t%03d' % k for k in range(25)]
+    q2 = [td.Tree(t).prune_to_subset(set(labels[:20])).newick for t in q[:6]]
+    block2 = td.bootstrap.query_reference_distances(q2, r, 'euc')
+    want2 = squareform(oracle_mod.matrix(q2 + r, 'euc', nthreads=NTHREADS))[:6, 6:]
+    assert_close(block2, want2)
+    with pytest.raises(NotImplementedError):
+        _lib.pairwise_rect(_lib.TreeSet(q2), tr, ('rf',))                       # different taxon tables: encode together instead
+
+
 def test_baseline_config_2_full_vs_oracle(td, oracle_mod):
     """BASELINE configs[1] = the bench workload (5,000 x 50, seed of bench.py): EVERY entry of the rf, euc and wrf matrices against
     the oracle (12.5 M pairs per metric), plus the size-independent properties."""

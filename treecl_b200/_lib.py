@@ -77,6 +77,8 @@ def load():
     lib.td_condensed_offset.restype = i64
     lib.td_pairwise_device.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, vp]
     lib.td_pairwise.argtypes = [vp, u32, i32, i32, dbl, i64, i64, _c_void_p4, i32]
+    if hasattr(lib, 'td_pairwise_rect'):
+        lib.td_pairwise_rect.argtypes = [vp, vp, u32, i32, _c_void_p4, i32]
     if hasattr(lib, 'td_pairwise_device2'):
         lib.td_pairwise_device2.argtypes = [vp, u32, i32, i32, dbl, i64 * 2, i64 * 2, _c_void_p4, _c_void_p4, vp]
     lib.td_pairwise_rect_device.argtypes = [vp, i64, u32, i32, _c_void_p4, vp]
@@ -403,6 +405,19 @@ def device_count():
     c = ctypes.c_int()
     load().td_device_count(ctypes.byref(c))
     return c.value
+
+
+def pairwise_rect(query, reference, metrics, normalise=False, device=0):
+    """{metric: (n_query, n_reference) ndarray} for two separately encoded TreeSets over the same taxa (td_pairwise_rect)."""
+    lib = load()
+    nq, nr = query.n_trees, reference.n_trees
+    mask, table, res = 0, [None] * 4, {}
+    for m in metrics:
+        mask |= 1 << METRIC_INDEX[m]
+        res[m] = result_empty((nq, nr))
+        table[METRIC_INDEX[m]] = res[m].ctypes.data
+    check(lib.td_pairwise_rect(query._h, reference._h, mask, int(bool(normalise)), _c_void_p4(*table), int(device)))
+    return res
 
 
 def cmds_host(square, dimensions=3, max_iter=0, tol=0.0, device=0):

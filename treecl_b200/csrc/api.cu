@@ -1552,6 +1552,39 @@ int td_trim_cache(int device)
     return TD_OK;
 }
 
+int td_pairwise_rect(td_treeset *query, td_treeset *reference, uint32_t metric_mask, int normalise, double *const out[4], int device)
+{
+    if (!query || !reference || !out) { set_error("null argument"); return TD_ERR_ARG; }
+    if (!(metric_mask & 15u) || (metric_mask & ~15u)) { set_error("metric_mask 0x%x: expected a combination of TD_MASK(TD_RF..TD_GEO)", metric_mask); return TD_ERR_ARG; }
+    for (int m = 0; m < 4; m++) if ((metric_mask >> m & 1u) && !out[m]) { set_error("output pointer for metric %d is null", m); return TD_ERR_ARG; }
+    DeviceScope scope;
+    // one set with a joint split dictionary: query trees first, then the reference trees
+    td_treeset *both = new (std::nothrow) td_treeset();
+    if (!both) { set_error("out of memory"); return TD_ERR_NOMEM; }
+    struct Free { td_treeset *t; ~Free() { delete t; } } own{both};
+    int rc;
+    try { rc = concat_sets(query->host, reference->host, 0, both->host); }
+    catch (const std::bad_alloc &) { set_error("out of memory"); rc = TD_ERR_NOMEM; }
+    if (rc) return rc;
+    if ((rc = upload(both, device, 0))) return rc;
+    DeviceSet *dset = resident(both, device);
+    const int64_t nq = query->host.N, nr = reference->host.N, cells = nq * nr;
+    CUDA_TRY(cudaSetDevice(device));
+    HostCall hc; hc.device = device;
+    void *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u) {
+        cudaError_t e = pool_alloc(device, (size_t)cells * sizeof(double), &hc.dbuf[0][m], &hc.dsize[0][m]);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)cells * 8, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+        d_out[m] = hc.dbuf[0][m];
+    }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    if ((rc = run_pairwise(both, dset, metric_mask, normalise, 4, 0.0, true, nq, 0, nq, d_out, hc.bs.compute))) return rc;
+    for (int m = 0; m < 4; m++) if (metric_mask >> m & 1u)
+        CUDA_TRY(cudaMemcpyAsync(out[m], d_out[m], (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
+    CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    return take_error_flag(both, dset);
+}
+
 int td_rf_incidence_device(td_treeset *ts, int normalise, int64_t row_begin, int64_t row_end, void *d_out, int out_is_u16, void *stream)
 {
     if (!ts || !d_out) { set_error("null argument"); return TD_ERR_ARG; }

@@ -768,6 +768,39 @@ int encode_kendall_colijn(const char *const *newick, int64_t N, double lambda, i
 // ------------------------------------------------------------------------------------------------------------
 namespace td {
 
+// per-tree encoding of tree t of a packed set, splits sorted by mask (a uniform set keeps them sorted by dictionary id)
+static void tree_of_set(const HostSet &h, size_t t, TreeEnc &e)
+{
+    const int W = h.W, n_taxa = h.n_taxa, S = h.n_splits[t];
+    const size_t stride = (size_t)std::max(h.max_splits, 1);
+    e.rooted = h.tree_rooted[t]; e.n_leaves = h.n_leaves[t];
+    e.leafmask.assign(h.leafmask.begin() + t * W, h.leafmask.begin() + (t + 1) * W);
+    std::vector<int> order(S);
+    for (int s = 0; s < S; s++) order[s] = s;
+    const uint64_t *m = &h.masks[t * stride * W];
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return mask_cmp(m + (size_t)a * W, m + (size_t)b * W, W) < 0; });
+    e.masks.resize((size_t)S * W); e.lens.resize(S);
+    for (int s = 0; s < S; s++) { memcpy(&e.masks[(size_t)s * W], m + (size_t)order[s] * W, (size_t)W * 8); e.lens[s] = h.lens[t * stride + order[s]]; }
+    e.leaflen.assign(h.leaflen.begin() + t * n_taxa, h.leaflen.begin() + (t + 1) * n_taxa);
+    e.sum_len = h.sum_len[t]; e.sum_sq = h.sum_sq[t];
+}
+
+// query set followed by reference set as ONE set (joint split dictionary): what the rectangular kernels need.  Both sets must have been
+// encoded over the same taxon table (same labels); otherwise encode the two lists of trees with one call.
+int concat_sets(const HostSet &a, const HostSet &b, int n_threads, HostSet &out)
+{
+    if (a.labels != b.labels) {
+        set_error("the two sets were encoded over different taxon tables (%d and %d labels): encode their trees with one td_encode_newick call", a.n_taxa, b.n_taxa);
+        return TD_ERR_UNSUPPORTED;
+    }
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<TreeEnc> enc((size_t)(a.N + b.N));
+    parallel_for(a.N + b.N, n_threads, [&](int64_t i, int) {
+        if (i < a.N) tree_of_set(a, (size_t)i, enc[(size_t)i]); else tree_of_set(b, (size_t)(i - a.N), enc[(size_t)i]);
+    });
+    return finish_encode(enc, a.labels, n_threads, out, [](const char *) {});
+}
+
 int encode_group(const HostSet &parent, const std::vector<int32_t> &members, int n_threads, HostSet &sub)
 {
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());

@@ -74,6 +74,7 @@ int newick_labels(const char *newick, std::vector<std::string> &labels, int &roo
 int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
 // leaf-set group of a non-uniform set: the member trees (ascending indices into `parent`) re-encoded as a set of their own - uniform, with
 // its own split dictionary - for the fast kernels
+int concat_sets(const HostSet &a, const HostSet &b, int n_threads, HostSet &out);
 int encode_group(const HostSet &parent, const std::vector<int32_t> &members, int n_threads, HostSet &sub);
 size_t serialize_set(const HostSet &hs, std::vector<unsigned char> *out);      // out == nullptr: size only
 int deserialize_set(const void *data, size_t bytes, HostSet &hs);
