@@ -221,9 +221,11 @@ class Ctx(object):
         return ts, int(size.item())
 
 
-def my_blocks(ctx, n_trees):
+def my_blocks(ctx, n_trees, align=64):
+    """This rank's folded row blocks.  align: 64 rows = a tile row of the pair kernels; 512 = a tile of the 2-SM incidence kernel (a block
+    boundary inside a tile makes both neighbours compute it)."""
     from treecl_b200 import engine
-    return engine.folded_row_ranges(n_trees, ctx.world)[ctx.rank]
+    return engine.folded_row_ranges(n_trees, ctx.world, align=align)[ctx.rank]
 
 
 def block_pairs(n, blocks):
@@ -306,7 +308,7 @@ def run_config(ctx, index, steps, warmup, n_trees=None, parity_rows=2, u16=False
     t_setup = time.perf_counter() - t0
     ts.upload(ctx.local, ctx.stream.cuda_stream)
     info = ts.info
-    blocks = my_blocks(ctx, nt)
+    blocks = my_blocks(ctx, nt, 512 if u16 else 64)
     pairs_total = nt * (nt - 1) // 2
     outs = device_outputs(ctx, nt, blocks, metrics, ctx.torch.int16 if u16 else None)
 
@@ -514,7 +516,7 @@ def config4_e2e(ctx, ts, pairs_total):
     (td_rf_incidence: row bands, kernels under the copies).  Set already resident; wall clock, max over ranks."""
     from treecl_b200 import _lib
     n = ts.n_trees
-    blocks = my_blocks(ctx, n)
+    blocks = my_blocks(ctx, n, 512)
     if block_pairs(n, blocks) * 2 > (3 << 30):
         return {'skipped': 'this rank alone would need {:.1f} GB of page-locked host memory; measured at N >= 4'.format(block_pairs(n, blocks) * 2 / 1e9)}
     host = [(a, b, _lib.pinned_empty(max(_lib.condensed_offset(n, b) - _lib.condensed_offset(n, a), 1), np.uint16)) for a, b in blocks]
