@@ -392,6 +392,31 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = pairs_total * args.steps / (total_ms * 1e-3)
 
+    # ---- N > 1: the same matrix on ONE GPU of this box (rank 0 alone, the others wait), so that the strong-scaling factor can be read from
+    # this record alone: value / (pairs / one_gpu_ms)
+    one_gpu = None
+    if n_gpus > 1 and not args.no_extra:
+        one_ms = 0.0
+        if ctx.rank == 0:
+            full = {m: torch.empty(pairs_total, dtype=torch.float64, device=ctx.dev) for m in metrics}
+            f = lambda: ts.pairwise_device(metrics, {m: full[m].data_ptr() for m in metrics}, stream=ctx.stream.cuda_stream)
+            f(); f()
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(3):
+                ctx.flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ctx.stream); f(); e1.record(ctx.stream)
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            one_ms = float(np.median(ms))
+            del full
+            torch.cuda.empty_cache()
+        ctx.barrier()
+        if ctx.rank == 0:
+            one_gpu = {'ms_per_step': one_ms, 'pairs_per_s': pairs_total / (one_ms * 1e-3),
+                       'what': 'the whole matrix of this workload on rank 0 alone, same box, same kernels (median of 3 steps)'}
+
     # ---- end to end through the public call, host buffers ------------------------------------------------------------------------
     host = [(a, b, {m: _lib.pinned_empty(max(_lib.condensed_offset(nt, b) - _lib.condensed_offset(nt, a), 1)) for m in metrics}) for a, b in blocks]
 
@@ -492,6 +517,7 @@ def run_ours(args):
                        'dict_size': int(info.dict_size), 'dict_shared': int(info.dict_shared), 'max_shared': int(info.max_shared),
                        'note': None if n_gpus == 1 else 'N > 1 measures configs[2] strong-scaled; the N = 1 line measures configs[1] - compare this value with '
                                'config.extra.config3_wrf+euc of the N = 1 line (same workload on one GPU), not with its main value',
+                       'same_workload_on_one_gpu': one_gpu,
                        'extra': extra},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
