@@ -208,8 +208,8 @@ int td_rf_incidence(td_treeset *ts, int64_t row_begin, int64_t row_end, uint16_t
  *     _embedding_classical_mds     treeCl/distance_matrix.py:301-315   coords = evecs[:, :dims] * sqrt(|vals[:dims]|)
  * but only the `dimensions` leading eigenpairs are computed (blocked subspace iteration with Rayleigh-Ritz on the fp64 tensor cores),
  * and in td_cmds the N x N matrix never leaves the GPU: only the N x dimensions embedding does.  Eigenvectors are defined up to sign, as
- * with eigh.  1 <= dimensions <= 12.  The iteration stops when the leading eigenvalues move by less than `tol` (relative; <= 0: 1e-13) twice in a
- * row, or after max_iter (<= 0: 2000) products; *iterations / *residual (last relative eigenvalue change) report how it ended - a
+ * with eigh.  1 <= dimensions <= 12.  The iteration stops when the residuals || B v - lambda v || of the wanted eigenpairs fall below `tol` x the
+ * largest |eigenvalue| (<= 0: 1e-12), or after max_iter (<= 0: 5000) products; *iterations / *residual (that relative residual) report how it ended - a
  * matrix whose leading eigenvalues are (nearly) degenerate, e.g. independent random trees, converges slowly and has no well-defined
  * embedding in the reference either.
  *   td_cmds_device : condensed matrix already on the device (output of td_pairwise_device), coordinates stay on the device
@@ -221,6 +221,25 @@ int td_cmds(td_treeset *ts, int metric, int normalise, int min_overlap, double o
             double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device);
 int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol,
                  int *iterations, double *residual, int device);
+
+/* Spectral clustering's front end (treeCl/clustering.py:125-303, class Spectral) for the pruning options NONE / MANUAL and the scale options
+ * MEDIAN / MANUAL (the ESTIMATE options search a connected k-nearest-neighbour graph on the host and are not rebuilt):
+ *     kdists / kmask / kscale      treeCl/distance_matrix.py:153-186   k-th nearest distance per row, neighbour mask (OR / AND), local scale
+ *     affinity                     treeCl/distance_matrix.py:32-55     exp(-d^2 / (s_i s_j)), masked entries 0
+ *     laplace + eigen              treeCl/distance_matrix.py:189-207,285-298
+ * scale_k = 0: s = row medians (LOCAL_SCALE_MEDIAN), else the scale_k-th nearest distance (LOCAL_SCALE_MANUAL); prune_k = 0: no pruning,
+ * else kmask(prune_k) combined with its transpose by OR (prune_and = 0) or AND.
+ *   td_affinity_host             Spectral(...).affinity: the N x N affinity matrix with a unit diagonal (Spectral.decompose)
+ *   td_spectral_embedding_host   Spectral(...).spectral_embedding_(dimensions) (algo ZELNIKMANOR): affinity with a zero diagonal ->
+ *                                D^-1/2 A D^-1/2 -> leading eigenvectors -> rows scaled to unit length; coords[n_trees * dimensions]
+ *   td_spectral_embedding        the same with the distances of `metric` computed on the device: the matrix never leaves the GPU
+ * When the leading eigenvalues are (nearly) equal - well separated clusters - the eigenvectors are defined up to a rotation inside their
+ * subspace (in the reference too); the unit-length rows then agree up to that rotation. */
+int td_affinity_host(const double *square, int64_t n_trees, int prune_k, int prune_and, int scale_k, double *affinity, int device);
+int td_spectral_embedding_host(const double *square, int64_t n_trees, int dimensions, int prune_k, int prune_and, int scale_k, double *coords,
+                               double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device);
+int td_spectral_embedding(td_treeset *ts, int metric, int normalise, int dimensions, int prune_k, int prune_and, int scale_k, double *coords,
+                          double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device);
 
 /* Counters of the last geodesic launch on this set (mean GTP iterations etc.), for DESIGN.md / bench.py. */
 typedef struct {

@@ -542,7 +542,7 @@ class TestClassicalMDS:
         ts = _lib.TreeSet(trees)
         coords, vals, info = ts.cmds(metric, dims)
         want_coords, want_vals = oracle_mod.mds.classical_mds(squareform(oracle_mod.matrix(trees, metric, nthreads=NTHREADS)), dims)
-        assert info['iterations'] < 2000, info
+        assert info['iterations'] < 5000, info
         self.check(coords, vals, want_coords, want_vals, dims)
         # the same through the device-pointer entry on the library's own condensed matrix
         import torch
@@ -582,6 +582,49 @@ def test_query_reference_block_of_two_separate_sets(td, oracle_mod, kind):
     assert_close(block2, want2)
     with pytest.raises(NotImplementedError):
         _lib.pairwise_rect(_lib.TreeSet(q2), tr, ('rf',))                       # different taxon tables: encode together instead
+
+
+class TestSpectralFrontEnd:
+    """kNN distances / mask, local scale, affinity, Laplacian and its leading eigenvectors on the GPU
+    (treeCl/distance_matrix.py:32-55,153-207; treeCl/clustering.py:125-303)."""
+
+    @staticmethod
+    def same_rows(coords, want, atol=1e-6):
+        # (nearly) equal leading eigenvalues leave a rotation of the eigenvectors free: the inner products of the unit rows are invariant
+        assert np.allclose(coords.dot(coords.T), want.dot(want.T), rtol=0, atol=atol)
+
+    def test_reference_goldens(self, td):
+        import json
+        opt = td.spectral.options
+        with open(os.path.join(GOLDEN, 'mds_golden.json')) as fh:
+            cases = json.load(fh)
+        for name, c in cases.items():
+            m, dims = np.array(c['matrix']), c['dimensions']
+            dm = td.DistanceMatrix.from_array(m, ['n%d' % k for k in range(len(m))])
+            for sp in c['spectral']:
+                s = td.spectral.Spectral(dm, opt.PRUNING_MANUAL if sp['prune_k'] else opt.PRUNING_NONE,
+                                         opt.LOCAL_SCALE_MANUAL if sp['scale_k'] else opt.LOCAL_SCALE_MEDIAN,
+                                         manual_pruning=sp['prune_k'] or None, manual_scale=sp['scale_k'] or None, logic=sp['logic'])
+                assert np.allclose(s.affinity, np.array(sp['affinity']), rtol=1e-12, atol=1e-300), (name, sp)
+                emb = s.spectral_embedding_(dims)
+                assert emb.values.shape == (len(m), dims) and np.allclose(np.linalg.norm(emb.values, axis=1), 1.0)
+                assert np.all(np.abs(s.eigenvalues - np.array(sp['eigenvalues'][:dims])) <= 1e-8), (name, sp['prune_k'], s.eigenvalues)
+                self.same_rows(emb.values, np.array(sp['coords']))
+        with pytest.raises(NotImplementedError):
+            td.spectral.Spectral(dm, opt.PRUNING_ESTIMATE)
+
+    @pytest.mark.parametrize('n_trees,n_taxa,metric,dims,prune_k,logic,scale_k', [(400, 24, 'euc', 3, 0, 'or', 0), (901, 30, 'geo', 4, 60, 'or', 7),
+                                                                                    (640, 40, 'wrf', 5, 300, 'and', 0)])
+    def test_tree_sets_never_leave_the_device(self, td, oracle_mod, n_trees, n_taxa, metric, dims, prune_k, logic, scale_k):
+        from treecl_b200 import _lib, synth
+        trees = synth.structured_trees(n_trees, n_taxa, n_classes=dims, class_nni=n_taxa // 3, lam=0.7, seed=60 + dims)
+        ts = _lib.TreeSet(trees)
+        coords, vals, info = ts.spectral_embedding(metric, dims, prune_k, logic, scale_k)
+        sq = squareform(oracle_mod.matrix(trees, metric, nthreads=NTHREADS))
+        want, want_vals = oracle_mod.mds.spectral_embedding(sq, dims, prune_k, logic, scale_k)
+        assert info['iterations'] < 5000, info
+        assert np.all(np.abs(vals - want_vals[:dims]) <= 1e-8), (vals, want_vals[:dims])
+        self.same_rows(coords, want)
 
 
 def test_baseline_config_2_full_vs_oracle(td, oracle_mod):

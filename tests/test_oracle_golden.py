@@ -104,3 +104,26 @@ def test_mds_restatement_matches_the_reference_functions():
         for j in range(dims):
             s = np.sign(np.dot(coords[:, j], want[:, j]))
             assert np.allclose(s * coords[:, j], want[:, j], rtol=1e-8, atol=1e-9 * abs(want).max()), (name, j)
+
+
+def test_spectral_restatement_matches_the_reference_functions():
+    """oracle/mds.py's Spectral chain against the outputs of the reference's own kmask / kscale / affinity / laplace / eigen /
+    normalise_rows, called in the order of treeCl/clustering.py:171-228,288-303 (tests/golden/make_mds_golden.py)."""
+    import json
+    import oracle
+    with open(os.path.join(GOLDEN, 'mds_golden.json')) as fh:
+        cases = json.load(fh)
+    n_checked = 0
+    for name, c in cases.items():
+        m, dims = np.array(c['matrix']), c['dimensions']
+        for sp in c['spectral']:
+            assert np.allclose(oracle.mds.kdists(m, sp['kdists_k']).ravel(), sp['kdists'], rtol=0, atol=0)
+            aff = oracle.mds.spectral_affinity(m, sp['prune_k'], sp['logic'], sp['scale_k'])
+            assert np.allclose(aff, np.array(sp['affinity']), rtol=1e-14, atol=1e-300), (name, sp['prune_k'])
+            coords, vals = oracle.mds.spectral_embedding(m, dims, sp['prune_k'], sp['logic'], sp['scale_k'])
+            assert np.allclose(vals, sp['eigenvalues'], rtol=0, atol=1e-10)
+            want = np.array(sp['coords'])
+            # (nearly) equal leading eigenvalues leave a rotation free: compare the inner products of the unit rows
+            assert np.allclose(coords.dot(coords.T), want.dot(want.T), rtol=0, atol=1e-7), (name, sp['prune_k'], sp['scale_k'])
+            n_checked += 1
+    assert n_checked >= 8

@@ -97,6 +97,11 @@ def load():
         lib.td_cmds_device.argtypes = [vp, i64, i32, vp, vp, i32, dbl, pi_, pd_, vp]
         lib.td_cmds.argtypes = [vp, i32, i32, i32, dbl, i32, vp, vp, i32, dbl, pi_, pd_, i32]
         lib.td_cmds_host.argtypes = [vp, i64, i32, vp, vp, i32, dbl, pi_, pd_, i32]
+    if hasattr(lib, 'td_spectral_embedding'):
+        pd_, pi_ = ctypes.POINTER(dbl), ctypes.POINTER(i32)
+        lib.td_affinity_host.argtypes = [vp, i64, i32, i32, i32, vp, i32]
+        lib.td_spectral_embedding_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, i32, dbl, pi_, pd_, i32]
+        lib.td_spectral_embedding.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, dbl, pi_, pd_, i32]
     if hasattr(lib, 'td_check_errors'):         # (absent from older builds loaded through TREEDIST_LIB for A/B timing)
         lib.td_check_errors.argtypes = [vp, i32]
         lib.td_trim_cache.argtypes = [i32]
@@ -367,6 +372,17 @@ class TreeSet(object):
         it, res = ctypes.c_int(), ctypes.c_double()
         check(self._lib.td_cmds(self._h, METRIC_INDEX[metric], int(bool(normalise)), int(min_overlap), float(overlap_fail_value), int(dimensions),
                                 coords.ctypes.data, vals.ctypes.data, int(max_iter), float(tol), ctypes.byref(it), ctypes.byref(res), int(device)))
+        return coords, vals, {'iterations': it.value, 'last_relative_change': res.value}
+
+    def spectral_embedding(self, metric, dimensions=3, prune_k=0, logic='or', scale_k=0, normalise=False, device=0):
+        """Spectral(dm, ...).spectral_embedding_(dimensions) with the distance matrix of `metric` computed, turned into an affinity matrix and
+        decomposed on the GPU (td_spectral_embedding; treeCl/clustering.py:171-228,288-303).  Returns (coords with unit rows, eigenvalues, info)."""
+        coords = np.empty((self.n_trees, int(dimensions)), dtype=np.float64)
+        vals = np.empty(int(dimensions), dtype=np.float64)
+        it, res = ctypes.c_int(), ctypes.c_double()
+        check(self._lib.td_spectral_embedding(self._h, METRIC_INDEX[metric], int(bool(normalise)), int(dimensions), int(prune_k),
+                                              int(logic in ('and', '&')), int(scale_k), coords.ctypes.data, vals.ctypes.data, 0, 0.0,
+                                              ctypes.byref(it), ctypes.byref(res), int(device)))
         return coords, vals, {'iterations': it.value, 'last_relative_change': res.value}
 
     def check_errors(self, device=0):

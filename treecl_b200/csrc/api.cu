@@ -1436,12 +1436,20 @@ int td_pairwise_square(td_treeset *ts, int metric, int normalise, int min_overla
 // ---- classical MDS of a device-resident matrix --------------------------------------------------------------------------------
 namespace {
 // cond: condensed matrix on `device` (rows 0..n); coords: n x dims on the device.  Synchronous.
+// what to do with the square matrix once it is on the device
+struct EmbedJob {
+    int kind = 0;                     // 0: classical MDS; 1: spectral embedding (Spectral.spectral_embedding_); 2: affinity matrix only
+    int prune_k = 0, prune_and = 0, scale_k = 0;
+    double *affinity_host = nullptr;  // kind 2: n x n result (host)
+};
+
 int cmds_on_device(int device, const double *cond, const double *square_host, int64_t n, int dims, double *d_coords, double *eigenvalues, int max_iter,
-                   double tol, int *iterations, double *residual, cudaStream_t st)
+                   double tol, int *iterations, double *residual, cudaStream_t st, const EmbedJob &job = EmbedJob())
 {
-    if (n < 2 || dims < 1 || dims > cmds_block() - 4 || dims >= n) { set_error("cmds: need 1 <= dimensions <= %d and dimensions < n_trees", cmds_block() - 4); return TD_ERR_ARG; }
-    if (max_iter <= 0) max_iter = 2000;
-    if (!(tol > 0.0)) tol = 1e-13;
+    if (job.kind != 2 && (n < 2 || dims < 1 || dims > cmds_block() - 4 || dims >= n)) { set_error("embedding: need 1 <= dimensions <= %d and dimensions < n_trees", cmds_block() - 4); return TD_ERR_ARG; }
+    if (job.kind != 0 && (job.prune_k < 0 || job.prune_k >= n || job.scale_k < 0 || job.scale_k >= n)) { set_error("spectral: pruning / scale neighbour counts must lie in [0, n_trees)"); return TD_ERR_ARG; }
+    if (max_iter <= 0) max_iter = 5000;
+    if (!(tol > 0.0)) tol = 1e-12;
     struct Own { int device; void *sq = nullptr, *work = nullptr, *pin = nullptr; size_t sq_got = 0, work_got = 0;
                  ~Own() { if (sq) pool_free(device, sq, sq_got); if (work) pool_free(device, work, work_got); pinned_free(pin); } } own{device};
     cudaError_t e = pool_alloc(device, (size_t)n * n * sizeof(double), &own.sq, &own.sq_got);
@@ -1450,7 +1458,17 @@ int cmds_on_device(int device, const double *cond, const double *square_host, in
     if ((e = pinned_alloc(3 * 16 * 16 * sizeof(double) + 64, &own.pin)) != cudaSuccess) { set_error("cudaHostAlloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
     if (cond) { CUDA_TRY(launch_square_rows(cond, (double *)own.sq, n, 0, n, st)); launch_counter_add(1); }
     else CUDA_TRY(cudaMemcpyAsync(own.sq, square_host, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(run_cmds((double *)own.sq, n, dims, (double *)own.work, (double *)own.pin, d_coords, eigenvalues, max_iter, tol, iterations, residual, st));
+    if (job.kind == 0)
+        CUDA_TRY(run_cmds((double *)own.sq, n, dims, (double *)own.work, (double *)own.pin, d_coords, eigenvalues, max_iter, tol, iterations, residual, st));
+    else if (job.kind == 1)
+        CUDA_TRY(run_spectral((double *)own.sq, n, dims, job.prune_k, job.prune_and, job.scale_k, (double *)own.work, (double *)own.pin, d_coords, eigenvalues,
+                              max_iter, tol, iterations, residual, st));
+    else {
+        // Spectral.decompose: the affinity matrix with a unit diagonal (treeCl/clustering.py:171-228), back to the host
+        CUDA_TRY(run_affinity((double *)own.sq, n, job.prune_k, job.prune_and, job.scale_k, 1.0, (double *)own.work, st));
+        CUDA_TRY(cudaMemcpyAsync(job.affinity_host, own.sq, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return TD_OK;
 }
 }  // namespace
@@ -1492,13 +1510,14 @@ int td_cmds(td_treeset *ts, int metric, int normalise, int min_overlap, double o
     return take_error_flag(ts, dset);
 }
 
-int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol, int *iterations,
-                 double *residual, int device)
+// shared body of the host-matrix entry points (td_cmds_host, td_spectral_embedding_host, td_affinity_host)
+static int embed_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol, int *iterations,
+                      double *residual, int device, const EmbedJob &job)
 {
-    if (!square || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); set_error("no CUDA device available; libtreedist_cuda has no CPU fallback"); return TD_ERR_NO_DEVICE; }
     if (device < 0 || device >= count) { set_error("device %d out of range", device); return TD_ERR_ARG; }
+    if (n_trees < 1) { set_error("empty matrix"); return TD_ERR_ARG; }
     DeviceScope scope;
     CUDA_TRY(cudaSetDevice(device));
     HostCall hc; hc.device = device;
@@ -1506,10 +1525,61 @@ int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *
     if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
     CUDA_TRY(acquire_streams(device, &hc.bs));
     int rc;
-    if ((rc = cmds_on_device(device, nullptr, square, n_trees, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)n_trees * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
-    CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    if ((rc = cmds_on_device(device, nullptr, square, n_trees, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute, job))) return rc;
+    if (job.kind != 2) {
+        CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)n_trees * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
+        CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    }
     return TD_OK;
+}
+
+int td_cmds_host(const double *square, int64_t n_trees, int dimensions, double *coords, double *eigenvalues, int max_iter, double tol, int *iterations,
+                 double *residual, int device)
+{
+    if (!square || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    return embed_host(square, n_trees, dimensions, coords, eigenvalues, max_iter, tol, iterations, residual, device, EmbedJob());
+}
+
+int td_spectral_embedding_host(const double *square, int64_t n_trees, int dimensions, int prune_k, int prune_and, int scale_k, double *coords,
+                               double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device)
+{
+    if (!square || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    EmbedJob job; job.kind = 1; job.prune_k = prune_k; job.prune_and = prune_and; job.scale_k = scale_k;
+    return embed_host(square, n_trees, dimensions, coords, eigenvalues, max_iter, tol, iterations, residual, device, job);
+}
+
+int td_affinity_host(const double *square, int64_t n_trees, int prune_k, int prune_and, int scale_k, double *affinity, int device)
+{
+    if (!square || !affinity) { set_error("null argument"); return TD_ERR_ARG; }
+    EmbedJob job; job.kind = 2; job.prune_k = prune_k; job.prune_and = prune_and; job.scale_k = scale_k; job.affinity_host = affinity;
+    double dummy = 0.0;
+    return embed_host(square, n_trees, 1, &dummy, &dummy, 0, 0.0, nullptr, nullptr, device, job);
+}
+
+int td_spectral_embedding(td_treeset *ts, int metric, int normalise, int dimensions, int prune_k, int prune_and, int scale_k, double *coords,
+                          double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, int device)
+{
+    if (!ts || !coords || !eigenvalues) { set_error("null argument"); return TD_ERR_ARG; }
+    if (metric < 0 || metric > 3) { set_error("unknown metric %d", metric); return TD_ERR_ARG; }
+    DeviceScope scope;
+    int rc;
+    if ((rc = upload(ts, device, 0))) return rc;
+    DeviceSet *dset = resident(ts, device);
+    const int64_t N = ts->host.N, pairs = N * (N - 1) / 2;
+    CUDA_TRY(cudaSetDevice(device));
+    HostCall hc; hc.device = device;
+    cudaError_t e = pool_alloc(device, (size_t)std::max<int64_t>(pairs, 1) * sizeof(double), &hc.extra, &hc.extra_size);
+    if (e == cudaSuccess) e = pool_alloc(device, (size_t)N * std::max(dimensions, 1) * sizeof(double) + 64, &hc.dbuf[0][0], &hc.dsize[0][0]);
+    if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+    CUDA_TRY(acquire_streams(device, &hc.bs));
+    void *d_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    d_out[metric] = hc.extra;
+    if ((rc = run_pairwise(ts, dset, 1u << metric, normalise, 4, 0.0, false, 0, 0, N, d_out, hc.bs.compute))) return rc;
+    EmbedJob job; job.kind = 1; job.prune_k = prune_k; job.prune_and = prune_and; job.scale_k = scale_k;
+    if ((rc = cmds_on_device(device, (const double *)hc.extra, nullptr, N, dimensions, (double *)hc.dbuf[0][0], eigenvalues, max_iter, tol, iterations, residual, hc.bs.compute, job))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(coords, hc.dbuf[0][0], (size_t)N * dimensions * sizeof(double), cudaMemcpyDeviceToHost, hc.bs.compute));
+    CUDA_TRY(cudaStreamSynchronize(hc.bs.compute));
+    return take_error_flag(ts, dset);
 }
 
 int td_alloc_pinned(int64_t bytes, void **out)

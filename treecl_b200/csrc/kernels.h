@@ -120,6 +120,9 @@ cudaError_t launch_bigtree(const GeoParams &g, int general, int max_splits, unsi
 // classical MDS on the device-resident matrix (kernels_embed.cu)
 size_t cmds_workspace_doubles(int64_t n);
 int cmds_block();
+cudaError_t run_affinity(double *sq, int64_t n, int prune_k, int prune_and, int scale_k, double diag, double *vec, cudaStream_t st);
+cudaError_t run_spectral(double *sq, int64_t n, int dims, int prune_k, int prune_and, int scale_k, double *work, double *h_pinned, double *d_coords,
+                         double *eigenvalues, int max_iter, double tol, int *iterations, double *residual, cudaStream_t st);
 cudaError_t run_cmds(double *sq, int64_t n, int dims, double *work, double *h_pinned, double *d_coords, double *eigenvalues, int max_iter, double tol,
                      int *iterations, double *residual, cudaStream_t st);
 
