@@ -169,6 +169,10 @@ class Collection(object):
         :param normalise, min_overlap, overlap_fail_value: as in the reference (overlap_fail_value is coerced to float).
         :param devices: optional list of CUDA device ordinals to shard the matrix over (extension).
         :return: DistanceMatrix with names == self.names.
+
+        Needs a CUDA device (no CPU fallback).  Trees of any size are accepted: up to 128 internal edges per tree run on the fast
+        kernels, larger ones (to 1,024 internal edges) on a slower warp-per-pair kernel; trees that differ in leaf set are grouped by
+        leaf set and only the pairs across groups are pruned to their common leaves (treeCl/treedist.py:63-68).
         """
         metrics = {'euc': tasks.EuclideanTreeDistance,
                    'geo': tasks.GeodesicTreeDistance,
