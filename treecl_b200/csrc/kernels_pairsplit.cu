@@ -46,14 +46,21 @@ constexpr int KCH = 16;               // taxa per staged chunk
 #ifndef PS_NSTAGE
 #define PS_NSTAGE 4
 #endif
-#ifndef PS_MINB
-#define PS_MINB 3
+// CTAs per SM and rows of the epilogue handled together, per metric mask.  Four CTAs per SM (64 registers) with two rows at a time beat
+// three CTAs (80 registers) with eight rows - 0.1403 vs 0.1479 ms per step of the bench set, A/B in one call - wherever the kernel fits
+// 64 registers without spilling, i.e. for every mask except wrf + euc together (20 bytes of spills there: 5.42 vs 5.34 ms on config 3).
+// -DPS_MINB / -DPS_OB force one setting for all masks (experiments).
+#ifdef PS_MINB
+constexpr int min_blocks(uint32_t) { return PS_MINB; }
+#else
+constexpr int min_blocks(uint32_t mask) { return (mask & 6u) == 6u ? 3 : 4; }
 #endif
-#ifndef PS_OB
-#define PS_OB 8
+#ifdef PS_OB
+constexpr int rows_at_once(uint32_t) { return PS_OB; }
+#else
+constexpr int rows_at_once(uint32_t mask) { return (mask & 6u) == 6u ? 8 : 2; }
 #endif
 constexpr int NSTAGE = PS_NSTAGE;     // chunks in flight
-constexpr int OB = PS_OB;             // rows of the epilogue handled together
 constexpr int SA = 68, SB = 36;       // row strides (doubles) of the staged leaf chunks: = 4 mod 16 -> conflict-free DMMA fragments
 constexpr int ES = 40;                // row stride (doubles) of the per-cell slots: conflict-free 16-byte accesses of the C fragments
 // (Q + E) subtracts.  A result below 0.2 % of Q = Q_i + Q_j (error amplification 500: relative error <= 500 * (n_taxa + splits) * 2^-53,
@@ -327,12 +334,13 @@ __device__ __noinline__ void queue_exact(const PairParams &p, int64_t i, int64_t
 // One CTA per 64 x 32 tile.  Every global read of the tile is requested in the first instructions (segment bounds, per-tree scalars
 // into registers, the first NSTAGE leaf chunks as TMA bulk copies) and consumed as late as possible.
 template <uint32_t MASK, bool RECT, bool NORM>
-__global__ void __launch_bounds__(NT, PS_MINB) pair_dense_kernel(const __grid_constant__ PairParams p, const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(NT, min_blocks(MASK)) pair_dense_kernel(const __grid_constant__ PairParams p, const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b)
 {
     constexpr bool kRF = MASK & 1u, kWRF = (MASK >> 1) & 1u, kEUC = (MASK >> 2) & 1u;
     constexpr bool kWeighted = kWRF || kEUC;
     constexpr int WMODE = wmode_of(MASK), REC = rec_bytes(WMODE);
+    constexpr int OB = rows_at_once(MASK);                 // rows of the epilogue handled together
 
     // ---- which tile.  Rectangular: blockIdx = (column tile, tile row).  Triangular: tile row u holds L0 - 2u column tiles; rows u
     // and R-1-u are folded into one grid row of constant length 2 L0 - 2 (R-1), so no CTA has to invert the triangular numbering.
