@@ -37,6 +37,12 @@ struct Bits {
 #pragma unroll
         for (int h = H - 1; h >= 0; h--) if (w[h]) r = 32 * h + __ffs(w[h]) - 1;
         return r; }
+    // lowest set bit, cleared (the set must not be empty)
+    __device__ __forceinline__ int pop_first() {
+        int r = -1; bool done = false;
+#pragma unroll
+        for (int h = 0; h < H; h++) if (!done && w[h]) { r = 32 * h + __ffs(w[h]) - 1; w[h] &= w[h] - 1; done = true; }
+        return r; }
     __device__ __forceinline__ void reset(int i) {
 #pragma unroll
         for (int h = 0; h < H; h++) w[h] &= ~((uint32_t)((i >> 5) == h) << (i & 31)); }
@@ -195,7 +201,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
     {
         Bits<H> it = setB;
         while (it.any()) {
-            const int b = it.first(); it.reset(b);
+            const int b = it.pop_first();
             uint64_t mb[W];
 #pragma unroll
             for (int w = 0; w < W; w++) mb[w] = sm.maskB[b * W + w];
@@ -252,14 +258,16 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
             st.flows++;
             // vertex weights -> residual capacities of the source / sink edges
             double ra[H], rb[H], wa[H], wb[H];
+            Bits<H> fpos[H];                    // my row a of "flow[a][b] > FLOW_TOL", kept in step with every write of the flow matrix
 #pragma unroll
             for (int h = 0; h < H; h++) {
+                fpos[h].clear();
                 wa[h] = RA.mine(h, lane) ? la2[h] / sa : 0.0;
                 wb[h] = RB.mine(h, lane) ? lb2[h] / sb : 0.0;
                 ra[h] = wa[h]; rb[h] = wb[h];
                 if (RA.mine(h, lane)) {                             // zero my row of the flow matrix (only edges of the graph)
                     Bits<H> nb = inc[h] & RB;
-                    while (nb.any()) { const int b = nb.first(); nb.reset(b); flow[(lane + 32 * h) * FS + b] = 0.0; }
+                    while (nb.any()) { const int b = nb.pop_first(); flow[(lane + 32 * h) * FS + b] = 0.0; }
                 }
             }
             __syncwarp();
@@ -267,7 +275,7 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
             {
                 Bits<H> it = RA;
                 while (it.any()) {
-                    const int a = it.first(); it.reset(a);
+                    const int a = it.pop_first();
                     double x = fetch_d<H>(ra, a);
                     const Bits<H> nbm = fetch_bits<H>(inc, a) & RB;
 #pragma unroll
@@ -280,6 +288,9 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
                         const double tot = __shfl_sync(FULL, incl, 31);
                         const double take = fmin(avail, fmax(0.0, x - (incl - avail)));
                         if (take > 0.0) { rb[h] -= take; flow[a * FS + lane + 32 * h] = take; }
+                        const uint32_t carries = __ballot_sync(FULL, take > FLOW_TOL);
+#pragma unroll
+                        for (int ha = 0; ha < H; ha++) if ((a >> 5) == ha && lane == (a & 31)) fpos[ha].w[h] = carries;
                         x = fmax(0.0, x - tot);
                     }
                     owner_store<H>(ra, a, lane, x);
@@ -313,16 +324,13 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
 #pragma unroll
                     for (int h = 0; h < H; h++) sinks.w[h] = __ballot_sync(FULL, mine_sink[h]);
                     if (sinks.any()) { sink = sinks.first(); break; }
-                    // B -> A through edges that carry flow
+                    // B -> A through edges that carry flow (fpos: no walk over the candidates, no shared-memory reads)
                     Bits<H> newA;
 #pragma unroll
                     for (int h = 0; h < H; h++) {
-                        const int s = lane + 32 * h;
-                        bool found = false;
-                        if (RA.mine(h, lane) && !visA.mine(h, lane)) {
-                            Bits<H> cand = inc[h] & newB;
-                            while (cand.any()) { const int b = cand.first(); cand.reset(b); if (flow[s * FS + b] > FLOW_TOL) { parA[h] = b; found = true; break; } }
-                        }
+                        const Bits<H> cand = fpos[h] & newB;
+                        const bool found = RA.mine(h, lane) && !visA.mine(h, lane) && cand.any();
+                        if (found) parA[h] = cand.first();
                         newA.w[h] = __ballot_sync(FULL, found);
                     }
 #pragma unroll
@@ -343,9 +351,19 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
                 b = sink;
                 for (int hop = 0; hop < 2 * CAP + 2; hop++) {
                     const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
-                    if (lane == 0) flow[a * FS + b] += delta;
+                    int carries = 0;                                            // lane 0 owns the flow matrix; bit 0: forward edge, bit 1: back edge
+                    if (lane == 0) {
+                        const double fwd = flow[a * FS + b] + delta; flow[a * FS + b] = fwd; carries = fwd > FLOW_TOL;
+                        if (pb >= 0) { const double back = flow[a * FS + pb] - delta; flow[a * FS + pb] = back; carries |= (int)(back > FLOW_TOL) << 1; }
+                    }
+                    carries = __shfl_sync(FULL, carries, 0);
+                    const bool mine_a = lane == (a & 31);
+#pragma unroll
+                    for (int ha = 0; ha < H; ha++) if ((a >> 5) == ha && mine_a) {
+                        if (carries & 1) fpos[ha].set(b); else fpos[ha].reset(b);
+                        if (pb >= 0) { if (carries & 2) fpos[ha].set(pb); else fpos[ha].reset(pb); }
+                    }
                     if (pb < 0) { owner_sub<H>(ra, a, lane, delta); break; }
-                    if (lane == 0) flow[a * FS + pb] -= delta;
                     b = pb;
                 }
                 __syncwarp();

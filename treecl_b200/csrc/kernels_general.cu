@@ -97,7 +97,7 @@ __device__ __forceinline__ Bits<H> restrict_tree(const GeoParams &p, int64_t t, 
         if (rep) {
             Bits<H> it = valid;
             while (it.any()) {
-                const int t2 = it.first(); it.reset(t2);
+                const int t2 = it.pop_first();
                 if (t2 == s || !mask_eq<W>(&smask[t2 * W], m[h])) continue;
                 if (t2 < s) { rep = false; break; }
                 sum += slen[t2];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
                 sumA += lenA[h]; sqA += la2[h];
                 int partner = -1;
                 Bits<H> it = validB;
-                while (it.any()) { const int b = it.first(); it.reset(b); if (mask_eq<W>(&sm.core.maskB[b * W], mA[h])) { partner = b; break; } }
+                while (it.any()) { const int b = it.pop_first(); if (mask_eq<W>(&sm.core.maskB[b * W], mA[h])) { partner = b; break; } }
                 if (partner >= 0) { const double d = lenA[h] - sm.core.lenB[partner]; c1 += fabs(d); c2 = fma(d, d, c2); }
                 else { ncA = true; o1 += fabs(lenA[h]); o2 += la2[h]; }
             }
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
                 sumB += lenB[h]; sqB += lb2[h];
                 bool found = false;
                 Bits<H> it = validA;
-                while (it.any()) { const int a = it.first(); it.reset(a); if (mask_eq<W>(&sm.maskA[a * W], mB[h])) { found = true; break; } }
+                while (it.any()) { const int a = it.pop_first(); if (mask_eq<W>(&sm.maskA[a * W], mB[h])) { found = true; break; } }
                 if (!found) { ncB = true; o1 += fabs(lenB[h]); o2 += lb2[h]; }
             }
             setA.w[h] = __ballot_sync(FULL, ncA); setB.w[h] = __ballot_sync(FULL, ncB);
