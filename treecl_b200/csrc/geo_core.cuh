@@ -171,6 +171,29 @@ __device__ __forceinline__ bool next_pair(const GeoParams &p, PairFeed &f, int l
     return true;
 }
 
+// Warps per CTA of a warp-per-pair kernel whose warps each own `warp_bytes` of dynamic shared memory: the block size (4, 2 or 1 warps)
+// that puts the most warps on an SM.  These kernels are latency-bound (ncu: 8 warps/SM at 50 taxa with 4-warp blocks, issue slots
+// 35 % busy), and the per-warp flow matrix is what limits residency, so the granularity of a block matters.
+template <class Kernel>
+inline cudaError_t pick_block_warps(Kernel k, size_t warp_bytes, int &warps, int &per_sm)
+{
+    if (warp_bytes > 225 * 1024) return cudaErrorInvalidConfiguration;
+    int first = GEO_WARPS;
+    while (first > 1 && warp_bytes * first > 200 * 1024) first >>= 1;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * first));
+    if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    warps = first; per_sm = 0;
+    for (int w = first; w >= 1; w >>= 1) {
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, w * 32, warp_bytes * w);
+        if (e != cudaSuccess) return e;
+        if (n * w > per_sm * warps) { warps = w; per_sm = n; }
+    }
+    if (per_sm < 1) per_sm = 1;
+    return cudaSuccess;
+}
+
 template <int H, int W>
 struct WarpSmem {
     static constexpr int CAP = 32 * H;
@@ -265,10 +288,6 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
                 wa[h] = RA.mine(h, lane) ? la2[h] / sa : 0.0;
                 wb[h] = RB.mine(h, lane) ? lb2[h] / sb : 0.0;
                 ra[h] = wa[h]; rb[h] = wb[h];
-                if (RA.mine(h, lane)) {                             // zero my row of the flow matrix (only edges of the graph)
-                    Bits<H> nb = inc[h] & RB;
-                    while (nb.any()) { const int b = nb.pop_first(); flow[(lane + 32 * h) * FS + b] = 0.0; }
-                }
             }
             __syncwarp();
             // greedy saturation: push every source edge into its neighbours' sink edges, in split order
@@ -351,17 +370,19 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
                 b = sink;
                 for (int hop = 0; hop < 2 * CAP + 2; hop++) {
                     const int a = fetch_i<H>(parB, b); const int pb = fetch_i<H>(parA, a);
-                    int carries = 0;                                            // lane 0 owns the flow matrix; bit 0: forward edge, bit 1: back edge
-                    if (lane == 0) {
-                        const double fwd = flow[a * FS + b] + delta; flow[a * FS + b] = fwd; carries = fwd > FLOW_TOL;
-                        if (pb >= 0) { const double back = flow[a * FS + pb] - delta; flow[a * FS + pb] = back; carries |= (int)(back > FLOW_TOL) << 1; }
-                    }
-                    carries = __shfl_sync(FULL, carries, 0);
+                    // the owner lane of row a updates the flow matrix and its bit row; a cell whose bit is clear counts as 0 (it may
+                    // hold a value of an earlier max-flow: the matrix is never cleared)
                     const bool mine_a = lane == (a & 31);
 #pragma unroll
                     for (int ha = 0; ha < H; ha++) if ((a >> 5) == ha && mine_a) {
-                        if (carries & 1) fpos[ha].set(b); else fpos[ha].reset(b);
-                        if (pb >= 0) { if (carries & 2) fpos[ha].set(pb); else fpos[ha].reset(pb); }
+                        const double fwd = (fpos[ha].test(b) ? flow[a * FS + b] : 0.0) + delta;
+                        flow[a * FS + b] = fwd;
+                        if (fwd > FLOW_TOL) fpos[ha].set(b); else fpos[ha].reset(b);
+                        if (pb >= 0) {
+                            const double back = flow[a * FS + pb] - delta;          // parA[a] = pb was taken from fpos: the cell is live
+                            flow[a * FS + pb] = back;
+                            if (!(back > FLOW_TOL)) fpos[ha].reset(pb);
+                        }
                     }
                     if (pb < 0) { owner_sub<H>(ra, a, lane, delta); break; }
                     b = pb;

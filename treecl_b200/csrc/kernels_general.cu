@@ -226,18 +226,11 @@ template <int H, int W>
 cudaError_t launch_gen(const GeoParams &p, int n_sms, cudaStream_t st)
 {
     auto k = general_kernel<H, W>;
-    // warps per CTA: as many (<= GEO_WARPS) as the per-warp shared-memory region allows
     const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double);
-    int warps = GEO_WARPS;
-    while (warps > 1 && warp_bytes * warps > 200 * 1024) warps--;
-    if (warp_bytes > 225 * 1024) return cudaErrorInvalidConfiguration;
+    int warps = 1, per_sm = 1;
+    cudaError_t e = pick_block_warps(k, warp_bytes, warps, per_sm);
+    if (e != cudaSuccess) return e;
     const size_t smem = warp_bytes * warps;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, warps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
     const int64_t pairs = p.p_end - p.p_begin;
     int64_t blocks = (int64_t)n_sms * per_sm;
     const int64_t need = (pairs + warps - 1) / warps;
