@@ -727,6 +727,39 @@ static int run_bigtree(td_treeset *ts, DeviceSet *d, GeoParams &g, int general, 
     return TD_OK;
 }
 
+// Warp-per-pair GTP kernels (geodesic / general): plan the launch, provide the per-warp flow matrices in global memory when the plan asks
+// for them (the set's big-tree scratch buffer, one such launch at a time: later ones wait on big_done), launch.
+static int run_warp_kernel(td_treeset *ts, DeviceSet *d, GeoParams &g, int general, cudaStream_t st)
+{
+    const HostSet &h = ts->host;
+    const int cap = h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128);
+    GeoPlan plan;
+    CUDA_TRY(general ? plan_general(g, cap, d->sm_count, plan) : plan_geodesic(g, cap, d->sm_count, plan));
+    CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
+    if (plan.scratch_bytes == 0) {
+        g.flow_scratch = nullptr;
+        CUDA_TRY(general ? launch_general(g, cap, plan, st) : launch_geodesic(g, cap, plan, st));
+    } else {
+        std::lock_guard<std::mutex> guard(d->big_mu);
+        if (!d->big_done) CUDA_TRY(cudaEventCreateWithFlags(&d->big_done, cudaEventDisableTiming));
+        if (plan.scratch_bytes > d->big_bytes) {
+            CUDA_TRY(cudaEventSynchronize(d->big_done));
+            if (d->big_scratch) pool_free(d->device, d->big_scratch, d->big_got);
+            d->big_scratch = nullptr; d->big_bytes = 0;
+            void *blk = nullptr; size_t got = 0;
+            cudaError_t e = pool_alloc(d->device, plan.scratch_bytes, &blk, &got);
+            if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes of flow scratch failed: %s", (long long)plan.scratch_bytes, cudaGetErrorString(e)); return TD_ERR_NOMEM; }
+            d->big_scratch = (unsigned char *)blk; d->big_bytes = plan.scratch_bytes; d->big_got = got;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(st, d->big_done, 0));
+        g.flow_scratch = (double *)d->big_scratch;
+        CUDA_TRY(general ? launch_general(g, cap, plan, st) : launch_geodesic(g, cap, plan, st));
+        CUDA_TRY(cudaEventRecord(d->big_done, st));
+    }
+    launch_counter_add(1);
+    return TD_OK;
+}
+
 static int upload(td_treeset *ts, int device, cudaStream_t st);
 static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normalise, int min_overlap, double fail_value, bool rect,
                         int64_t split, int64_t row_begin, int64_t row_end, void *const d_out[4], cudaStream_t st, const RowBlock *second = nullptr);
@@ -824,11 +857,7 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
         if (g.p_end > g.p_begin) {
             if (big) { int rc = run_bigtree(ts, d, g, 1, st); if (rc) return rc; }
-            else {
-                CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
-                CUDA_TRY(launch_general(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
-                launch_counter_add(1);
-            }
+            else { int rc = run_warp_kernel(ts, d, g, 1, st); if (rc) return rc; }
             if (grouped) return run_groups(ts, d, mask, normalise, row_begin, row_end, d_out, st);
         }
         return TD_OK;
@@ -956,9 +985,7 @@ geodesic:
             g.outs[3] = g.out; g.metric_mask = 8u;
             int rc = run_bigtree(ts, d, g, 0, st); if (rc) return rc;
         } else if (g.p_end > g.p_begin) {
-            CUDA_TRY(cudaMemsetAsync(g.work_counter, 0, sizeof(unsigned long long), st));
-            CUDA_TRY(launch_geodesic(g, h.max_splits <= 32 ? 32 : (h.max_splits <= 64 ? 64 : 128), d->sm_count, st));
-            launch_counter_add(1);
+            int rc = run_warp_kernel(ts, d, g, 0, st); if (rc) return rc;
         }
     }
     if (second) {                                     // what the merged launch set did not cover for the second block

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 
@@ -177,20 +179,43 @@ __device__ __forceinline__ bool next_pair(const GeoParams &p, PairFeed &f, int l
 template <class Kernel>
 inline cudaError_t pick_block_warps(Kernel k, size_t warp_bytes, int &warps, int &per_sm)
 {
-    if (warp_bytes > 225 * 1024) return cudaErrorInvalidConfiguration;
+    warps = 0; per_sm = 0;
+    if (warp_bytes > 225 * 1024) return cudaSuccess;          // does not fit: 0 warps
     int first = GEO_WARPS;
     while (first > 1 && warp_bytes * first > 200 * 1024) first >>= 1;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * first));
     if (e != cudaSuccess) return e;
     (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    warps = first; per_sm = 0;
     for (int w = first; w >= 1; w >>= 1) {
         int n = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, w * 32, warp_bytes * w);
         if (e != cudaSuccess) return e;
         if (n * w > per_sm * warps) { warps = w; per_sm = n; }
     }
-    if (per_sm < 1) per_sm = 1;
+    return cudaSuccess;
+}
+
+// Shared or global flow matrix (kernels.h GeoPlan): global when it keeps at least 1.3 x the warps resident.  TREEDIST_GEO_FLOW=smem|global
+// forces one form (A/B runs).
+template <class Kernel>
+inline cudaError_t plan_warp_kernel(Kernel k, size_t fixed_bytes, size_t flow_bytes, int64_t pairs, int n_sms, GeoPlan &plan)
+{
+    int ws = 0, ns = 0, wg = 0, ng = 0;
+    cudaError_t e = pick_block_warps(k, fixed_bytes, wg, ng);
+    if (e != cudaSuccess) return e;
+    e = pick_block_warps(k, fixed_bytes + flow_bytes, ws, ns);
+    if (e != cudaSuccess) return e;
+    if (wg * ng == 0) return cudaErrorInvalidConfiguration;
+    bool global = ws * ns == 0 || wg * ng * 10 >= ws * ns * 13;
+    if (const char *f = getenv("TREEDIST_GEO_FLOW")) { if (!strcmp(f, "global")) global = true; else if (!strcmp(f, "smem") && ws * ns > 0) global = false; }
+    const int warps = global ? wg : ws, per_sm = global ? ng : ns;
+    plan.warps = warps; plan.smem = (fixed_bytes + (global ? 0 : flow_bytes)) * warps;
+    int64_t blocks = (int64_t)n_sms * per_sm;
+    const int64_t need = (pairs + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    if (blocks < 1) blocks = 1;
+    plan.blocks = (int)blocks;
+    plan.scratch_bytes = global ? (size_t)blocks * warps * flow_bytes : 0;
     return cudaSuccess;
 }
 

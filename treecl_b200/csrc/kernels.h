@@ -101,15 +101,21 @@ struct GeoParams {
     int min_overlap;
     double fail_value;
     unsigned long long *work_counter;    // dynamic pair scheduler
+    double *flow_scratch;                // per-warp flow matrices in global memory (GeoPlan::scratch_bytes), or nullptr: in shared memory
     unsigned long long *stats;           // [4]: pairs, maxflow solves, final ratios, augmentations
     int *error_flag;                     // bit 0: an iteration cap was hit; bit 1: rooted vs unrooted pair
 };
 
-// cap: 32 or 64 (max internal edges per tree the warp-per-pair GTP kernel holds in registers/shared memory)
-cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
-size_t geodesic_smem_bytes(int cap, int W, int warps);
+// Launch shape of the warp-per-pair GTP kernels.  The fp64 flow matrix of a warp (flow_rows x (flow_rows|1)) lives in shared memory when
+// that does not cost residency, else in a per-warp slice of global memory (scratch_bytes > 0: the caller provides GeoParams::flow_scratch):
+// since the BFS reads bit rows held in registers, the matrix is touched only by the greedy start and along augmenting paths.
+struct GeoPlan { int warps = 0, blocks = 0; size_t smem = 0, scratch_bytes = 0; };
+// cap: 32, 64 or 128 (max internal edges per tree the warp-per-pair GTP kernel holds in registers/shared memory)
+cudaError_t plan_geodesic(const GeoParams &p, int cap, int n_sms, GeoPlan &plan);
+cudaError_t launch_geodesic(const GeoParams &p, int cap, const GeoPlan &plan, cudaStream_t st);
 // pairs with different leaf sets (non-uniform sets): restrict-then-join, all four metrics
-cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st);
+cudaError_t plan_general(const GeoParams &p, int cap, int n_sms, GeoPlan &plan);
+cudaError_t launch_general(const GeoParams &p, int cap, const GeoPlan &plan, cudaStream_t st);
 
 // trees with more than 128 internal edges (kernels_bigtrees.cu): all four metrics, same or different leaf sets, per-warp global scratch
 size_t bigtree_warp_bytes(int max_splits, int W, int n_taxa);

@@ -118,10 +118,12 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int FS = p.flow_rows | 1;
-    const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (size_t)p.flow_rows * FS * sizeof(double);
+    const size_t flow_doubles = (size_t)p.flow_rows * FS;
+    const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (p.flow_scratch ? 0 : flow_doubles * sizeof(double));
     unsigned char *wbase = smem_raw + (size_t)(threadIdx.x >> 5) * warp_bytes;
     GeneralSmem<H, W> &sm = *reinterpret_cast<GeneralSmem<H, W> *>(wbase);
-    double *flow = reinterpret_cast<double *>(wbase + sizeof(GeneralSmem<H, W>));
+    double *flow = p.flow_scratch ? p.flow_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * flow_doubles
+                                  : reinterpret_cast<double *>(wbase + sizeof(GeneralSmem<H, W>));
     const int lane = threadIdx.x & 31;
     Counters st;
     bool failed = false;
@@ -223,33 +225,33 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
 }
 
 template <int H, int W>
-cudaError_t launch_gen(const GeoParams &p, int n_sms, cudaStream_t st)
+cudaError_t plan_gen(const GeoParams &p, int n_sms, GeoPlan &plan)
+{
+    return plan_warp_kernel(general_kernel<H, W>, sizeof(GeneralSmem<H, W>), (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double), p.p_end - p.p_begin, n_sms, plan);
+}
+
+template <int H, int W>
+cudaError_t launch_gen(const GeoParams &p, const GeoPlan &plan, cudaStream_t st)
 {
     auto k = general_kernel<H, W>;
-    const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double);
-    int warps = 1, per_sm = 1;
-    cudaError_t e = pick_block_warps(k, warp_bytes, warps, per_sm);
+    if ((plan.scratch_bytes != 0) != (p.flow_scratch != nullptr)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
-    const size_t smem = warp_bytes * warps;
-    const int64_t pairs = p.p_end - p.p_begin;
-    int64_t blocks = (int64_t)n_sms * per_sm;
-    const int64_t need = (pairs + warps - 1) / warps;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    k<<<(unsigned)blocks, warps * 32, smem, st>>>(p);
+    k<<<(unsigned)plan.blocks, plan.warps * 32, plan.smem, st>>>(p);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_general(const GeoParams &p, int cap, int n_sms, cudaStream_t st)
-{
-    if (cap <= 32 && p.W == 1) return launch_gen<1, 1>(p, n_sms, st);
-    if (cap <= 64 && p.W == 1) return launch_gen<2, 1>(p, n_sms, st);
-    if (cap <= 64 && p.W == 2) return launch_gen<2, 2>(p, n_sms, st);
-    if (cap <= 128 && p.W == 2) return launch_gen<4, 2>(p, n_sms, st);
-    if (cap <= 128 && p.W == 3) return launch_gen<4, 3>(p, n_sms, st);
+#define GEN_DISPATCH(fn, ...)                                         \
+    if (cap <= 32 && p.W == 1) return fn<1, 1>(__VA_ARGS__);          \
+    if (cap <= 64 && p.W == 1) return fn<2, 1>(__VA_ARGS__);          \
+    if (cap <= 64 && p.W == 2) return fn<2, 2>(__VA_ARGS__);          \
+    if (cap <= 128 && p.W == 2) return fn<4, 2>(__VA_ARGS__);         \
+    if (cap <= 128 && p.W == 3) return fn<4, 3>(__VA_ARGS__);         \
     return cudaErrorInvalidValue;
-}
+
+cudaError_t plan_general(const GeoParams &p, int cap, int n_sms, GeoPlan &plan) { GEN_DISPATCH(plan_gen, p, n_sms, plan) }
+cudaError_t launch_general(const GeoParams &p, int cap, const GeoPlan &plan, cudaStream_t st) { GEN_DISPATCH(launch_gen, p, plan, st) }
 
 }  // namespace td

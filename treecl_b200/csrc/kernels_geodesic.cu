@@ -33,10 +33,12 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per warp: fixed part, then the fp64 flow matrix sized for THIS set: flow_rows x FS doubles (FS odd: bank spread)
     const int FS = p.flow_rows | 1;
-    const size_t warp_bytes = sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * FS * sizeof(double);
+    const size_t flow_doubles = (size_t)p.flow_rows * FS;
+    const size_t warp_bytes = sizeof(WarpSmem<H, W>) + (p.flow_scratch ? 0 : flow_doubles * sizeof(double));
     unsigned char *wbase = smem_raw + (size_t)(threadIdx.x >> 5) * warp_bytes;
     WarpSmem<H, W> &sm = *reinterpret_cast<WarpSmem<H, W> *>(wbase);
-    double *flow = reinterpret_cast<double *>(wbase + sizeof(WarpSmem<H, W>));
+    double *flow = p.flow_scratch ? p.flow_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * flow_doubles
+                                  : reinterpret_cast<double *>(wbase + sizeof(WarpSmem<H, W>));
     const int lane = threadIdx.x & 31;
     Counters st;
     bool failed = false;
@@ -115,40 +117,33 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParam
 }
 
 template <int H, int W>
-cudaError_t launch_geo(const GeoParams &p, int n_sms, cudaStream_t st)
+cudaError_t plan_geo(const GeoParams &p, int n_sms, GeoPlan &plan)
+{
+    return plan_warp_kernel(geodesic_kernel<H, W>, sizeof(WarpSmem<H, W>), (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double), p.p_end - p.p_begin, n_sms, plan);
+}
+
+template <int H, int W>
+cudaError_t launch_geo(const GeoParams &p, const GeoPlan &plan, cudaStream_t st)
 {
     auto k = geodesic_kernel<H, W>;
-    const size_t warp_bytes = sizeof(WarpSmem<H, W>) + (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double);
-    int warps = 1, per_sm = 1;
-    cudaError_t e = pick_block_warps(k, warp_bytes, warps, per_sm);
+    if ((plan.scratch_bytes != 0) != (p.flow_scratch != nullptr)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
-    const size_t smem = warp_bytes * warps;
-    const int64_t pairs = p.p_end - p.p_begin;
-    int64_t blocks = (int64_t)n_sms * per_sm;
-    const int64_t need = (pairs + warps - 1) / warps;
-    if (blocks > need) blocks = need;
-    if (blocks < 1) blocks = 1;
-    k<<<(unsigned)blocks, warps * 32, smem, st>>>(p);
+    k<<<(unsigned)plan.blocks, plan.warps * 32, plan.smem, st>>>(p);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t geodesic_smem_bytes(int cap, int W, int warps)
-{
-    const size_t flow = (size_t)cap * (cap | 1) * sizeof(double);
-    if (cap <= 32) return (sizeof(WarpSmem<1, 1>) + flow) * warps;
-    return ((W == 1 ? sizeof(WarpSmem<2, 1>) : sizeof(WarpSmem<2, 2>)) + flow) * warps;
-}
-
-cudaError_t launch_geodesic(const GeoParams &p, int cap, int n_sms, cudaStream_t st)
-{
-    if (cap <= 32 && p.W == 1) return launch_geo<1, 1>(p, n_sms, st);
-    if (cap <= 64 && p.W == 1) return launch_geo<2, 1>(p, n_sms, st);
-    if (cap <= 64 && p.W == 2) return launch_geo<2, 2>(p, n_sms, st);
-    if (cap <= 128 && p.W == 2) return launch_geo<4, 2>(p, n_sms, st);
-    if (cap <= 128 && p.W == 3) return launch_geo<4, 3>(p, n_sms, st);
+#define GEO_DISPATCH(fn, ...)                                         \
+    if (cap <= 32 && p.W == 1) return fn<1, 1>(__VA_ARGS__);          \
+    if (cap <= 64 && p.W == 1) return fn<2, 1>(__VA_ARGS__);          \
+    if (cap <= 64 && p.W == 2) return fn<2, 2>(__VA_ARGS__);          \
+    if (cap <= 128 && p.W == 2) return fn<4, 2>(__VA_ARGS__);         \
+    if (cap <= 128 && p.W == 3) return fn<4, 3>(__VA_ARGS__);         \
     return cudaErrorInvalidValue;
-}
+
+cudaError_t plan_geodesic(const GeoParams &p, int cap, int n_sms, GeoPlan &plan) { GEO_DISPATCH(plan_geo, p, n_sms, plan) }
+cudaError_t launch_geodesic(const GeoParams &p, int cap, const GeoPlan &plan, cudaStream_t st) { GEO_DISPATCH(launch_geo, p, plan, st) }
 
 }  // namespace td
