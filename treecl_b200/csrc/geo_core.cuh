@@ -14,6 +14,20 @@ namespace geo {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GEO_WARPS = 4;
+// Min resident 4-warp blocks per SM (= register cap) of geodesic_kernel<H, W>.  With the flow matrix in global memory registers limit
+// residency, and the kernel is latency-bound: measured in one call each (gpurun_out/r2_geo_ab4.log, r2_geo_ab5.log), 2,000 x 50 (H = 2):
+// 192 ms at 96 registers, 164 at 80 (6 blocks), 139 at 64 (8), 133 at 48 (10), 128 at 40 (12); 1,000 x 100 (H = 4): 362 ms uncapped, 230 at
+// 5 blocks, 227 at 6, 232 at 7, 240 at 8; 2,000 x 30 (H = 1, 70 registers uncapped): 35.8 ms at 8 blocks, 37.8 at 10, 36.9 at 12.
+#ifndef GEO_MINB_H1
+#define GEO_MINB_H1 8
+#endif
+#ifndef GEO_MINB_H2
+#define GEO_MINB_H2 12
+#endif
+#ifndef GEO_MINB_H4
+#define GEO_MINB_H4 6
+#endif
+constexpr int geo_min_blocks(int H) { return H == 1 ? GEO_MINB_H1 : (H == 2 ? GEO_MINB_H2 : GEO_MINB_H4); }
 constexpr double FLOW_TOL = 1e-13;
 constexpr double SPLIT_TOL = 1e-12;
 

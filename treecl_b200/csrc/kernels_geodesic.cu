@@ -28,7 +28,7 @@ namespace {
 using namespace geo;
 
 template <int H, int W>
-__global__ void __launch_bounds__(GEO_WARPS * 32) geodesic_kernel(const GeoParams p)
+__global__ void __launch_bounds__(GEO_WARPS * 32, geo_min_blocks(H)) geodesic_kernel(const GeoParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per warp: fixed part, then the fp64 flow matrix sized for THIS set: flow_rows x FS doubles (FS odd: bank spread)
