@@ -221,6 +221,24 @@ def test_geodesic_vs_oracle(td, oracle_mod, n_trees, n_taxa, kind, norm):
     assert st['pairs'] == n_trees * (n_trees - 1) // 2 and st['ratios'] >= 0
 
 
+@pytest.mark.parametrize('n_trees,n_taxa', [(300, 30), (200, 50), (60, 100)])
+def test_flow_matrix_in_shared_or_global_memory(td, monkeypatch, n_trees, n_taxa):
+    """The GTP kernels keep the per-warp flow matrix in shared memory or in a global scratch slice, whichever keeps more warps resident
+    (GeoPlan); both forms run the same arithmetic: identical bytes, uniform and non-uniform sets."""
+    from treecl_b200 import _lib, synth
+    trees = synth.uniform_trees(n_trees, n_taxa, seed=900 + n_taxa)
+    labels = synth.taxon_labels(n_taxa)
+    rng = np.random.default_rng(n_taxa)
+    odd = [td.Tree(t).prune_to_subset({labels[i] for i in rng.choice(n_taxa, size=n_taxa - 3, replace=False)}).newick if k % 3 else t
+           for k, t in enumerate(trees[:40])]
+    res = {}
+    for form in ('smem', 'global'):
+        monkeypatch.setenv('TREEDIST_GEO_FLOW', form)
+        res[form] = (_lib.TreeSet(trees).pairwise(('geo',))['geo'], _lib.TreeSet(odd).pairwise(('geo', 'euc')))
+    assert np.array_equal(res['smem'][0], res['global'][0])
+    assert np.array_equal(res['smem'][1]['geo'], res['global'][1]['geo']) and np.array_equal(res['smem'][1]['euc'], res['global'][1]['euc'])
+
+
 @pytest.mark.parametrize('n_taxa,n_trees', [(12, 60), (30, 80), (40, 50), (66, 30), (110, 16), (160, 14), (260, 10)])
 @pytest.mark.parametrize('norm', [False, True])
 def test_different_leaf_sets_vs_oracle(td, oracle_mod, n_taxa, n_trees, norm):
@@ -287,6 +305,14 @@ def test_leaf_set_groups(td, oracle_mod, monkeypatch):
         part = ts.pairwise(('wrf', 'geo'), normalise=True, min_overlap=11, overlap_fail_value=-2.0, row_begin=a, row_end=b)
         p0, p1 = _lib.condensed_offset(n, a), _lib.condensed_offset(n, b)
         assert np.array_equal(part['wrf'], whole['wrf'][p0:p1]) and np.array_equal(part['geo'], whole['geo'][p0:p1])
+    # the pairs across groups normally come from lists; without them the kernel skips same-group pairs chunk by chunk: same bytes
+    monkeypatch.setenv('TREEDIST_NO_CROSS_LISTS', '1')
+    skipping = _lib.TreeSet(trees)
+    sk = skipping.pairwise(metrics, normalise=True, min_overlap=11, overlap_fail_value=-2.0)
+    assert skipping.info.n_groups == 2
+    for m in metrics:
+        assert np.array_equal(sk[m], got[m])
+    monkeypatch.delenv('TREEDIST_NO_CROSS_LISTS')
     # ungrouped: every pair through the restrict-then-join kernel
     monkeypatch.setenv('TREEDIST_NO_GROUPS', '1')
     plain = _lib.TreeSet(trees)

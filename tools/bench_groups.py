@@ -32,6 +32,9 @@ def timed(ts):
 res = {'uniform_ms': timed(_lib.TreeSet(full))}
 g = _lib.TreeSet(trees); res['grouped_ms'] = timed(g); res['n_groups'] = int(g.info.n_groups)
 grouped = {m: out[m].clone() for m in out}
+os.environ['TREEDIST_NO_CROSS_LISTS'] = '1'
+res['grouped_chunk_skipping_ms'] = timed(_lib.TreeSet(trees))
+os.environ.pop('TREEDIST_NO_CROSS_LISTS')
 os.environ['TREEDIST_NO_GROUPS'] = '1'
 res['ungrouped_ms'] = timed(_lib.TreeSet(trees))
 res['same_rf'] = bool(torch.equal(grouped['rf'], out['rf'])); res['max_rel_euc'] = float(((grouped['euc'] - out['euc']).abs() / out['euc'].abs().clamp_min(1e-300)).max())

@@ -1,6 +1,8 @@
 // api.cu -- extern "C" entry points of libtreedist_cuda.so (see include/treedist_cuda.h).
 #include <cuda_runtime.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -244,6 +246,8 @@ struct DeviceSet {
     // leaf-set groups of a non-uniform set: group id per tree, per group the member list and a scratch matrix per metric (the group's own
     // condensed slice before it is scattered into the set's matrix; one launch at a time per set: later launches wait on grp_done)
     int32_t *group_of = nullptr;
+    int32_t *cross_cols = nullptr;
+    int64_t *cross_first = nullptr, *cross_prefix = nullptr;
     std::vector<int32_t *> grp_members;
     std::mutex grp_mu;
     void *grp_tmp[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -651,6 +655,7 @@ static int run_split_rows(td_treeset *ts, DeviceSet *d, uint32_t m3, PairParams 
 }
 
 // ---- leaf-set groups of a non-uniform set ---------------------------------------------------------------------------------------------------
+constexpr int64_t kMaxCrossList = 64ll << 20;       // entries of td_treeset::cross_cols (256 MB); beyond it same-group pairs are skipped chunk by chunk
 constexpr int kMinGroup = 48;                       // fewer trees with one leaf set are not worth kernels of their own
 
 static int ensure_groups(td_treeset *ts)
@@ -687,6 +692,30 @@ static int ensure_groups(td_treeset *ts)
                 ts->groups.push_back(std::move(g));
             }
             lo = hi;
+        }
+        // the pairs across groups as lists (td_internal.h): per group the sorted trees outside it; a tree in no group wants every later tree
+        if (!ts->groups.empty() && !getenv("TREEDIST_NO_CROSS_LISTS")) {
+            int64_t total = 0;
+            for (auto &g : ts->groups) total += h.N - (int64_t)g.members.size();
+            if (total <= kMaxCrossList) {
+                std::vector<int64_t> group_begin(ts->groups.size() + 1, 0);
+                for (size_t g = 0; g < ts->groups.size(); g++) group_begin[g + 1] = group_begin[g] + (h.N - (int64_t)ts->groups[g].members.size());
+                ts->cross_cols.resize((size_t)total);
+                std::vector<int64_t> fill(group_begin.begin(), group_begin.end() - 1);
+                for (int64_t t = 0; t < h.N; t++)
+                    for (size_t g = 0; g < ts->groups.size(); g++) if (ts->group_of[(size_t)t] != (int32_t)g) ts->cross_cols[(size_t)fill[g]++] = (int32_t)t;
+                ts->cross_first.assign((size_t)h.N, -1); ts->cross_prefix.assign((size_t)h.N + 1, 0);
+                for (int64_t i = 0; i < h.N; i++) {
+                    const int32_t g = ts->group_of[(size_t)i];
+                    int64_t count = h.N - 1 - i;
+                    if (g >= 0) {
+                        const int32_t *b = ts->cross_cols.data() + group_begin[(size_t)g], *e = ts->cross_cols.data() + group_begin[(size_t)g + 1];
+                        const int32_t *pos = std::upper_bound(b, e, (int32_t)i);
+                        ts->cross_first[(size_t)i] = pos - ts->cross_cols.data(); count = e - pos;
+                    }
+                    ts->cross_prefix[(size_t)i + 1] = ts->cross_prefix[(size_t)i] + count;
+                }
+            }
         }
     }
     ts->groups_built = true;
@@ -840,6 +869,14 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
             if (!d->group_of) {
                 int rc = dev_alloc(d, &d->group_of, (size_t)h.N); if (rc) return rc;
                 CUDA_TRY(cudaMemcpyAsync(d->group_of, ts->group_of.data(), (size_t)h.N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                if (!ts->cross_prefix.empty()) {
+                    rc = dev_alloc(d, &d->cross_cols, std::max<size_t>(ts->cross_cols.size(), 1)); if (rc) return rc;
+                    rc = dev_alloc(d, &d->cross_first, (size_t)h.N); if (rc) return rc;
+                    rc = dev_alloc(d, &d->cross_prefix, (size_t)h.N + 1); if (rc) return rc;
+                    CUDA_TRY(cudaMemcpyAsync(d->cross_cols, ts->cross_cols.data(), ts->cross_cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaMemcpyAsync(d->cross_first, ts->cross_first.data(), (size_t)h.N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaMemcpyAsync(d->cross_prefix, ts->cross_prefix.data(), ((size_t)h.N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                }
                 CUDA_TRY(cudaStreamSynchronize(st));
             }
         }
@@ -855,11 +892,16 @@ static int run_pairwise(td_treeset *ts, DeviceSet *d, uint32_t mask, int normali
         g.work_counter = d->work_counter + (d->next_counter.fetch_add(1) % kCounters); g.stats = d->stats; g.error_flag = d->error_flag;
         if (rect) { g.rect = 1; g.rect_split = split; g.rect_cols = d->N - split; g.p_begin = 0; g.p_end = split * g.rect_cols; g.p_base = 0; }
         else { g.rect = 0; g.p_begin = condensed_offset(d->N, row_begin); g.p_end = condensed_offset(d->N, row_end); g.p_base = g.p_begin; }
+        const bool any_pairs = g.p_end > g.p_begin;
+        if (grouped && d->cross_prefix) {                   // the wanted pairs of these rows, by list
+            g.group_of = nullptr; g.cross_prefix = d->cross_prefix; g.cross_first = d->cross_first; g.cross_cols = d->cross_cols;
+            g.p_begin = ts->cross_prefix[(size_t)row_begin]; g.p_end = ts->cross_prefix[(size_t)row_end];
+        }
         if (g.p_end > g.p_begin) {
             if (big) { int rc = run_bigtree(ts, d, g, 1, st); if (rc) return rc; }
             else { int rc = run_warp_kernel(ts, d, g, 1, st); if (rc) return rc; }
-            if (grouped) return run_groups(ts, d, mask, normalise, row_begin, row_end, d_out, st);
         }
+        if (any_pairs && grouped) return run_groups(ts, d, mask, normalise, row_begin, row_end, d_out, st);
         return TD_OK;
     }
     CUDA_TRY(cudaSetDevice(d->device));
@@ -1050,8 +1092,10 @@ int td_encode_newick(const char *const *newick, int64_t n_trees, int n_threads, 
     td_treeset *ts = new (std::nothrow) td_treeset();
     if (!ts) { set_error("out of memory"); return TD_ERR_NOMEM; }
     int rc;
+    const auto t0 = std::chrono::steady_clock::now();
     try { rc = encode_newick(newick, n_trees, n_threads, ts->host); }
     catch (const std::bad_alloc &) { set_error("out of memory while encoding"); rc = TD_ERR_NOMEM; }
+    if (getenv("TREEDIST_TIMING")) fprintf(stderr, "[encode] td_encode_newick %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (rc) { delete ts; return rc; }
     *out = ts;
     return TD_OK;

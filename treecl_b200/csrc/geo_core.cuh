@@ -146,7 +146,9 @@ __device__ __forceinline__ int64_t tri_row_start(int64_t i, int64_t N) { return 
 // Work distribution of the warp-per-pair kernels that may SKIP pairs (kernels_general.cu, kernels_bigtrees.cu): a warp takes a chunk of 32
 // consecutive pair indices from the launch's work counter, every lane decodes its own pair and tests whether it is wanted - pairs of two
 // trees of the same leaf-set group (GeoParams::group_of) belong to that group's uniform kernels - and the warp then walks the wanted
-// pairs of the chunk one by one.  A set with a few odd trees costs the odd pairs plus one ballot per 32 skipped pairs.
+// pairs of the chunk one by one.  That costs one chunk per 32 skipped pairs (a 5,000-tree set with 50 odd trees: 390 k chunks for 250 k
+// wanted pairs), so the library normally hands over the wanted pairs as lists instead (GeoParams::cross_*): the chunk then holds 32
+// WANTED pairs, found by a binary search over the per-row prefix.
 struct PairFeed {
     uint32_t pending = 0;
     int64_t base = 0, my_ti = 0, my_tj = 0;
@@ -163,7 +165,16 @@ __device__ __forceinline__ void decode_pair(const GeoParams &p, int64_t pidx, in
     ti = i; tj = pidx - tri_row_start(i, p.N) + i + 1;
 }
 
-// false: no work left.  All lanes of the warp call it together and receive the same pair.
+// q-th wanted pair of the cross-group lists: the row is the last one whose prefix is <= q
+__device__ __forceinline__ void decode_cross(const GeoParams &p, int64_t q, int64_t &ti, int64_t &tj)
+{
+    int64_t lo = 0, hi = p.N;                                   // cross_prefix has N + 1 entries; prefix[lo] <= q < prefix[hi]
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (p.cross_prefix[mid] <= q) lo = mid; else hi = mid; }
+    const int64_t off = q - p.cross_prefix[lo], first = p.cross_first[lo];
+    ti = lo; tj = first < 0 ? lo + 1 + off : (int64_t)p.cross_cols[first + off];
+}
+
+// false: no work left.  All lanes of the warp call it together and receive the same pair; pidx is its condensed (or rectangular) index.
 __device__ __forceinline__ bool next_pair(const GeoParams &p, PairFeed &f, int lane, int64_t &pidx, int64_t &ti, int64_t &tj)
 {
     while (f.pending == 0) {
@@ -175,15 +186,18 @@ __device__ __forceinline__ bool next_pair(const GeoParams &p, PairFeed &f, int l
         const int64_t mine = f.base + lane;
         bool want = mine < p.p_end;
         if (want) {
-            decode_pair(p, mine, f.my_ti, f.my_tj);
-            if (p.group_of) { const int ga = p.group_of[f.my_ti]; want = ga < 0 || ga != p.group_of[f.my_tj]; }
+            if (p.cross_prefix) decode_cross(p, mine, f.my_ti, f.my_tj);
+            else {
+                decode_pair(p, mine, f.my_ti, f.my_tj);
+                if (p.group_of) { const int ga = p.group_of[f.my_ti]; want = ga < 0 || ga != p.group_of[f.my_tj]; }
+            }
         }
         f.pending = __ballot_sync(FULL, want);
     }
     const int src = __ffs(f.pending) - 1;
     f.pending &= f.pending - 1;
-    pidx = f.base + src;
     ti = __shfl_sync(FULL, f.my_ti, src); tj = __shfl_sync(FULL, f.my_tj, src);
+    pidx = p.cross_prefix ? tri_row_start(ti, p.N) + tj - ti - 1 : f.base + src;
     return true;
 }
 

@@ -449,6 +449,7 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
         if (rc) { std::string m = std::string("tree 0: ") + last_error(); set_error("%s", m.c_str()); return rc; }
         tab.build(std::move(l0));
     }
+    lap("setup");
     std::atomic<bool> missing{false};
     struct Scratch { FlatTree t; std::vector<uint64_t> clade; std::vector<int> order; };
     std::vector<Scratch> scratch(n_threads);

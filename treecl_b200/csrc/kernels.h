@@ -88,6 +88,9 @@ struct GeoParams {
     const uint64_t *leafmask; // [N][W] taxa present in each tree (general kernel)
     const int32_t *rooted;    // [N]
     const int32_t *group_of;  // [N] leaf-set group served by uniform kernels (-1: none), or nullptr: the warp-per-pair kernels skip same-group pairs
+    // pairs across leaf-set groups as lists (td_treeset::cross_*): when cross_prefix is set, [p_begin, p_end) counts WANTED pairs
+    const int64_t *cross_prefix, *cross_first;
+    const int32_t *cross_cols;
     int64_t N;
     int stride, n_taxa, W;
     int flow_rows;                       // max internal edges of any tree of the set: the flow matrix is flow_rows x (flow_rows|1)

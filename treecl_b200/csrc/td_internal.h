@@ -93,5 +93,10 @@ struct td_treeset {
     bool groups_built = false;
     std::vector<Group> groups;
     std::vector<int32_t> group_of;             // [N] index into `groups`, -1: in no group
+    // The pairs ACROSS groups, enumerated without visiting the others: for row i the wanted columns j > i are cross_cols[cross_first[i] ..]
+    // (cross_first[i] < 0: every j > i, the row of a tree in no group), cross_prefix[i] = wanted pairs of the rows before i.  Empty when
+    // the lists would be too large (the kernels then skip same-group pairs chunk by chunk).
+    std::vector<int32_t> cross_cols;
+    std::vector<int64_t> cross_first, cross_prefix;
     ~td_treeset();
 };
