@@ -27,6 +27,8 @@ struct GeneralSmem {
     WarpSmem<H, W> core;                     // flow, lenB, maskB, idA/idB (unused here), stack
     uint64_t maskA[32 * H * W];
     double lenA[32 * H];
+    int table[64 * H];                       // open-addressing table of slot indices keyed by restricted mask (load <= 1/2)
+    int partnerA[32 * H];                    // per slot of tree A: slot of the equal split of tree B, or -1
     double leafA[64 * W], leafB[64 * W];     // restricted leaf-edge lengths (taxa outside the intersection stay 0)
 };
 
@@ -38,14 +40,25 @@ template <int W> __device__ __forceinline__ bool mask_eq(const uint64_t *a, cons
     return e;
 }
 
+template <int W> __device__ __forceinline__ uint32_t mask_hash(const uint64_t (&m)[W])
+{
+    uint64_t x = m[0];
+#pragma unroll
+    for (int w = 1; w < W; w++) x ^= m[w] * (0x9E3779B97F4A7C15ull + 2 * w);
+    x *= 0xD6E8FEB86659FD93ull;
+    return (uint32_t)(x >> 40);
+}
+
 // restrict my split(s) of one tree to the common leaf set M; leaf folds go to `leaf`, internal splits (deduplicated, lengths
 // summed in ascending slot order) stay lane-owned: mine[h] (valid representative), m[h], len[h].  Returns the valid set.
 template <int H, int W>
 __device__ __forceinline__ Bits<H> restrict_tree(const GeoParams &p, int64_t t, const uint64_t (&M)[W], int nM, int ref, int rooted,
-                                                 uint64_t *smask, double *slen, double *leaf, int lane,
+                                                 uint64_t *smask, double *slen, double *leaf, int *table, int lane,
                                                  uint64_t (&m)[H][W], double (&len)[H])
 {
+    constexpr int T = 64 * H;
     const int S = p.nsplits[t];
+    for (int k = lane; k < T; k += 32) table[k] = -1;
     Bits<H> valid;
 #pragma unroll
     for (int h = 0; h < H; h++) {
@@ -87,30 +100,49 @@ __device__ __forceinline__ Bits<H> restrict_tree(const GeoParams &p, int64_t t, 
         valid.w[h] = __ballot_sync(FULL, internal);
     }
     __syncwarp();
-    // merge equal masks: the lowest slot is the representative and takes the sum (ascending slot order).  A plain scan over the tree's
-    // slots: slots that hold no internal split carry a zero mask and never match; the loads are independent of each other (the former walk
-    // over the valid-set bits was a dependent chain of ~20 instructions per slot: 5,000 x 50 with 1 % odd trees, rf+euc, 5.6 -> 1.9 ms)
-    Bits<H> reps;
+    // merge equal masks: the lowest slot is the representative and takes the sum, in ascending slot order.  Every valid slot enters the
+    // hash table (on an equal mask the entry keeps the lowest slot); the table is left holding the representatives for the caller.
+    // (Round 2 history, 5,000 x 50 with 1 % odd trees, rf+euc: a walk over the valid-set bits per lane 5.6 ms, a linear scan 1.9 ms.)
+    // (the probe loops are warp-uniform - one step per pass for every lane still looking - so that the warp stays converged: with a
+    // per-lane `for (;;)` the lanes left their loops at different times and ran the rest of the pair in up to five separate groups)
+    int entry[H];
 #pragma unroll
     for (int h = 0; h < H; h++) {
         const int s = lane + 32 * h;
-        bool rep = valid.mine(h, lane);
-        double sum = len[h];
-        if (rep) {
-            int lower = 0; uint32_t later = 0;              // equal masks below me; equal masks above me exist
-#pragma unroll 4
-            for (int t2 = 0; t2 < S; t2++) {
-                const bool eq = mask_eq<W>(&smask[t2 * W], m[h]) && t2 != s;
-                lower += (eq && t2 < s); later |= (uint32_t)(eq && t2 > s);
+        uint32_t e = mask_hash<W>(m[h]) & (T - 1);
+        bool looking = valid.mine(h, lane);
+        while (__any_sync(FULL, looking)) {
+            if (looking) {
+                const int prev = atomicCAS(&table[e], -1, s);
+                if (prev == -1) looking = false;
+                else if (mask_eq<W>(&smask[prev * W], m[h])) { atomicMin(&table[e], s); looking = false; }
+                else e = (e + 1) & (T - 1);
             }
-            if (lower) rep = false;
-            else if (later) { for (int t2 = s + 1; t2 < S; t2++) if (mask_eq<W>(&smask[t2 * W], m[h])) sum += slen[t2]; }
         }
-        len[h] = rep ? sum : 0.0;
-        reps.w[h] = __ballot_sync(FULL, rep);
+        entry[h] = (int)e;
     }
     __syncwarp();
-    // only representatives keep their mask: the common-split scans below can then run over all slots
+    Bits<H> reps;
+    int my_rep[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        my_rep[h] = valid.mine(h, lane) ? table[entry[h]] : -1;
+        reps.w[h] = __ballot_sync(FULL, my_rep[h] == lane + 32 * h);
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < H; h2++) {                    // merged slots hand their length to the representative, in ascending slot order
+        uint32_t dups = valid.w[h2] & ~reps.w[h2];
+        while (dups) {
+            const int src = __ffs(dups) - 1; dups &= dups - 1;
+            const int r = __shfl_sync(FULL, my_rep[h2], src); const double l = __shfl_sync(FULL, len[h2], src);
+#pragma unroll
+            for (int h = 0; h < H; h++) if (lane + 32 * h == r) len[h] += l;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; h++) if (!reps.mine(h, lane)) len[h] = 0.0;
+    __syncwarp();
+    // only representatives keep their mask
 #pragma unroll
     for (int h = 0; h < H; h++) if (!reps.mine(h, lane)) {
 #pragma unroll
@@ -171,8 +203,9 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
         }
         __syncwarp();
         uint64_t mA[H][W], mB[H][W]; double lenA[H], lenB[H];
-        const Bits<H> validA = restrict_tree<H, W>(p, ti, M, nM, ref, rooted, sm.maskA, sm.lenA, sm.leafA, lane, mA, lenA);
-        const Bits<H> validB = restrict_tree<H, W>(p, tj, M, nM, ref, rooted, sm.core.maskB, sm.core.lenB, sm.leafB, lane, mB, lenB);
+        // tree B first: the table is left holding the representatives of tree A
+        const Bits<H> validB = restrict_tree<H, W>(p, tj, M, nM, ref, rooted, sm.core.maskB, sm.core.lenB, sm.leafB, sm.table, lane, mB, lenB);
+        const Bits<H> validA = restrict_tree<H, W>(p, ti, M, nM, ref, rooted, sm.maskA, sm.lenA, sm.leafA, sm.table, lane, mA, lenA);
 
         // ---- leaf terms and per-tree normalisers ---------------------------------------------------------------------------------
         double l1 = 0, l2 = 0, sumA = 0, sumB = 0, sqA = 0, sqB = 0;
@@ -180,31 +213,47 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
             const double a = sm.leafA[k], b = sm.leafB[k], d = a - b;
             l1 += fabs(d); l2 = fma(d, d, l2); sumA += a; sumB += b; sqA = fma(a, a, sqA); sqB = fma(b, b, sqB);
         }
-        // ---- common splits: equal restricted masks --------------------------------------------------------------------------------
-        const int Si = p.nsplits[ti], Sj = p.nsplits[tj];
+        // ---- common splits: equal restricted masks; the lanes of tree B look their masks up in tree A's table ------------------------
         Bits<H> setA, setB;
         double c1 = 0, c2 = 0, o1 = 0, o2 = 0;      // common: |la-lb|, (la-lb)^2 ; one-sided: |l|, l^2
         double la2[H], lb2[H];
 #pragma unroll
+        for (int h = 0; h < H; h++) sm.partnerA[lane + 32 * h] = -1;
+        __syncwarp();
+#pragma unroll
         for (int h = 0; h < H; h++) {
-            bool ncA = false, ncB = false;
-            la2[h] = lenA[h] * lenA[h]; lb2[h] = lenB[h] * lenB[h];
+            bool ncB = false;
+            lb2[h] = lenB[h] * lenB[h];
+            if (validB.mine(h, lane)) { sumB += lenB[h]; sqB += lb2[h]; }
+            int partner = -1;
+            uint32_t e = mask_hash<W>(mB[h]) & (64 * H - 1);
+            bool looking = validB.mine(h, lane);
+            while (__any_sync(FULL, looking)) {                 // warp-uniform probe loop (see restrict_tree)
+                if (looking) {
+                    const int a = sm.table[e];
+                    if (a < 0) looking = false;
+                    else if (mask_eq<W>(&sm.maskA[a * W], mB[h])) { partner = a; looking = false; }
+                    else e = (e + 1) & (64 * H - 1);
+                }
+            }
+            if (validB.mine(h, lane)) {
+                if (partner >= 0) sm.partnerA[partner] = lane + 32 * h;
+                else { ncB = true; o1 += fabs(lenB[h]); o2 += lb2[h]; }
+            }
+            setB.w[h] = __ballot_sync(FULL, ncB);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            bool ncA = false;
+            la2[h] = lenA[h] * lenA[h];
             if (validA.mine(h, lane)) {
                 sumA += lenA[h]; sqA += la2[h];
-                int partner = -1;
-#pragma unroll 4
-                for (int b = 0; b < Sj; b++) if (mask_eq<W>(&sm.core.maskB[b * W], mA[h])) partner = b;          // at most one (masks are unique)
+                const int partner = sm.partnerA[lane + 32 * h];
                 if (partner >= 0) { const double d = lenA[h] - sm.core.lenB[partner]; c1 += fabs(d); c2 = fma(d, d, c2); }
                 else { ncA = true; o1 += fabs(lenA[h]); o2 += la2[h]; }
             }
-            if (validB.mine(h, lane)) {
-                sumB += lenB[h]; sqB += lb2[h];
-                bool found = false;
-#pragma unroll 4
-                for (int a = 0; a < Si; a++) found |= mask_eq<W>(&sm.maskA[a * W], mB[h]);
-                if (!found) { ncB = true; o1 += fabs(lenB[h]); o2 += lb2[h]; }
-            }
-            setA.w[h] = __ballot_sync(FULL, ncA); setB.w[h] = __ballot_sync(FULL, ncB);
+            setA.w[h] = __ballot_sync(FULL, ncA);
         }
         const int rf = setA.count() + setB.count(), rf_den = validA.count() + validB.count();
         l1 = warp_sum(l1); l2 = warp_sum(l2); c1 = warp_sum(c1); c2 = warp_sum(c2); o1 = warp_sum(o1); o2 = warp_sum(o2);
