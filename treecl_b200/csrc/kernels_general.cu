@@ -155,12 +155,17 @@ __device__ __forceinline__ Bits<H> restrict_tree(const GeoParams &p, int64_t t, 
     return reps;
 }
 
-template <int H, int W>
-__global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams p)
+#ifndef GEN_MINB
+#define GEN_MINB 8
+#endif
+// GEO: the launch wants the geodesic.  Without it the kernel needs neither the GTP code nor its registers (128 -> the 64 of the cap
+// below: twice the warps on an SM for a latency-bound kernel).
+template <int H, int W, bool GEO>
+__global__ void __launch_bounds__(GEO_WARPS * 32, GEO ? 1 : GEN_MINB) general_kernel(const GeoParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int FS = p.flow_rows | 1;
-    const size_t flow_doubles = (p.metric_mask & 8u) ? (size_t)p.flow_rows * FS : 0;
+    const size_t flow_doubles = GEO ? (size_t)p.flow_rows * FS : 0;
     const size_t warp_bytes = sizeof(GeneralSmem<H, W>) + (p.flow_scratch ? 0 : flow_doubles * sizeof(double));
     unsigned char *wbase = smem_raw + (size_t)(threadIdx.x >> 5) * warp_bytes;
     GeneralSmem<H, W> &sm = *reinterpret_cast<GeneralSmem<H, W> *>(wbase);
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
         sumA = warp_sum(sumA); sumB = warp_sum(sumB); sqA = warp_sum(sqA); sqB = warp_sum(sqB);
 
         double geo2 = 0.0;
-        if (p.metric_mask & 8u) {
+        if constexpr (GEO) {
             double part = 0.0;
             const double total = gtp_noncommon<H, W>(sm.core, flow, FS, mA, setA, setB, la2, lb2, lane, part, st, failed);
             geo2 = warp_sum(part) + total + c2 + l2;
@@ -287,20 +292,26 @@ __global__ void __launch_bounds__(GEO_WARPS * 32) general_kernel(const GeoParams
 template <int H, int W>
 cudaError_t plan_gen(const GeoParams &p, int n_sms, GeoPlan &plan)
 {
-    // without the geodesic no flow matrix is needed: more warps fit
-    const size_t flow_bytes = (p.metric_mask & 8u) ? (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double) : 0;
-    return plan_warp_kernel(general_kernel<H, W>, sizeof(GeneralSmem<H, W>), flow_bytes, p.p_end - p.p_begin, n_sms, plan);
+    if (p.metric_mask & 8u)
+        return plan_warp_kernel(general_kernel<H, W, true>, sizeof(GeneralSmem<H, W>), (size_t)p.flow_rows * (p.flow_rows | 1) * sizeof(double), p.p_end - p.p_begin, n_sms, plan);
+    return plan_warp_kernel(general_kernel<H, W, false>, sizeof(GeneralSmem<H, W>), 0, p.p_end - p.p_begin, n_sms, plan);
 }
 
-template <int H, int W>
-cudaError_t launch_gen(const GeoParams &p, const GeoPlan &plan, cudaStream_t st)
+template <int H, int W, bool GEO>
+cudaError_t launch_gen_as(const GeoParams &p, const GeoPlan &plan, cudaStream_t st)
 {
-    auto k = general_kernel<H, W>;
+    auto k = general_kernel<H, W, GEO>;
     if ((plan.scratch_bytes != 0) != (p.flow_scratch != nullptr)) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     if (e != cudaSuccess) return e;
     k<<<(unsigned)plan.blocks, plan.warps * 32, plan.smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int H, int W>
+cudaError_t launch_gen(const GeoParams &p, const GeoPlan &plan, cudaStream_t st)
+{
+    return (p.metric_mask & 8u) ? launch_gen_as<H, W, true>(p, plan, st) : launch_gen_as<H, W, false>(p, plan, st);
 }
 
 }  // namespace
