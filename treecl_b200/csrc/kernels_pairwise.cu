@@ -302,8 +302,15 @@ __global__ void scatter_group_kernel(const double *__restrict__ tmp, double *__r
     if (a >= a1) return;
     const int64_t local_base = (a * n_local - a * (a + 1) / 2) - (a0 * n_local - a0 * (a0 + 1) / 2);
     const int64_t gi = members[a], row_base = gi * N - gi * (gi + 1) / 2 - gi - 1 - p_base;
-    for (int64_t b = a + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_local; b += (int64_t)gridDim.x * blockDim.x)
-        out[row_base + members[b]] = tmp[local_base + (b - a - 1)];
+    // four independent elements per thread and pass (one block per 1,024 columns: blocks of one element per thread were launch-bound)
+    const int64_t step = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t b0 = a + 1 + (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; b0 < n_local; b0 += step) {
+        double v[4]; int32_t m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t b = b0 + k * blockDim.x; if (b < n_local) { v[k] = tmp[local_base + (b - a - 1)]; m[k] = members[b]; } }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t b = b0 + k * blockDim.x; if (b < n_local) out[row_base + m[k]] = v[k]; }
+    }
 }
 
 cudaError_t launch_scatter_group(const double *tmp, double *out, const int32_t *members, int64_t n_local, int64_t a0, int64_t a1, int64_t N,
@@ -313,7 +320,7 @@ cudaError_t launch_scatter_group(const double *tmp, double *out, const int32_t *
     for (int64_t r = a0; r < a1; r += 65535) {                    // (grid.y limit)
         const int64_t r1 = std::min(a1, r + 65535);
         const int64_t tmp_off = (r * n_local - r * (r + 1) / 2) - (a0 * n_local - a0 * (a0 + 1) / 2);
-        const dim3 grid((unsigned)std::min<int64_t>(64, (n_local + 255) / 256), (unsigned)(r1 - r));
+        const dim3 grid((unsigned)std::min<int64_t>(16, (n_local + 1023) / 1024), (unsigned)(r1 - r));
         scatter_group_kernel<<<grid, 256, 0, st>>>(tmp + tmp_off, out, members, n_local, r, r1, N, p_base);
     }
     return cudaGetLastError();
