@@ -39,6 +39,7 @@ struct Slab {                          // per-warp scratch, carved from one allo
     double *ra, *rb, *wa, *wb;         // [S] residual capacities and vertex weights of the current ratio
     int *parA, *parB;                  // [S] BFS parents
     uint32_t *inc, *incT;              // [S][HW] incompatibility rows: split a of A over B, split b of B over A
+    uint32_t *fpos;                    // [S][HW] row a of "flow[a][b] > FLOW_TOL", kept in step with every write of the flow matrix (geo_core.cuh)
     uint32_t *stack;                   // [S + 2][2 HW] ratios still to be examined
     double *flow;                      // [S][FS]
     double *leafA, *leafB;             // [n_taxa_pad] restricted leaf-edge lengths
@@ -70,7 +71,7 @@ __device__ __forceinline__ Slab carve(const BigParams &bp, int warp_global)
     s.lenA = (double *)take(S * 8); s.lenB = (double *)take(S * 8); s.la2 = (double *)take(S * 8); s.lb2 = (double *)take(S * 8);
     s.ra = (double *)take(S * 8); s.rb = (double *)take(S * 8); s.wa = (double *)take(S * 8); s.wb = (double *)take(S * 8);
     s.parA = (int *)take(S * 4); s.parB = (int *)take(S * 4);
-    s.inc = (uint32_t *)take(S * bp.HW * 4); s.incT = (uint32_t *)take(S * bp.HW * 4);
+    s.inc = (uint32_t *)take(S * bp.HW * 4); s.incT = (uint32_t *)take(S * bp.HW * 4); s.fpos = (uint32_t *)take(S * bp.HW * 4);
     s.stack = (uint32_t *)take((S + 2) * 2 * bp.HW * 4);
     s.flow = (double *)take(S * (size_t)bp.FS * 8);
     s.leafA = (double *)take((size_t)bp.taxa_pad * 8); s.leafB = (double *)take((size_t)bp.taxa_pad * 8);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) bigtree_kernel(const BigParams
         if (p.metric_mask & 8u) {
             double part = 0.0, total = 0.0;
             // ---- incompatibility bit matrix --------------------------------------------------------------------------------------------------
-            for (int s = lane; s < bp.S; s += 32) for (int h = 0; h < HW; h++) { sl.inc[(size_t)s * HW + h] = 0u; sl.incT[(size_t)s * HW + h] = 0u; }
+            for (int s = lane; s < bp.S; s += 32) for (int h = 0; h < HW; h++) { sl.inc[(size_t)s * HW + h] = 0u; sl.incT[(size_t)s * HW + h] = 0u; sl.fpos[(size_t)s * HW + h] = 0u; }
             __syncwarp();
             for (int hb = 0; hb < HW; hb++) {
                 uint32_t wordB = setB[hb];
@@ -308,10 +309,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) bigtree_kernel(const BigParams
                         const bool ina = set_test(RA, s), inb = set_test(RB, s);
                         const double wa = ina ? sl.la2[s] / sa : 0.0, wb = inb ? sl.lb2[s] / sb : 0.0;
                         sl.wa[s] = wa; sl.wb[s] = wb; sl.ra[s] = wa; sl.rb[s] = wb;
-                        if (ina) for (int h = 0; h < HW; h++) {               // zero my row of the flow matrix (only edges of the graph)
-                            uint32_t nb = sl.inc[(size_t)s * HW + h] & RB[h];
-                            while (nb) { const int b = 32 * h + __ffs(nb) - 1; nb &= nb - 1; sl.flow[(size_t)s * FS + b] = 0.0; }
-                        }
+                        // no edge carries flow.  A word without a neighbour in RB may keep bits of an earlier max-flow OF THIS PAIR: they sit on edges
+                        // whose B end is outside RB, and every read masks with a subset of RB (rows are cleared in full when a new pair starts).  The flow matrix itself is never cleared
+                        if (ina) for (int h = 0; h < HW; h++) if (sl.inc[(size_t)s * HW + h] & RB[h]) sl.fpos[(size_t)s * HW + h] = 0u;
                     }
                     __syncwarp();
                     // greedy saturation: push every source edge into its neighbours' sink edges, in split order
@@ -330,6 +330,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) bigtree_kernel(const BigParams
                                 const double tot = __shfl_sync(FULL, incl, 31);
                                 const double take = fmin(avail, fmax(0.0, x - (incl - avail)));
                                 if (take > 0.0) { sl.rb[b] -= take; sl.flow[(size_t)a * FS + b] = take; }
+                                const uint32_t carries = __ballot_sync(FULL, take > FLOW_TOL);
+                                if (lane == 0) sl.fpos[(size_t)a * HW + h] = carries;
                                 x = fmax(0.0, x - tot);
                             }
                             __syncwarp();
@@ -375,8 +377,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) bigtree_kernel(const BigParams
                                 bool found = false;
                                 if (set_test(RA, a) && !set_test(visA, a)) {
                                     for (int k = 0; k < HW && !found; k++) {
-                                        uint32_t cand = sl.inc[(size_t)a * HW + k] & newB[k];
-                                        while (cand) { const int b = 32 * k + __ffs(cand) - 1; cand &= cand - 1; if (sl.flow[(size_t)a * FS + b] > FLOW_TOL) { sl.parA[a] = b; found = true; break; } }
+                                        const uint32_t cand = sl.fpos[(size_t)a * HW + k] & newB[k];
+                                        if (cand) { sl.parA[a] = 32 * k + __ffs(cand) - 1; found = true; }
                                     }
                                 }
                                 const uint32_t na = __ballot_sync(FULL, found);
@@ -401,9 +403,14 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) bigtree_kernel(const BigParams
                             b = sink;
                             for (int hop = 0; hop < 2 * bp.S + 2; hop++) {
                                 const int a = sl.parB[b], pb = sl.parA[a];
-                                sl.flow[(size_t)a * FS + b] += delta;
+                                uint32_t &wb_ = sl.fpos[(size_t)a * HW + (b >> 5)];
+                                const double fwd = ((wb_ >> (b & 31)) & 1u ? sl.flow[(size_t)a * FS + b] : 0.0) + delta;
+                                sl.flow[(size_t)a * FS + b] = fwd;
+                                if (fwd > FLOW_TOL) wb_ |= 1u << (b & 31); else wb_ &= ~(1u << (b & 31));
                                 if (pb < 0) { sl.ra[a] -= delta; break; }
-                                sl.flow[(size_t)a * FS + pb] -= delta;
+                                const double back = sl.flow[(size_t)a * FS + pb] - delta;      // parA[a] = pb was taken from fpos: the cell is live
+                                sl.flow[(size_t)a * FS + pb] = back;
+                                if (!(back > FLOW_TOL)) sl.fpos[(size_t)a * HW + (pb >> 5)] &= ~(1u << (pb & 31));
                                 b = pb;
                             }
                         }
@@ -462,7 +469,7 @@ size_t bigtree_warp_bytes(int max_splits, int W, int n_taxa)
 {
     const size_t S = (size_t)((std::max(max_splits, 1) + 31) / 32 * 32), HW = S / 32, FS = S | 1, tp = (size_t)((n_taxa + 63) / 64 * 64);
     auto up = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return 2 * up(S * W * 8) + 8 * up(S * 8) + 2 * up(S * 4) + 2 * up(S * HW * 4) + up((S + 2) * 2 * HW * 4) + up(S * FS * 8) + 2 * up(tp * 8) + 64;
+    return 2 * up(S * W * 8) + 8 * up(S * 8) + 2 * up(S * 4) + 3 * up(S * HW * 4) + up((S + 2) * 2 * HW * 4) + up(S * FS * 8) + 2 * up(tp * 8) + 64;
 }
 
 int bigtree_max_splits() { return 32 * (kSetWords / 2); }
