@@ -353,17 +353,19 @@ __device__ __forceinline__ double gtp_noncommon(WarpSmem<H, W> &sm, double *flow
 #pragma unroll
                     for (int h = 0; h < H; h++) {
                         if (!(x > FLOW_TOL) || nbm.w[h] == 0) continue;       // warp-uniform
-                        const double avail = ((nbm.w[h] >> lane) & 1u) ? rb[h] : 0.0;
-                        double incl = avail;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const double t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
-                        const double tot = __shfl_sync(FULL, incl, 31);
-                        const double take = fmin(avail, fmax(0.0, x - (incl - avail)));
-                        if (take > 0.0) { rb[h] -= take; flow[a * FS + lane + 32 * h] = take; }
-                        const uint32_t carries = __ballot_sync(FULL, take > FLOW_TOL);
+                        // the neighbours that still have sink capacity take x one after the other, in split order, until it is used up
+                        // (a source is mostly absorbed by its first one or two; the former warp scan over all 32 lanes: config 5 35.7 ms, this form 31.5)
+                        uint32_t live = __ballot_sync(FULL, ((nbm.w[h] >> lane) & 1u) && rb[h] > 0.0);
+                        bool carry = false;
+                        while (live && x > 0.0) {
+                            const int src = __ffs(live) - 1; live &= live - 1;
+                            const double take = fmin(__shfl_sync(FULL, rb[h], src), x);
+                            if (lane == src) { rb[h] -= take; flow[a * FS + lane + 32 * h] = take; carry = take > FLOW_TOL; }
+                            x -= take;
+                        }
+                        const uint32_t carries = __ballot_sync(FULL, carry);
 #pragma unroll
                         for (int ha = 0; ha < H; ha++) if ((a >> 5) == ha && lane == (a & 31)) fpos[ha].w[h] = carries;
-                        x = fmax(0.0, x - tot);
                     }
                     owner_store<H>(ra, a, lane, x);
                 }
