@@ -211,7 +211,7 @@ inline cudaError_t pick_block_warps(Kernel k, size_t warp_bytes, int &warps, int
     if (warp_bytes > 225 * 1024) return cudaSuccess;          // does not fit: 0 warps
     int first = GEO_WARPS;
     while (first > 1 && warp_bytes * first > 200 * 1024) first >>= 1;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * first));
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     for (int w = first; w >= 1; w >>= 1) {

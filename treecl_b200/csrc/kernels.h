@@ -2,11 +2,37 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include <cstdint>
 
 #include "td_internal.h"
 
 namespace td {
+
+// Opt a kernel in to the device's full dynamic shared memory, once per (kernel, device).  Every launcher calls this instead of setting the
+// attribute to its own launch's size: the attribute belongs to the function, not to the launch, so two host threads launching the same
+// kernel for sets of different sizes could shrink it under each other's feet ("invalid argument" at launch).
+inline cudaError_t allow_full_smem(const void *kernel)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> guard(mu);
+    if (done.count({kernel, dev})) return cudaSuccess;
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+    int optin = 0;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
+    done.insert({kernel, dev});
+    return cudaSuccess;
+}
+
 
 struct PairParams {
     const double *leafT;      // [n_k][ldT] taxon-major leaf-edge lengths (zero padded)

@@ -302,7 +302,7 @@ cudaError_t launch_gen_as(const GeoParams &p, const GeoPlan &plan, cudaStream_t 
 {
     auto k = general_kernel<H, W, GEO>;
     if ((plan.scratch_bytes != 0) != (p.flow_scratch != nullptr)) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     k<<<(unsigned)plan.blocks, plan.warps * 32, plan.smem, st>>>(p);
     return cudaGetLastError();

@@ -388,7 +388,7 @@ cudaError_t launch_rf_incidence(const void *tmap, const void *tmap_half, const i
         const int64_t T = p.tiles - p.tile_row0, pair_rows = ((row_end + TILE - 1) / TILE - p.tile_row0 + 1) / 2;
         const int64_t clusters = pair_rows * T - pair_rows * (pair_rows - 1);
         if (clusters <= 0) return cudaSuccess;
-        cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = allow_full_smem((const void *)rf_incidence_kernel<true>);
         if (e != cudaSuccess) return e;
         rf_incidence_kernel<true><<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
         return cudaGetLastError();
@@ -397,7 +397,7 @@ cudaError_t launch_rf_incidence(const void *tmap, const void *tmap_half, const i
     const int64_t L0 = p.tiles - p.tile_row0;
     const int64_t clusters = pair_prefix(L0, tile_rows);
     if (clusters <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(rf_incidence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_full_smem((const void *)rf_incidence_kernel<false>);
     if (e != cudaSuccess) return e;
     rf_incidence_kernel<false><<<(unsigned)(2 * clusters), NTHREADS, smem, st>>>(map, map_half, p);
     return cudaGetLastError();

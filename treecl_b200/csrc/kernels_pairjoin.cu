@@ -700,7 +700,7 @@ template <uint32_t MASK, bool RECT>
 cudaError_t launch_one_persistent(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
     auto k = p.normalise ? pairjoin_persistent<MASK, RECT, true> : pairjoin_persistent<MASK, RECT, false>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     k<<<grid, NTP, smem, st>>>(p);
     return cudaGetLastError();
@@ -725,7 +725,7 @@ template <uint32_t MASK, bool RECT>
 cudaError_t launch_one(const PairParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
     auto k = pairjoin_kernel<MASK, RECT>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     k<<<grid, NT, smem, st>>>(p);
     return cudaGetLastError();

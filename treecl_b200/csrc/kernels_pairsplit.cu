@@ -646,7 +646,7 @@ template <uint32_t MASK, bool RECT>
 cudaError_t launch_dense(const PairParams &p, dim3 grid, size_t smem, cudaStream_t st, bool pdl)
 {
     auto k = p.normalise ? pair_dense_kernel<MASK, RECT, true> : pair_dense_kernel<MASK, RECT, false>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     CUtensorMap ma, mb;
     if (p.tmap_a && p.tmap_b) { memcpy(&ma, p.tmap_a, sizeof ma); memcpy(&mb, p.tmap_b, sizeof mb); }
@@ -679,7 +679,7 @@ template <bool RECT>
 cudaError_t launch_events(int wmode, const PairParams &p, unsigned groups, unsigned parts, size_t smem, cudaStream_t st)
 {
     auto run = [&](auto k) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = allow_full_smem((const void *)k);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(groups * parts); cfg.blockDim = dim3(EVT); cfg.dynamicSmemBytes = smem; cfg.stream = st;

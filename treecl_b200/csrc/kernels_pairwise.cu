@@ -216,7 +216,7 @@ template <uint32_t MASK, int TILE, bool RECT>
 cudaError_t launch_one(const PairParams &p, dim3 grid, size_t smem, cudaStream_t st)
 {
     auto k = pairwise_kernel<MASK, TILE, RECT>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_full_smem((const void *)k);
     if (e != cudaSuccess) return e;
     k<<<grid, (TILE / 4) * (TILE / 4), smem, st>>>(p);
     return cudaGetLastError();
