@@ -379,6 +379,36 @@ def test_first_rf_only_calls_race_on_two_streams(td, oracle_mod):
         ts.close()
 
 
+def test_host_threads_with_sets_of_different_sizes(td):
+    """Host threads running the same kernels for sets of different sizes at the same time: the dynamic shared memory a kernel may use
+    is a property of the function, not of a launch - it is opted in once per kernel (allow_full_smem), not resized by every launch."""
+    import threading
+    from treecl_b200 import _lib
+    cases = [(400, 12), (300, 40), (250, 64), (120, 100)]
+    sets = [_lib.TreeSet(make('uniform', n, taxa, seed=40 + taxa)) for n, taxa in cases]
+    metrics = ('rf', 'wrf', 'euc', 'geo')
+    want = [ts.pairwise(metrics) for ts in sets]
+    errors = []
+    go = threading.Barrier(len(sets))
+
+    def work(k):
+        try:
+            go.wait()
+            for _ in range(6):
+                got = sets[k].pairwise(metrics)
+                for m in metrics:
+                    assert np.array_equal(got[m], want[k][m]), (cases[k], m)
+        except Exception as exc:                       # noqa: BLE001 - reported below, in the main thread
+            errors.append(exc)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(sets))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
 def test_polytomies_and_rooted_trees(td, oracle_mod):
     """UNPINNED by the reference (no golden): extended common-edge rule and clade (rooted) mode, oracle vs CUDA."""
     from treecl_b200 import _lib
