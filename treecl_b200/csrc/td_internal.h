@@ -69,6 +69,9 @@ const char *last_error();
 
 // host_encoder.cpp
 int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, HostSet &hs);
+// dst[0, bytes) = src[0, bytes), then dst[bytes, bytes + pad_bytes) = pad_value; all jobs spread over the encoder's worker pool
+struct CopyJob { void *dst; const void *src; size_t bytes, pad_bytes; int pad_value; };
+void parallel_copy(const std::vector<CopyJob> &jobs);
 int encode_kendall_colijn(const char *const *newick, int64_t n_trees, double lambda, int n_threads, HostSet &hs);
 int newick_labels(const char *newick, std::vector<std::string> &labels, int &rooted);
 int newick_prune(const char *newick, const std::vector<std::string> &keep, std::string &out);
