@@ -543,9 +543,11 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     }
     hs.max_splits = smax; hs.uniform = uniform; hs.rooted = enc[0].rooted; hs.total_splits = total;
     const size_t stride = (size_t)std::max(smax, 1);
-    hs.masks.assign((size_t)N * stride * W, 0); hs.lens.assign((size_t)N * stride, 0.0);
-    hs.ids.assign((size_t)N * stride, kSentinelId);
+    // (uninitialised: every row is written in full, padding included, by the parallel `lists` pass below)
+    hs.masks.resize((size_t)N * stride * W); hs.lens.resize((size_t)N * stride);
+    hs.ids.resize((size_t)N * stride);
     hs.leaflen.resize((size_t)N * std::max(n_taxa, 1));
+    if (n_taxa == 0) std::fill(hs.leaflen.begin(), hs.leaflen.end(), 0.0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
         memcpy(&hs.leaflen[(size_t)i * n_taxa], enc[i].leaflen.data(), (size_t)n_taxa * 8);
     });
@@ -684,8 +686,8 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     hs.n_shared.assign(nsh.begin(), nsh.end()); hs.max_shared = shmax;
     for (int64_t b = 0; b < N; b += kTile) { int tot = 0; for (int64_t i = b; i < std::min<int64_t>(N, b + kTile); i++) tot += nsh[i]; hs.max_tile_entries = std::max(hs.max_tile_entries, tot); }
     hs.sh_stride = ((shmax + 1) + 1) & ~1;                   // >= one sentinel, even -> 32-byte rows
-    hs.shared.assign((size_t)N * hs.sh_stride, SplitRec{kSentinelId, 0, 0.0});
-    hs.shared_x.assign((size_t)N * hs.sh_stride, -1);
+    hs.shared.resize((size_t)N * hs.sh_stride);            // (rows written in full below: entries, then sentinels)
+    hs.shared_x.resize((size_t)N * hs.sh_stride);
     hs.q2t.assign(N, 0.0); hs.q1_light.assign(N, 0.0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
         const int S = hs.n_splits[i];
@@ -705,6 +707,11 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             if (mult_of[at] >= 2) { hs.shared_x[(size_t)i * hs.sh_stride + sh] = (int32_t)x_of[at]; hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len}; }
             else { s1 += std::fabs(len); s2 += len * len; }
         }
+        for (size_t k = (size_t)S; k < stride; k++) {                                  // padding of the full lists
+            for (int w = 0; w < W; w++) hs.masks[((size_t)i * stride + k) * W + w] = 0;
+            hs.lens[(size_t)i * stride + k] = 0.0; hs.ids[(size_t)i * stride + k] = kSentinelId;
+        }
+        for (int k = sh; k < hs.sh_stride; k++) { hs.shared[(size_t)i * hs.sh_stride + k] = SplitRec{kSentinelId, 0, 0.0}; hs.shared_x[(size_t)i * hs.sh_stride + k] = -1; }
         hs.single_l1[i] = s1; hs.single_l2[i] = s2; hs.q1[i] = t1; hs.q2[i] = t2; hs.q1_light[i] = h1;
         double sl = 0.0;
         for (int k = 0; k < n_taxa; k++) { const double l = hs.leaflen[(size_t)i * n_taxa + k]; sl += l * l; }
@@ -879,13 +886,13 @@ struct Writer {
     std::vector<unsigned char> *out; size_t size = 0;         // out == nullptr: only measure
     void raw(const void *p, size_t n) { if (out) { const unsigned char *b = (const unsigned char *)p; out->insert(out->end(), b, b + n); } size += n; }
     template <class T> void pod(const T &v) { raw(&v, sizeof v); }
-    template <class T> void vec(const std::vector<T> &v) { const uint64_t n = v.size(); pod(n); raw(v.data(), n * sizeof(T)); const uint64_t pad = (8 - (n * sizeof(T)) % 8) % 8, z = 0; raw(&z, pad); }
+    template <class T, class A> void vec(const std::vector<T, A> &v) { const uint64_t n = v.size(); pod(n); raw(v.data(), n * sizeof(T)); const uint64_t pad = (8 - (n * sizeof(T)) % 8) % 8, z = 0; raw(&z, pad); }
 };
 struct Reader {
     const unsigned char *p, *end; bool ok = true;
     void raw(void *dst, size_t n) { if (!ok || (size_t)(end - p) < n) { ok = false; return; } memcpy(dst, p, n); p += n; }
     template <class T> void pod(T &v) { raw(&v, sizeof v); }
-    template <class T> void vec(std::vector<T> &v)
+    template <class T, class A> void vec(std::vector<T, A> &v)
     {
         uint64_t n = 0; pod(n);
         if (!ok || n > (uint64_t)(end - p) / sizeof(T)) { ok = false; return; }

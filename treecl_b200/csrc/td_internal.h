@@ -3,6 +3,10 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <memory>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/treedist_cuda.h"
@@ -19,6 +23,18 @@ struct SplitRec {
     double len;
 };
 static_assert(sizeof(SplitRec) == 16, "SplitRec must be 16 bytes");
+
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big arrays of a set are written in full by the
+// encoder's workers (first touch in parallel) instead of being zero-filled by one thread first (7 MB, ~1 ms of the bench set's encode)
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    default_init_allocator() = default;
+    template <class U> default_init_allocator(const default_init_allocator<U> &) noexcept {}
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 struct HostSet {
     int64_t N = 0;
@@ -46,15 +62,15 @@ struct HostSet {
     double mean_common = 0.0;                  // expected number of common splits of a random pair of the set
 
     // full lists, rows sorted by split id (uniform sets) or by mask (otherwise); stride max_splits
-    std::vector<uint64_t> masks;               // [N][max_splits][W]
-    std::vector<double> lens;                  // [N][max_splits]
-    std::vector<uint32_t> ids;                 // [N][max_splits], kSentinelId padded (uniform sets only)
-    std::vector<double> leaflen;               // [N][n_taxa]
+    raw_vector<uint64_t> masks;                // [N][max_splits][W]
+    raw_vector<double> lens;                   // [N][max_splits]
+    raw_vector<uint32_t> ids;                  // [N][max_splits], kSentinelId padded (uniform sets only)
+    raw_vector<double> leaflen;                // [N][n_taxa]
 
     // shared-split lists (splits that occur in >= 2 trees), sentinel padded, stride sh_stride
     int32_t sh_stride = 0;
-    std::vector<SplitRec> shared;              // [N][sh_stride]
-    std::vector<int32_t> shared_x;             // [N][sh_stride] position of the entry in the postings, -1 = none
+    raw_vector<SplitRec> shared;               // [N][sh_stride]
+    raw_vector<int32_t> shared_x;              // [N][sh_stride] position of the entry in the postings, -1 = none
 
     // postings of the shared splits: entries grouped by split, trees ascending inside a group.  post_end[x] is the end of x's
     // group, so "all later holders of the split of entry x" is the range (x, post_end[x]).
