@@ -261,8 +261,9 @@ __global__ void __launch_bounds__(GEO_WARPS * 32, GEO ? 1 : GEN_MINB) general_ke
             setA.w[h] = __ballot_sync(FULL, ncA);
         }
         const int rf = setA.count() + setB.count(), rf_den = validA.count() + validB.count();
-        l1 = warp_sum(l1); l2 = warp_sum(l2); c1 = warp_sum(c1); c2 = warp_sum(c2); o1 = warp_sum(o1); o2 = warp_sum(o2);
-        sumA = warp_sum(sumA); sumB = warp_sum(sumB); sqA = warp_sum(sqA); sqB = warp_sum(sqB);
+        // only the sums the requested metrics read (ten warp reductions were a tenth of the kernel's instructions)
+        if (p.metric_mask & 2u) { l1 = warp_sum(l1); c1 = warp_sum(c1); o1 = warp_sum(o1); if (p.normalise) { sumA = warp_sum(sumA); sumB = warp_sum(sumB); } }
+        if (p.metric_mask & 12u) { l2 = warp_sum(l2); c2 = warp_sum(c2); o2 = warp_sum(o2); if (p.normalise) { sqA = warp_sum(sqA); sqB = warp_sum(sqB); } }
 
         double geo2 = 0.0;
         if constexpr (GEO) {
