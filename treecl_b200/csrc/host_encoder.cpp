@@ -580,7 +580,9 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     // per (tree, slot): dictionary id, multiplicity, compact shared index, position in the postings.  Only slots < n_splits are ever
     // written or read, so the arrays are left uninitialised (a serial fill of four of them and of the two entry tables cost ~1.5 ms)
     const size_t n_slots = (size_t)N * stride;
-    std::unique_ptr<uint32_t[]> id_of(new uint32_t[n_slots]), mult_of(new uint32_t[n_slots]), sid_of(new uint32_t[n_slots]), x_of(new uint32_t[n_slots]);
+    // (one 16-byte record per slot: the dictionary pass writes them in hash order, i.e. at random - one cache line per entry, not four)
+    struct SlotInfo { uint32_t id, mult, sid, x; };
+    std::unique_ptr<SlotInfo[]> slot_of(new SlotInfo[n_slots]);
     if (total > 0) {
         std::vector<int64_t> off(N + 1, 0);
         for (int64_t i = 0; i < N; i++) off[i + 1] = off[i] + hs.n_splits[i];
@@ -684,9 +686,10 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
                 const int64_t x_end = x + (run - it);
                 for (auto k = it; k != run; k++) {
                     const size_t at = (size_t)k->tree * stride + k->slot;
-                    id_of[at] = (uint32_t)id; mult_of[at] = (uint32_t)(run - it);
+                    SlotInfo &si = slot_of[at];
+                    si.id = (uint32_t)id; si.mult = (uint32_t)(run - it);
                     if (is_shared) {
-                        sid_of[at] = sid_rank[(size_t)sid]; x_of[at] = (uint32_t)x;
+                        si.sid = sid_rank[(size_t)sid]; si.x = (uint32_t)x;
                         hs.post_tree[x] = (int32_t)k->tree; hs.post_end[x] = (int32_t)x_end; hs.post_len[x] = enc[k->tree].lens[k->slot];
                         x++;
                     }
@@ -701,7 +704,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
     std::vector<int32_t> nsh(N, 0);
     parallel_for(N, n_threads, [&](int64_t i, int) {
         int sh = 0;
-        for (int s = 0; s < hs.n_splits[i]; s++) sh += mult_of[(size_t)i * stride + s] >= 2;
+        for (int s = 0; s < hs.n_splits[i]; s++) sh += slot_of[(size_t)i * stride + s].mult >= 2;
         nsh[i] = sh;
     });
     int shmax = 0; for (int64_t i = 0; i < N; i++) shmax = std::max(shmax, nsh[i]);
@@ -715,7 +718,7 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         const int S = hs.n_splits[i];
         std::vector<int> perm(S);
         for (int s = 0; s < S; s++) perm[s] = s;
-        std::sort(perm.begin(), perm.end(), [&](int a, int b) { return id_of[(size_t)i * stride + a] < id_of[(size_t)i * stride + b]; });
+        std::sort(perm.begin(), perm.end(), [&](int a, int b) { return slot_of[(size_t)i * stride + a].id < slot_of[(size_t)i * stride + b].id; });
         int sh = 0; double s1 = 0, s2 = 0, t1 = 0, t2 = 0, h1 = 0;
         for (int k = 0; k < S; k++) {
             const int s = perm[k];
@@ -723,10 +726,11 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
             const double len = enc[i].lens[s];
             memcpy(&hs.masks[((size_t)i * stride + k) * W], &enc[i].masks[(size_t)s * W], W * 8);
             hs.lens[(size_t)i * stride + k] = len;
-            hs.ids[(size_t)i * stride + k] = id_of[at];
+            const SlotInfo &si = slot_of[at];
+            hs.ids[(size_t)i * stride + k] = si.id;
             t1 += std::fabs(len); t2 += len * len;
-            if (!(mult_of[at] >= 2 && (int)sid_of[at] < hs.heavy_rows)) h1 += std::fabs(len);      // everything but the heavy splits
-            if (mult_of[at] >= 2) { hs.shared_x[(size_t)i * hs.sh_stride + sh] = (int32_t)x_of[at]; hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{id_of[at], sid_of[at], len}; }
+            if (!(si.mult >= 2 && (int)si.sid < hs.heavy_rows)) h1 += std::fabs(len);      // everything but the heavy splits
+            if (si.mult >= 2) { hs.shared_x[(size_t)i * hs.sh_stride + sh] = (int32_t)si.x; hs.shared[(size_t)i * hs.sh_stride + sh++] = SplitRec{si.id, si.sid, len}; }
             else { s1 += std::fabs(len); s2 += len * len; }
         }
         for (size_t k = (size_t)S; k < stride; k++) {                                  // padding of the full lists
