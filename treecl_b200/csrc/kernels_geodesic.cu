@@ -3,14 +3,16 @@
 // Replaces getGeodesicDistance(t1.phylotree, t2.phylotree, normalise) of treeCl/treedist.py:70,112 (arithmetic in
 // the un-vendored PyPI package tree_distance, a C++ port of M. Owen's GTP) for every pair of the condensed matrix.
 //
-// Per pair, entirely inside one warp (registers + shared memory, no global scratch):
+// Per pair, entirely inside one warp (registers + shared memory; the flow matrix in a per-warp slice of global memory when shared
+// memory would limit residency, GeoPlan):
 //   1. leaf term            sum_k (a_k - b_k)^2, lanes strided over taxa
 //   2. common splits        binary search of each tree's sorted split ids in the other's  -> sum (li - lj)^2
 //   3. incompatibility      bit matrix inc[a] (over the other tree's non-common splits), one row per lane
 //   4. extended common rule splits compatible with every split of the other tree contribute l^2
 //   5. GTP                  explicit stack of ratios (A-subset, B-subset bitmasks); for each ratio a min-weight
 //                           vertex cover by max-flow: greedy saturation + BFS augmenting paths with the frontier
-//                           sets as warp-uniform bitmasks and the fp64 flow matrix in shared memory
+//                           sets as warp-uniform bitmasks; every lane keeps the bit row of its split's flow-carrying edges,
+//                           so the fp64 flow matrix is touched only along the paths (geo_core.cuh)
 //   distance^2 = sum_k (||A_k|| + ||B_k||)^2 + common + extended common + leaf
 // The lane that owns split s of tree i (s = lane + 32 h) keeps its id / length / mask / residual capacity in
 // registers; H = CAP / 32 splits per lane per tree.
