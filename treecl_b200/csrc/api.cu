@@ -478,7 +478,7 @@ static size_t split_event_bytes(const DeviceSet *d, int64_t capacity, int rec)
 {
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t groups = (size_t)d->Npad / pairsplit_row_group(), col_tiles = ((size_t)d->N + 31) / 32;
-    return 256 + up(groups * col_tiles * sizeof(uint2)) + up((size_t)capacity * rec);
+    return 256 + up(groups * sizeof(unsigned)) + up(groups * col_tiles * sizeof(uint2)) + up((size_t)capacity * rec);
 }
 
 static bool rf_incidence_fits(const HostSet &h);
@@ -515,6 +515,8 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
     const size_t groups = (size_t)d->Npad / pairsplit_row_group(), col_tiles = ((size_t)d->N + 31) / 32;
     unsigned char *b = d->ev_block;
     p.ev_cursor = (uint32_t *)b; b += 256;
+    unsigned *ready = (unsigned *)b; b += up(groups * sizeof(unsigned));          // (cleared together with the cursor)
+    p.ready = ready; p.ready_target = 0;                     // (launch_pairsplit decides whether the launch set uses them)
     p.seg = (uint2 *)b; b += up(groups * col_tiles * sizeof(uint2));
     p.ev = b;
     p.ev_capacity = (uint32_t)capacity;
@@ -548,7 +550,7 @@ static int run_pairsplit(td_treeset *ts, DeviceSet *d, uint32_t m3, bool rect, P
     int launches = 0;
     if (mk) {
     CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done, 0));
-    CUDA_TRY(cudaMemsetAsync(p.ev_cursor, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(p.ev_cursor, 0, 256 + up(groups * sizeof(unsigned)), st));
     unsigned long long *trace = nullptr;
     const char *trace_path = getenv("TREEDIST_TRACE");      // debug aid, only honoured by builds with -DPS_TRACE
     if (trace_path) { CUDA_TRY(cudaMalloc(&trace, (size_t)tiles * 64)); CUDA_TRY(cudaMemsetAsync(trace, 0, (size_t)tiles * 64, st)); p.trace = trace; }

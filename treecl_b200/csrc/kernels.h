@@ -59,6 +59,9 @@ struct PairParams {
     const int32_t *shared_x;  // [Npad][sh_stride] position of every shared-list entry in the postings (-1: none)
     uint2 *seg;               // [Npad / 16][col_tiles_total] (offset, count) of the events of (row group, column tile)
     uint32_t *ev_cursor;      // next free record of the event buffer
+    // per tile row (four row groups): CTAs of the events kernel that have finished their share of it (zeroed before the launch).  Set: a
+    // tile waits for its tile row to reach ready_target instead of for the whole events grid; nullptr: grid-wide dependency
+    unsigned *ready; unsigned ready_target;
     int col_tiles_total, rg0; // ceil(N / 32); first row group of this launch
     uint32_t ev_capacity;
     unsigned long long *trace;   // debug builds (-DPS_TRACE): 8 clock stamps per tile

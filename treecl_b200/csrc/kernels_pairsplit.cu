@@ -132,6 +132,7 @@ __device__ __forceinline__ FixScale fix_scale(double q)
 // kernel has completed and its segment table and records are visible.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l = 4 g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -311,6 +312,12 @@ __global__ void __launch_bounds__(EVT) pair_events_kernel(const __grid_constant_
             for (int u = 0; u < EVW; u++) emit(e0 + u, j[u], lb[u]);
         }
     }
+    // this CTA's share of the row group is written (segment table rows and records): tell the tiles that wait for the group
+    if (p.ready) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.ready + rg / (TR / RG), 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -384,6 +391,8 @@ __global__ void __launch_bounds__(NT, min_blocks(MASK)) pair_dense_kernel(const 
     const int g = lane >> 2, t4 = lane & 3;            // DMMA fragment coordinates
     const int wr = warp >> 1, wc = warp & 1;           // warp tile: rows 16 wr .., columns 16 wc ..
     TRACE(0);
+    // with per-group ready counters nothing in a later tile launch of the same launch set depends on this one: let it in early
+    if (kWeighted && p.ready) griddep_launch_dependents();
 
     // ---- leaf-length chunks: two TMA requests per chunk (rows of A, rows of B), issued by one thread ------------------------------------
     const int k_used = kWeighted ? (p.k_rows + 3) & ~3 : 0;                   // rows of the matrix behind the tensor maps (beyond: zeros)
@@ -407,6 +416,12 @@ __global__ void __launch_bounds__(NT, min_blocks(MASK)) pair_dense_kernel(const 
     for (int q = 0; q < TR / RG; q++) sg[q] = make_uint2(0u, 0u);
     auto load_segments = [&]() {
         if (!p.seg) return;                                // no table: no events
+        if (kWeighted && p.ready) {
+            // only the four row groups of this tile row have to be complete, not the whole events grid: every thread acquires the tile
+            // row's counter itself (its own later reads of the table and the records are then ordered behind the events kernel's writes)
+            const unsigned *f = p.ready + tile_r;
+            while (ld_acquire_gpu(f) < p.ready_target) __nanosleep(100);
+        } else
         griddep_wait();
         const uint2 *segp = p.seg + (size_t)(tile_r * (TR / RG)) * p.col_tiles_total + tile_c;
 #pragma unroll
@@ -799,6 +814,8 @@ static cudaError_t launch_tiles(uint32_t mask, bool rect, const PairParams &p, c
 cudaError_t launch_pairsplit_tiles(uint32_t mask, bool rect, const PairParams &p, cudaStream_t st) { return launch_tiles(mask, rect, p, st, false); }
 
 // p must carry the tile geometry (pairsplit_tiles), the postings, the segment table and the event buffer; *ev_cursor must be zero
+static bool no_pdl_env() { static const bool v = getenv("TREEDIST_NO_PDL") != nullptr; return v; }
+
 cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p_in, int n_sms, cudaStream_t st, int *launches, const PairParams *second)
 {
     *launches = 0;
@@ -832,17 +849,38 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p_in, i
         if (const char *f = getenv("TREEDIST_EVENT_PARTS")) parts = (unsigned)atoi(f);
         else while (parts < 8 && groups * parts * 2 <= 2ll * n_sms) parts *= 2;
         if (parts != 1 && parts != 2 && parts != 4 && parts != 8) parts = 1;
+        // Per-tile-row ready counters instead of the grid-wide dependency, for launch sets with two row blocks (multi-GPU folded blocks):
+        // the tiles of the short-row block, launched first, run while the long rows' events are still being written.  Config 3 as 8
+        // ranks, per rank on one GPU: 0.727 -> 0.69-0.72 ms (4 ranks 1.413 -> 1.390, 2 ranks 2.760 -> 2.725); a single block gains
+        // nothing (0.1396 vs 0.1393 ms on the bench set) and keeps the plain dependency.
+        {
+            static const char *force = getenv("TREEDIST_READY_FLAGS");           // "0" / "1": experiments
+            bool use = second && weighted && !rect && !no_pdl_env() && !sync_debug;
+            if (force && *force) use = *force != '0' && weighted && !no_pdl_env() && !sync_debug;
+            if (!use) p.ready = nullptr;
+        }
+        p.ready_target = parts * (TR / RG);
         e = checked(rect ? launch_events<true>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st) : launch_events<false>(wmode_of(mask), p, (unsigned)groups, parts, smem_e, st), "pair_events_kernel");
         ++*launches;
         if (e != cudaSuccess) return e;
     }
-    static const bool no_pdl = getenv("TREEDIST_NO_PDL") != nullptr;
-    e = checked(launch_tiles(mask, rect, p, st, !no_pdl && !sync_debug), "pair_dense_kernel");
+    const bool pdl = !no_pdl_env() && !sync_debug;
+    PairParams sb{};
+    if (second) { sb = *second; sb.ready = p.ready; sb.ready_target = p.ready_target; }
+    // With ready counters the SHORT-row block goes first: its row groups finish early in the events kernel and its tiles run while the
+    // long rows' events are still being written; block A's tiles follow under its tail.
+    const bool b_first = second && weighted && p.ready;
+    if (b_first) {
+        e = checked(launch_tiles(mask, rect, sb, st, pdl), "pair_dense_kernel (second block, first)");
+        ++*launches;
+        if (e != cudaSuccess) return e;
+    }
+    e = checked(launch_tiles(mask, rect, p, st, pdl), "pair_dense_kernel");
     ++*launches;
     if (e != cudaSuccess) return e;
-    if (second) {
+    if (second && !b_first) {
         // block B's tiles: a launch of its own geometry reading the same segment table and records; it may start under block A's tail
-        e = checked(launch_tiles(mask, rect, *second, st, !no_pdl && !sync_debug), "pair_dense_kernel (second block)");
+        e = checked(launch_tiles(mask, rect, sb, st, pdl), "pair_dense_kernel (second block)");
         ++*launches;
         if (e != cudaSuccess) return e;
     }
