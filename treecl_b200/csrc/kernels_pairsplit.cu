@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -847,7 +848,20 @@ cudaError_t launch_pairsplit(uint32_t mask, bool rect, const PairParams &p_in, i
         // row blocks: 76 - 106 groups) splits its groups until one wave of 2 CTAs per SM is full
         unsigned parts = 1;
         if (const char *f = getenv("TREEDIST_EVENT_PARTS")) parts = (unsigned)atoi(f);
-        else while (parts < 8 && groups * parts * 2 <= 2ll * n_sms) parts *= 2;
+        else {
+            while (parts < 8 && groups * parts * 2 <= 2ll * n_sms) parts *= 2;
+            // One block that is a share of the rows (the middle rank of a multi-GPU fold; the other ranks have a long-row and a short-row
+            // block and hide the events kernel behind the short block's tiles, see the ready counters below): the events kernel has to be
+            // short itself.  It is bound by per-SM throughput - the SMs that host two of e.g. 156 CTAs set its time - so the row groups
+            // are split into 1, 2 or 4 CTAs, whichever spreads most evenly over the SMs (83 -> 68 us; that rank's share 0.729 -> 0.709 ms).
+            if (!second && !rect && parts < 4 && (p.row_end - p.row_begin) * 2 < p.N) {
+                double best = 1e30;
+                for (unsigned c = 1; c <= 4; c *= 2) {
+                    const double per_sm = (double)(groups * c) / (double)n_sms, waste = std::ceil(per_sm) / per_sm * (1.0 + 0.02 * (c - 1));
+                    if (waste < best) { best = waste; parts = c; }
+                }
+            }
+        }
         if (parts != 1 && parts != 2 && parts != 4 && parts != 8) parts = 1;
         // Per-tile-row ready counters instead of the grid-wide dependency, for launch sets with two row blocks (multi-GPU folded blocks):
         // the tiles of the short-row block, launched first, run while the long rows' events are still being written.  Config 3 as 8
