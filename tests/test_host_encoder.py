@@ -312,3 +312,25 @@ def test_heavy_rows_follow_the_sharing_level(lib_built):
     assert dense.mean_common > 10.0
     assert 0 < dense.heavy_rows <= dense.dict_shared
     assert 0.9 * dense.mean_common <= dense.heavy_common <= dense.mean_common + 1e-9
+
+
+def test_encoding_does_not_depend_on_the_thread_count(lib_built):
+    """The encoder's workers write the big arrays of a set in full, padding included (raw_vector: nothing is zero-filled first), and the
+    dictionary is built from hash buckets filled in parallel: the serialised set must be the same bytes for any number of threads, for
+    uniform, clustered and non-uniform sets and for Kendall-Colijn vectors."""
+    import treecl_b200 as td
+    from treecl_b200 import _lib, synth
+    uniform = synth.uniform_trees(300, 40, seed=3)
+    clustered = synth.structured_trees(300, 70, n_classes=4, class_nni=6, lam=2.0, seed=4)
+    labels = synth.taxon_labels(40)
+    rng = np.random.default_rng(5)
+    odd = [td.Tree(t).prune_to_subset({labels[i] for i in rng.choice(40, size=int(rng.integers(20, 41)), replace=False)}).newick if k % 3 else t
+           for k, t in enumerate(uniform[:120])]
+    for trees in (uniform, clustered, odd):
+        blobs = [_lib.TreeSet(trees, n_threads=nt).serialize() for nt in (1, 2, 5, 8)]
+        for b in blobs[1:]:
+            assert b.size == blobs[0].size and np.array_equal(b, blobs[0])
+        back = _lib.TreeSet.deserialize(blobs[0]).serialize()
+        assert np.array_equal(back, blobs[0])
+    kc = [_lib.TreeSet.kendall_colijn(uniform[:80], lbda=0.3, n_threads=nt).serialize() for nt in (1, 6)]
+    assert np.array_equal(kc[0], kc[1])
