@@ -1701,6 +1701,7 @@ int td_check_errors(td_treeset *ts, int device)
 
 int td_trim_cache(int device)
 {
+    encoder_trim();
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return TD_OK; }      // no GPU: nothing is cached
     DeviceScope scope;

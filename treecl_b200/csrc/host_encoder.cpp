@@ -450,6 +450,19 @@ static void parallel_for(int64_t n, int n_threads, F &&fn)
 static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::string> &labels, int n_threads, HostSet &hs,
                          const std::function<void(const char *)> &lap);
 
+// The per-tree scratch of the last encode (four small vectors per tree) is kept for the next one when it is small: an application that
+// encodes one set after another (bootstrap replicates, simulations, the bench's end-to-end loop) then neither allocates nor frees 20,000
+// vectors per call.  At most kSpareBytes are kept; td_trim_cache() drops them.
+constexpr size_t kSpareBytes = 64u << 20;
+static std::mutex g_spare_mu;
+static std::vector<TreeEnc> g_spare;
+
+void encoder_trim()
+{
+    std::vector<TreeEnc> gone;
+    { std::lock_guard<std::mutex> g(g_spare_mu); gone.swap(g_spare); }
+}
+
 int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &hs)
 {
     if (N < 1 || !newick) { set_error("td_encode_newick: need at least one tree"); return TD_ERR_ARG; }
@@ -459,7 +472,9 @@ int encode_newick(const char *const *newick, int64_t N, int n_threads, HostSet &
     const bool timing = getenv("TREEDIST_TIMING") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (!timing) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[encode] %-12s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_last).count()); t_last = n; };
-    std::vector<TreeEnc> enc(N);
+    std::vector<TreeEnc> enc;
+    { std::lock_guard<std::mutex> g(g_spare_mu); enc.swap(g_spare); }
+    enc.resize(N);
     TaxonTable tab;
     std::atomic<int> status{TD_OK};
     std::mutex err_mu; std::string err_msg;
@@ -744,8 +759,15 @@ static int finish_encode(std::vector<TreeEnc> &enc, const std::vector<std::strin
         hs.q2t[i] = t2 + sl;
     });
     lap("lists");
-    // the per-tree vectors (four per tree) are released by the workers: left to the caller's single thread, 20,000 frees cost ~1 ms
-    parallel_for(N, n_threads, [&](int64_t i, int) { TreeEnc gone; std::swap(gone, enc[(size_t)i]); });
+    // the per-tree vectors (four per tree): kept for the next encode when small (see g_spare), else released by the workers - left to the
+    // caller's single thread, 20,000 frees cost ~1 ms
+    const size_t scratch_bytes = (size_t)N * (sizeof(TreeEnc) + (size_t)W * 8 + (size_t)n_taxa * 8) + (size_t)total * ((size_t)W * 8 + 8);
+    bool kept = false;
+    if (scratch_bytes <= kSpareBytes) {
+        std::lock_guard<std::mutex> g(g_spare_mu);
+        if (g_spare.empty()) { g_spare.swap(enc); kept = true; }
+    }
+    if (!kept) parallel_for(N, n_threads, [&](int64_t i, int) { TreeEnc gone; std::swap(gone, enc[(size_t)i]); });
     lap("release");
     return TD_OK;
 }

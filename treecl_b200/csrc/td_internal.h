@@ -85,6 +85,7 @@ const char *last_error();
 
 // host_encoder.cpp
 int encode_newick(const char *const *newick, int64_t n_trees, int n_threads, HostSet &hs);
+void encoder_trim();                       // drops the per-tree scratch kept between encodes
 // dst[0, bytes) = src[0, bytes), then dst[bytes, bytes + pad_bytes) = pad_value; all jobs spread over the encoder's worker pool
 struct CopyJob { void *dst; const void *src; size_t bytes, pad_bytes; int pad_value; };
 void parallel_copy(const std::vector<CopyJob> &jobs);
